@@ -1,0 +1,119 @@
+/*
+ * srt_b200.h — tier-B C ABI of libspleeterrt_b200.so: the batched, device-resident form of
+ * SpleeterRT's spectrogram-to-mask hot path on one B200 (sm_100a).
+ *
+ *   PCM -> STFT framer -> magnitude -> U-Net soft masks (n_stems nets) -> mask * spectrum
+ *       -> inverse STFT -> overlap-add -> stems
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types in any signature.  Every entry
+ * point returns 0 on success or a negative srt_status; srt_last_error() gives the text.
+ * There is no CPU fallback: without a working CUDA device every call fails loudly.
+ *
+ * What each entry point replaces in the reference (james34602/SpleeterRT):
+ *   srt_create            initSpleeter()  Executable/spleeter.c:111-172 (x n_stems, weights
+ *                         repacked for the tensor cores) + InitSTFT() stftFix.c:302-341 tables
+ *   srt_unet_host         processSpleeter()  Executable/spleeter.c:177-301, batched
+ *   srt_separate_batch    main.c:762-806 = channel_splitFloat framing + stft() + processMT()
+ *                         (main.c:444-541) + istft() + channel_joinFloat, for many streams and
+ *                         n_stems nets (the VST's "one net per stem", Spleeter4Stems.c:135)
+ *   srt_stft_host / srt_istft_host   stft()/istft()  Executable/stftFix.c:363-579
+ * The reference-compatible tier-A symbols (spleeter.h, stftFix.h) are thin shims over these.
+ */
+#ifndef SRT_B200_H
+#define SRT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRT_FFTSIZE 4096
+#define SRT_HOPSIZE 1024
+#define SRT_BINS 2049
+#define SRT_COEFF_FLOATS 9822725 /* sizeof(spleeterCoeff)/4, Executable/spleeter.h:5-31 */
+#define SRT_MAX_STEMS 8
+
+typedef enum {
+    SRT_OK = 0,
+    SRT_ERR_ARG = -1,      /* invalid argument (T/F not multiples of 64, too many stems, ...) */
+    SRT_ERR_CUDA = -2,     /* CUDA runtime / driver error, or no sm_100 device */
+    SRT_ERR_CAPACITY = -3, /* batch larger than the context was created for */
+    SRT_ERR_STATE = -4
+} srt_status;
+
+typedef struct srt_ctx srt_ctx;
+
+typedef struct {
+    int device;            /* CUDA device ordinal */
+    int n_stems;           /* nets evaluated per image, 0..SRT_MAX_STEMS (0 = transforms only) */
+    int time_step;         /* T: spectrogram frames per U-Net image (height), multiple of 64 */
+    int bin_limit;         /* F: frequency bins fed to the U-Net (width), multiple of 64, <= 2048 */
+    int max_images;        /* U-Net batch capacity: T-frame tiles evaluated per pass */
+    int max_batch_images;  /* tiles held per srt_separate_* call (>= max_images; 0 = max_images) */
+    int flavour;           /* 0 = Executable (LUT sigmoid, ELU clamp -15), 1 = VST (exact sigmoid) */
+    int conv_impl;         /* 0 = tcgen05 tensor-core kernels (the product), 1 = SIMT verification kernels */
+    void* cuda_stream;     /* optional cudaStream_t to enqueue on (NULL = context-owned stream) */
+} srt_config;
+
+/* coeffs[s]: one spleeterCoeff blob (SRT_COEFF_FLOATS floats, host memory) per stem;
+ * stem_modes[s]: 0 = LeakyReLU(0.2)/ReLU, !=0 = ELU/ELU (spleeter.c:130-139).
+ * The blobs are copied; they need not outlive the call. */
+int srt_create(const srt_config* cfg, const float* const* coeffs, const int* stem_modes, srt_ctx** out);
+void srt_destroy(srt_ctx* ctx);
+const char* srt_last_error(void);
+
+/* fp16 model blob (spleeterQuantized halves, Executable/spleeter.h:32-62) -> fp32 with
+ * denormals flushed to zero (f32Decompress, main.c:423-434).  Host side, exact. */
+void srt_half_to_float(const uint16_t* in, float* out, size_t n);
+
+/* ---- U-Net only -------------------------------------------------------------------------
+ * x: n_img images, each planar [2][T][F] like processSpleeter's input (host memory).
+ * y: [n_stems][n_img][2][T][F] masks (host memory).  n_img <= max_images. */
+int srt_unet_host(srt_ctx* ctx, const float* x, int n_img, float* y);
+/* device-resident variant: d_mag [n_img][T][F][2] (channel-interleaved), d_mask
+ * [n_stems][n_img][T][F][2]; pointers are device addresses on ctx's device. */
+int srt_unet_device(srt_ctx* ctx, const float* d_mag, int n_img, float* d_mask);
+
+/* ---- full path --------------------------------------------------------------------------
+ * n_streams stereo streams; stream i has n_samples[i] samples per channel (planar).
+ * stems_out[i * n_stems * 2 + s * 2 + c] receives stem s, channel c of stream i
+ * (n_samples[i] floats).  unaffected[s] scales the bins >= F (main.c:486-493; the VST uses
+ * 0.25 / 0.0, Spleeter4Stems.c:73,281); NULL = 0.1 for every stem (main.c:773).
+ * *_batch takes host pointers (copies inside), *_device takes device pointers. */
+int srt_separate_batch(srt_ctx* ctx, const float* const* pcmL, const float* const* pcmR,
+                       const size_t* n_samples, int n_streams, const float* unaffected,
+                       float* const* stems_out);
+int srt_separate_device(srt_ctx* ctx, const float* const* d_pcmL, const float* const* d_pcmR,
+                        const size_t* n_samples, int n_streams, const float* unaffected,
+                        float* const* d_stems_out);
+
+/* ---- transforms (Executable/stftFix.c) --------------------------------------------------
+ * srt_stft_host: rows = ceil(n/1024); planes are [rows][4096] host buffers supplied by the
+ * caller, zero-filled on return outside bins 0..2048 of the computed rows (stftFix.c:367-371).
+ * srt_istft_host: planes [frames][4096] -> outL/outR of frames*1024+3072 samples. */
+size_t srt_stft_rows(size_t n);
+int srt_stft_host(srt_ctx* ctx, const float* L, const float* R, size_t n,
+                  float* reL, float* imL, float* reR, float* imR);
+int srt_istft_host(srt_ctx* ctx, const float* reL, const float* imL, const float* reR, const float* imR,
+                   size_t frames, float* outL, float* outR);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+long long srt_launch_count(const srt_ctx* ctx);
+/* CUDA events on the context's stream around the most recent call's dominant kernel class:
+ * which = 0 tensor-core conv layers, 1 SIMT edge layers, 2 STFT, 3 iSTFT+OLA; returns ms. */
+int srt_last_timing(const srt_ctx* ctx, int which, float* ms_out);
+int srt_set_timing(srt_ctx* ctx, int enable);
+/* copy an internal activation tensor of the last U-Net pass to the host, converted to the
+ * reference's planar [stem][img][C][H][W] order.  name: "skip1".."skip6", "up1".."up6".
+ * Returns the number of floats written, or a negative status. */
+long long srt_debug_tensor(srt_ctx* ctx, const char* name, float* dst, size_t max_floats);
+/* pinned host memory helpers (so callers can hand page-locked buffers to *_batch) */
+void* srt_host_alloc(size_t bytes);
+void srt_host_free(void* p);
+int srt_synchronize(srt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

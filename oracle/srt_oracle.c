@@ -1,0 +1,518 @@
+/*
+ * srt_oracle.c — CPU restatement of SpleeterRT's spectrogram-to-mask hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity checker for the CUDA path; it is never
+ * linked into, imported by, or executed from the product (spleeterrt_b200/, include/,
+ * libspleeterrt_b200.so).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may touch anything under oracle/.
+ *
+ * Parity pin: the reference publishes no golden vectors, so this
+ * restatement is pinned against the reference's own C code compiled from
+ * /root/reference into oracle/_ref/ (oracle/build_ref.py) — see tests/test_oracle.py —
+ * and against the fixtures under tests/golden/ that were generated from that build
+ * (tests/golden/make_golden.py).
+ *
+ * Every function cites the reference file:line it follows.  The structure is deliberately
+ * NOT the reference's (no im2col buffer, no sgemm): convolutions are evaluated directly, but
+ * in the same accumulation order as the reference's naive gemm so results agree to the bit
+ * (modulo the compiler), which makes the pin sharp.
+ *
+ * All tensors are planar [channel][row][col] float32 exactly like the reference
+ * ("row" = time frame t, "col" = frequency bin f).
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define SRT_FFT 4096
+#define SRT_HOP 1024
+#define SRT_BINS 2049
+
+/* ------------------------------------------------------------------------------------
+ * Weight blob layout: one net = 9 822 725 floats in the order of `spleeterCoeff`
+ * (Executable/spleeter.h:5-31).  Offsets are derived, not copied.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+    const float *w, *b, *bn; /* bn: [0,C) offset, [C,2C) scale (Executable/spleeter.c:188) */
+    int cin, cout;
+} layer_t;
+
+typedef struct {
+    layer_t down[6];
+    layer_t up[6];
+    const float *w7, *b7;
+} net_t;
+
+static const int kEncCh[7] = {2, 16, 32, 64, 128, 256, 512};
+/* decoder: input channels (after concat) and output channels, Executable/spleeter.c:150-155 */
+static const int kDecIn[6] = {512, 512, 256, 128, 64, 32};
+static const int kDecOut[6] = {256, 128, 64, 32, 16, 1};
+
+size_t srt_oracle_coeff_floats(void)
+{
+    size_t n = 0;
+    for (int i = 0; i < 6; i++) {
+        n += (size_t)25 * kEncCh[i] * kEncCh[i + 1] + kEncCh[i + 1];
+        if (i < 5) n += 2 * kEncCh[i + 1]; /* down6 has no batch norm (spleeter.h:16) */
+    }
+    for (int i = 0; i < 6; i++) n += (size_t)25 * kDecIn[i] * kDecOut[i] + kDecOut[i] + 2 * kDecOut[i];
+    n += 4 * 4 * 1 * 2 + 2;
+    return n;
+}
+
+static void net_bind(net_t *n, const float *p)
+{
+    for (int i = 0; i < 6; i++) {
+        layer_t *l = &n->down[i];
+        l->cin = kEncCh[i];
+        l->cout = kEncCh[i + 1];
+        l->w = p; p += (size_t)25 * l->cin * l->cout;
+        l->b = p; p += l->cout;
+        if (i < 5) { l->bn = p; p += 2 * l->cout; } else l->bn = NULL;
+    }
+    for (int i = 0; i < 6; i++) {
+        layer_t *l = &n->up[i];
+        l->cin = kDecIn[i];
+        l->cout = kDecOut[i];
+        l->w = p; p += (size_t)25 * l->cin * l->cout;
+        l->b = p; p += l->cout;
+        l->bn = p; p += 2 * l->cout;
+    }
+    n->w7 = p; p += 32;
+    n->b7 = p;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Activations.  flavour 0 = Executable (LUT sigmoid spleeter.c:29-42, ELU clamp :51-56),
+ * flavour 1 = VST (exact logistic VST/Source/spleeter.c:56-65, unclamped ELU :74-77).
+ * ---------------------------------------------------------------------------------- */
+static float g_sig_tbl[1026];
+static int g_sig_ready = 0;
+
+/* The reference's table is sigma(-7 + i*14/1024) printed with 8 decimals, i = 0..1024,
+ * plus a final 1.0 (spleeter.c:29).  Regenerated here instead of copied; the pin test
+ * compares fastSigmoid() of oracle/_ref against srt_oracle_sigmoid_lut() on a dense grid. */
+static void sig_init(void)
+{
+    if (g_sig_ready) return;
+    for (int i = 0; i <= 1024; i++) {
+        double x = -7.0 + (double)i * (14.0 / 1024.0);
+        double s = 1.0 / (1.0 + exp(-x));
+        g_sig_tbl[i] = (float)(floor(s * 1e8 + 0.5) / 1e8);
+    }
+    g_sig_tbl[1025] = 1.0f;
+    g_sig_ready = 1;
+}
+
+const float *srt_oracle_sigmoid_table(void) { sig_init(); return g_sig_tbl; }
+
+float srt_oracle_sigmoid_lut(float x)
+{
+    const float step = 0.01367188f; /* spleeter.c:38 */
+    sig_init();
+    if (x > 7.0f) return 1.0f;
+    if (x < -7.0f) return 0.0f;
+    short idx = (short)((x + 7.0f) / step);
+    float x1 = -7.0f + step * idx;
+    return g_sig_tbl[idx] + (g_sig_tbl[idx + 1] - g_sig_tbl[idx]) / (-7.0f + step * (idx + 1) - x1) * (x - x1);
+}
+
+static float sigmoid_exact(float x)
+{
+    /* VST/Source/spleeter.c:56-65: numerically split logistic */
+    if (x >= 0.0f) return 1.0f / (1.0f + expf(-x));
+    float z = expf(x);
+    return z / (1.0f + z);
+}
+
+static inline float act_apply(int kind, float x)
+{
+    switch (kind) {
+    case 0: return x >= 0.0f ? x : 0.2f * x;                       /* leakyReLU spleeter.c:43-46 */
+    case 1: return x >= 0.0f ? x : 0.0f;                           /* ReLU      spleeter.c:47-50 */
+    case 2: if (x < -15.0f) return -1.0f;                          /* ELU exec  spleeter.c:51-56 */
+            return x >= 0.0f ? x : expf(x) - 1.0f;
+    default: return x >= 0.0f ? x : expf(x) - 1.0f;                /* ELU vst */
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * 5x5 stride-2 "SAME" convolution (processConv2dLayer spleeter.c:96-100 =
+ * im2col_dilated_cpu im2col_dilated.c:10-33 + gemm_nn gemm.c:6-18): input row 2h+kh-1,
+ * col 2w+kw-1, zero outside; fp32 accumulation in k = (c, kh, kw) ascending order.
+ * ---------------------------------------------------------------------------------- */
+static void conv5x5_s2(const float *x, int cin, int H, int W, const float *wgt, int cout, float *y)
+{
+    const int Ho = H / 2, Wo = W / 2;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int o = 0; o < cout; o++) {
+        float *yo = y + (size_t)o * Ho * Wo;
+        memset(yo, 0, sizeof(float) * (size_t)Ho * Wo);
+        for (int c = 0; c < cin; c++) {
+            const float *xc = x + (size_t)c * H * W;
+            for (int kh = 0; kh < 5; kh++)
+                for (int kw = 0; kw < 5; kw++) {
+                    const float wv = wgt[(((size_t)o * cin + c) * 5 + kh) * 5 + kw];
+                    /* valid output range so that 0 <= 2h+kh-1 < H */
+                    int h0 = (kh == 0) ? 1 : 0, h1 = Ho;
+                    while (h1 > h0 && 2 * (h1 - 1) + kh - 1 >= H) h1--;
+                    int w0 = (kw == 0) ? 1 : 0, w1 = Wo;
+                    while (w1 > w0 && 2 * (w1 - 1) + kw - 1 >= W) w1--;
+                    for (int h = h0; h < h1; h++) {
+                        const float *xr = xc + (size_t)(2 * h + kh - 1) * W + (kw - 1);
+                        float *yr = yo + (size_t)h * Wo;
+                        for (int w = w0; w < w1; w++) yr[w] += wv * xr[2 * w];
+                    }
+                }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * 5x5 stride-2 transposed convolution (processTransposeConv2dLayer spleeter.c:73-78 =
+ * gemm_tn gemm.c:33-45 + col2im_dilated_cpu im2col_dilated.c:42-65): output (2h+kh-1,
+ * 2w+kw-1) += sum_cin W[cin][co][kh][kw] x[cin][h][w]; per-tap partial sums over cin are
+ * formed first (the gemm) and then added in (kh, kw) ascending order (the col2im).
+ * ---------------------------------------------------------------------------------- */
+static void tconv5x5_s2(const float *x, int cin, int H, int W, const float *wgt, int cout, float *y)
+{
+    const int Ho = 2 * H, Wo = 2 * W;
+#pragma omp parallel
+    {
+        float *part = (float *)malloc(sizeof(float) * (size_t)H * W);
+#pragma omp for schedule(dynamic, 1)
+        for (int o = 0; o < cout; o++) {
+            float *yo = y + (size_t)o * Ho * Wo;
+            memset(yo, 0, sizeof(float) * (size_t)Ho * Wo);
+            for (int kh = 0; kh < 5; kh++)
+                for (int kw = 0; kw < 5; kw++) {
+                    memset(part, 0, sizeof(float) * (size_t)H * W);
+                    for (int c = 0; c < cin; c++) {
+                        const float wv = wgt[(((size_t)c * cout + o) * 5 + kh) * 5 + kw];
+                        const float *xc = x + (size_t)c * H * W;
+                        for (int i = 0; i < H * W; i++) part[i] += wv * xc[i];
+                    }
+                    for (int h = 0; h < H; h++) {
+                        int oh = 2 * h + kh - 1;
+                        if (oh < 0 || oh >= Ho) continue;
+                        for (int w = 0; w < W; w++) {
+                            int ow = 2 * w + kw - 1;
+                            if (ow < 0 || ow >= Wo) continue;
+                            yo[(size_t)oh * Wo + ow] += part[(size_t)h * W + w];
+                        }
+                    }
+                }
+        }
+        free(part);
+    }
+}
+
+/* 4x4, dilation 2, stride 1 head (spleeter.c:156, 295): rows h+2kh-3, cols w+2kw-3. */
+static void conv4x4_d2(const float *x, int H, int W, const float *wgt, float *y)
+{
+#pragma omp parallel for
+    for (int o = 0; o < 2; o++) {
+        float *yo = y + (size_t)o * H * W;
+        memset(yo, 0, sizeof(float) * (size_t)H * W);
+        for (int kh = 0; kh < 4; kh++)
+            for (int kw = 0; kw < 4; kw++) {
+                const float wv = wgt[(o * 4 + kh) * 4 + kw];
+                for (int h = 0; h < H; h++) {
+                    int ih = h + 2 * kh - 3;
+                    if (ih < 0 || ih >= H) continue;
+                    for (int w = 0; w < W; w++) {
+                        int iw = w + 2 * kw - 3;
+                        if (iw < 0 || iw >= W) continue;
+                        yo[(size_t)h * W + w] += wv * x[(size_t)ih * W + iw];
+                    }
+                }
+            }
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * processSpleeter (Executable/spleeter.c:177-301).  x, y: [2][T][F].
+ *   stemMode 0: encoder leakyReLU(0.2), decoder ReLU; !=0: ELU/ELU (spleeter.c:130-139)
+ *   flavour  0: Executable (LUT sigmoid, ELU clamp); 1: VST (exact sigmoid, no clamp)
+ *   taps (optional): receives, back to back, the 6 raw encoder outputs (conv+bias, the
+ *   skips), then the 6 decoder outputs after act+BN (up1..up6), planar NCHW.
+ * ---------------------------------------------------------------------------------- */
+size_t srt_oracle_taps_floats(int F, int T)
+{
+    size_t P = (size_t)F * T, n = 0;
+    for (int i = 0; i < 6; i++) n += (P >> (2 * (i + 1))) * kEncCh[i + 1];
+    for (int i = 0; i < 6; i++) n += (P >> (2 * (5 - i))) * kDecOut[i];
+    return n;
+}
+
+void srt_oracle_unet(const float *coeff, int F, int T, int stemMode, int flavour,
+                     const float *x, float *y, float *taps)
+{
+    net_t net;
+    net_bind(&net, coeff);
+    const int actEnc = stemMode ? (flavour ? 3 : 2) : 0;
+    const int actDec = stemMode ? (flavour ? 3 : 2) : 1;
+    const size_t P = (size_t)F * T;
+    float *skip[6];
+    float *cur = (float *)malloc(sizeof(float) * P * 8);   /* activated encoder feature */
+    float *cat = (float *)malloc(sizeof(float) * P * 32);  /* [skip | up] concat buffer */
+    int H = T, W = F;
+    const float *in = x;
+    for (int i = 0; i < 6; i++) {
+        const layer_t *l = &net.down[i];
+        const int Ho = H / 2, Wo = W / 2;
+        const size_t hw = (size_t)Ho * Wo;
+        skip[i] = (float *)malloc(sizeof(float) * hw * l->cout);
+        conv5x5_s2(in, l->cin, H, W, l->w, l->cout, skip[i]);
+        for (int c = 0; c < l->cout; c++)
+            for (size_t p = 0; p < hw; p++) {
+                float v = skip[i][c * hw + p] + l->b[c];          /* spleeter.c:186-187 */
+                skip[i][c * hw + p] = v;
+                if (l->bn) cur[c * hw + p] = act_apply(actEnc, l->bn[l->cout + c] * v + l->bn[c]);
+            }
+        if (taps) { memcpy(taps, skip[i], sizeof(float) * hw * l->cout); taps += hw * l->cout; }
+        in = cur;
+        H = Ho; W = Wo;
+    }
+    /* decoder: input of up1 is conv6; afterwards [skip_k | up] (spleeter.c:239-289) */
+    const float *din = skip[5];
+    for (int i = 0; i < 6; i++) {
+        const layer_t *l = &net.up[i];
+        const int Ho = 2 * H, Wo = 2 * W;
+        const size_t hw = (size_t)Ho * Wo;
+        const int nskip = (i < 5) ? l->cout : 0;   /* channels of the skip placed in front */
+        float *up = cat + hw * nskip;
+        float *tmp = (i == 5) ? (float *)malloc(sizeof(float) * hw) : up;
+        tconv5x5_s2(din, l->cin, H, W, l->w, l->cout, tmp);
+        for (int c = 0; c < l->cout; c++)
+            for (size_t p = 0; p < hw; p++) {
+                float v = act_apply(actDec, tmp[c * hw + p] + l->b[c]);   /* spleeter.c:244 */
+                tmp[c * hw + p] = l->bn[l->cout + c] * v + l->bn[c];      /* spleeter.c:245 */
+            }
+        if (taps) { memcpy(taps, tmp, sizeof(float) * hw * l->cout); taps += hw * l->cout; }
+        if (i < 5) {
+            memcpy(cat, skip[4 - i], sizeof(float) * hw * nskip);        /* spleeter.c:248 */
+            din = cat;
+        } else {
+            memcpy(cat, tmp, sizeof(float) * hw);
+            free(tmp);
+        }
+        H = Ho; W = Wo;
+    }
+    float *head = (float *)malloc(sizeof(float) * P * 2);
+    conv4x4_d2(cat, T, F, net.w7, head);
+    for (int c = 0; c < 2; c++)
+        for (size_t p = 0; p < P; p++) {
+            float v = head[c * P + p] + net.b7[c];
+            y[c * P + p] = flavour ? sigmoid_exact(v) : srt_oracle_sigmoid_lut(v);   /* spleeter.c:299 */
+        }
+    free(head);
+    for (int i = 0; i < 6; i++) free(skip[i]);
+    free(cur);
+    free(cat);
+}
+
+/* ------------------------------------------------------------------------------------
+ * Transforms.  Tables follow InitSTFT (stftFix.c:302-312): pre-window 0.5*hann(i+1/2)/4096,
+ * post-window (2/3)*hann(i+1/2), sine table sin(2*pi*i/4096), 12-bit bit reversal.
+ * ---------------------------------------------------------------------------------- */
+static float g_pre[SRT_FFT], g_post[SRT_FFT], g_sin[SRT_FFT];
+static unsigned g_rev[SRT_FFT];
+static int g_tab_ready = 0;
+
+static void tables_init(void)
+{
+    if (g_tab_ready) return;
+    const double w = 6.283185307179586476925286766559 / SRT_FFT;
+    for (int i = 0; i < SRT_FFT; i++) {
+        /* LLraisedCosTblFloat(n, LAP=4): (1/n) * hann(i + 0.5)   stftFix.c:48-57 */
+        float rc = (float)((1.0 / SRT_FFT) * (0.5 * (1.0 - cos(w * (i + 0.5)))));
+        g_pre[i] = rc * (2.0f / 4.0f);                            /* stftFix.c:307-308 */
+        /* LLCreatePostWindowFloat: scalefac = n * (1/2)/(3/8)   stftFix.c:64-75, then *0.5 :311-312 */
+        const float scalefac = (float)SRT_FFT * ((1.0f / 2.0f) / (3.0f / 8.0f));
+        g_post[i] = rc * scalefac * 0.5f;
+        g_sin[i] = (float)sin(w * i);                             /* stftFix.c:58-63 */
+        unsigned r = 0, v = (unsigned)i;
+        for (int b = 0; b < 12; b++) { r = (r << 1) | (v & 1); v >>= 1; }
+        g_rev[i] = r;
+    }
+    g_tab_ready = 1;
+}
+
+const float *srt_oracle_prewindow(void) { tables_init(); return g_pre; }
+const float *srt_oracle_postwindow(void) { tables_init(); return g_post; }
+
+/* In-place 4096-point discrete Hartley transform of bit-reversed input: the radix-2
+ * decimation-in-time scheme of DFT4096 (codelet.c:2-271) written as generic loops.
+ * H[k] = sum_n a[n] cas(2 pi n k / N).  Self-inverse up to a factor N. */
+static void dht4096(float *a)
+{
+    for (int len = 2; len <= SRT_FFT; len <<= 1) {
+        const int half = len >> 1, quarter = len >> 2, tstep = SRT_FFT / len;
+        for (int i = 0; i < SRT_FFT; i += len) {
+            float p = a[i], q = a[i + half];
+            a[i] = p + q; a[i + half] = p - q;
+            if (quarter) {
+                p = a[i + quarter]; q = a[i + half + quarter];
+                a[i + quarter] = p + q; a[i + half + quarter] = p - q;
+            }
+            for (int j = 1; j < quarter; j++) {
+                const float s = g_sin[j * tstep], c = g_sin[j * tstep + 1024];
+                const float e = a[i + half + j], f = a[i + len - j];
+                const float b1 = e * c + f * s, b2 = e * s - f * c;
+                p = a[i + j]; q = a[i + half - j];
+                a[i + j] = p + b1; a[i + half + j] = p - b1;
+                a[i + half - j] = q + b2; a[i + len - j] = q - b2;
+            }
+        }
+    }
+}
+
+/* stft (stftFix.c:363-495), single-thread branch :429-494.  Rows = ceil(n/1024); rows are
+ * 4096 floats wide, bins 0..2048 written, everything else (incl. trailing rows) zero.
+ * Output buffers are caller-allocated and must be zero-filled. */
+size_t srt_oracle_stft(const float *L, const float *R, size_t n,
+                       float *reL, float *imL, float *reR, float *imR)
+{
+    tables_init();
+    const size_t rows = (n + SRT_HOP - 1) / SRT_HOP;
+    const size_t rangeM = ((n - SRT_FFT + SRT_HOP / 4) / SRT_HOP) * SRT_HOP;   /* stftFix.c:377 */
+    const size_t nfull = rangeM / SRT_HOP;
+#pragma omp parallel
+    {
+        float *buf = (float *)malloc(sizeof(float) * 2 * SRT_FFT);
+#pragma omp for schedule(static)
+        for (size_t f = 0; f <= nfull; f++) {
+            const size_t pos = f * SRT_HOP;
+            float *b[2] = {buf, buf + SRT_FFT};
+            for (int i = 0; i < SRT_FFT; i++) {
+                const int ok = pos + i < n;       /* only the last frame can run past n (:460-473) */
+                b[0][g_rev[i]] = ok ? L[pos + i] * g_pre[i] : 0.0f;
+                b[1][g_rev[i]] = ok ? R[pos + i] * g_pre[i] : 0.0f;
+            }
+            dht4096(b[0]);
+            dht4096(b[1]);
+            float *re[2] = {reL + f * SRT_FFT, reR + f * SRT_FFT};
+            float *im[2] = {imL + f * SRT_FFT, imR + f * SRT_FFT};
+            for (int c = 0; c < 2; c++) {
+                re[c][0] = b[c][0] * 2.0f;        /* stftFix.c:441-444 */
+                im[c][0] = 0.0f;
+                for (int k = 1; k < SRT_BINS; k++) {
+                    re[c][k] = b[c][k] + b[c][SRT_FFT - k];   /* :448-455 */
+                    im[c][k] = b[c][k] - b[c][SRT_FFT - k];
+                }
+            }
+        }
+        free(buf);
+    }
+    return rows;
+}
+
+/* istft (stftFix.c:496-579), single-thread branch :552-577.  Outputs caller-allocated,
+ * zero-filled, length frames*1024 + 3072.  Inputs are not modified (the reference's
+ * multi-thread branch clobbers them, :537-538; callers must not rely on either). */
+size_t srt_oracle_istft(const float *reL, const float *imL, const float *reR, const float *imR,
+                        size_t frames, float *outL, float *outR)
+{
+    tables_init();
+    float *tmp = (float *)malloc(sizeof(float) * 2 * SRT_FFT * (frames ? frames : 1));
+#pragma omp parallel for schedule(static)
+    for (size_t f = 0; f < frames; f++) {
+        const float *re[2] = {reL + f * SRT_FFT, reR + f * SRT_FFT};
+        const float *im[2] = {imL + f * SRT_FFT, imR + f * SRT_FFT};
+        for (int c = 0; c < 2; c++) {
+            float *h = tmp + (2 * f + c) * SRT_FFT;
+            h[0] = re[c][0];
+            for (int j = 1; j < SRT_BINS; j++) {
+                h[g_rev[j]] = re[c][j] + im[c][j];               /* :563-566 */
+                h[g_rev[SRT_FFT - j]] = re[c][j] - im[c][j];
+            }
+            dht4096(h);
+        }
+    }
+    for (size_t f = 0; f < frames; f++)                           /* serial OLA, frame order (:570-575) */
+        for (int p = 0; p < SRT_FFT; p++) {
+            outL[f * SRT_HOP + p] += tmp[(2 * f) * SRT_FFT + p] * g_post[p];
+            outR[f * SRT_HOP + p] += tmp[(2 * f + 1) * SRT_FFT + p] * g_post[p];
+        }
+    free(tmp);
+    return frames * SRT_HOP + (SRT_FFT - SRT_HOP);
+}
+
+/* ------------------------------------------------------------------------------------
+ * Tile driver = processMT single-thread branch (main.c:447-541) generalised to nStems nets
+ * that each mask the same mixture spectrum (as the VST's 4 nets do, Spleeter4Stems.c:135),
+ * with the CLI's host framing (main.c:762-767: 4096 zeros in front, padded length
+ * 4096*ceil(n/4096)+8192) and un-framing (channel_joinFloat preshift 4096, main.c:806).
+ * stems: nStems*2 planar outputs of n samples, order [stem][L,R].
+ * masks_out (optional): nStems * nTiles * 2*T*F floats.
+ * ---------------------------------------------------------------------------------- */
+size_t srt_oracle_padded_len(size_t n) { return (size_t)SRT_FFT * ((n + SRT_FFT - 1) / SRT_FFT) + 2 * SRT_FFT; }
+
+int srt_oracle_separate(const float *const *coeffs, const int *stemModes, int nStems, int flavour,
+                        const float *pcmL, const float *pcmR, size_t n, int T, int F,
+                        float unaffectedWeight, float *const *stems, float *masks_out)
+{
+    const size_t padded = srt_oracle_padded_len(n);
+    const size_t frames = padded / SRT_HOP;
+    float *pl = (float *)calloc(padded, sizeof(float)), *pr = (float *)calloc(padded, sizeof(float));
+    memcpy(pl + SRT_FFT, pcmL, n * sizeof(float));
+    memcpy(pr + SRT_FFT, pcmR, n * sizeof(float));
+    float *spec[4];
+    for (int i = 0; i < 4; i++) spec[i] = (float *)calloc(frames * SRT_FFT, sizeof(float));
+    srt_oracle_stft(pl, pr, padded, spec[0], spec[1], spec[2], spec[3]);
+    const size_t P = (size_t)T * F;
+    const size_t tiles = (frames + T - 1) / T;
+    float *mag = (float *)malloc(sizeof(float) * 2 * P);
+    float *mask = (float *)malloc(sizeof(float) * 2 * P);
+    float *ms[4];
+    for (int i = 0; i < 4; i++) ms[i] = (float *)malloc(sizeof(float) * frames * SRT_FFT);
+    const size_t outLen = frames * SRT_HOP + (SRT_FFT - SRT_HOP);
+    float *oL = (float *)malloc(sizeof(float) * outLen), *oR = (float *)malloc(sizeof(float) * outLen);
+    for (int s = 0; s < nStems; s++) {
+        for (int i = 0; i < 4; i++) memcpy(ms[i], spec[i], sizeof(float) * frames * SRT_FFT);
+        for (size_t j = 0; j < tiles; j++) {
+            const size_t f0 = j * T;
+            for (int t = 0; t < T; t++)
+                for (int i = 0; i < F; i++) {
+                    const size_t idx = (f0 + t) * SRT_FFT + i;
+                    const int live = f0 + t < frames;            /* tail tile rows zeroed, main.c:507-514 */
+                    mag[0 * P + (size_t)t * F + i] = live ? hypotf(spec[0][idx], spec[1][idx]) * (float)SRT_FFT : 0.0f;
+                    mag[1 * P + (size_t)t * F + i] = live ? hypotf(spec[2][idx], spec[3][idx]) * (float)SRT_FFT : 0.0f;
+                }
+            srt_oracle_unet(coeffs[s], F, T, stemModes[s], flavour, mag, mask, NULL);
+            if (masks_out) memcpy(masks_out + ((size_t)s * tiles + j) * 2 * P, mask, sizeof(float) * 2 * P);
+            for (int t = 0; t < T && f0 + t < frames; t++) {
+                const size_t off = (f0 + t) * SRT_FFT;
+                for (int i = 0; i < F; i++) {                    /* main.c:476-485 */
+                    const float mL = mask[0 * P + (size_t)t * F + i], mR = mask[1 * P + (size_t)t * F + i];
+                    ms[0][off + i] *= mL; ms[1][off + i] *= mL;
+                    ms[2][off + i] *= mR; ms[3][off + i] *= mR;
+                }
+                for (int i = F; i < SRT_BINS; i++)               /* main.c:486-493 */
+                    for (int q = 0; q < 4; q++) ms[q][off + i] *= unaffectedWeight;
+            }
+        }
+        memset(oL, 0, sizeof(float) * outLen);
+        memset(oR, 0, sizeof(float) * outLen);
+        srt_oracle_istft(ms[0], ms[1], ms[2], ms[3], frames, oL, oR);
+        memcpy(stems[2 * s + 0], oL + SRT_FFT, n * sizeof(float));
+        memcpy(stems[2 * s + 1], oR + SRT_FFT, n * sizeof(float));
+    }
+    for (int i = 0; i < 4; i++) { free(spec[i]); free(ms[i]); }
+    free(mag); free(mask); free(oL); free(oR); free(pl); free(pr);
+    return 0;
+}
+
+/* half -> float with denormals flushed to zero (f32Decompress, main.c:423-434). */
+void srt_oracle_half_to_float(const uint16_t *in, float *out, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        uint32_t h = in[i], mag = (h & 0x7fffu) << 13, sign = (h & 0x8000u) << 16;
+        uint32_t bits = ((h & 0x7c00u) == 0) ? 0u : mag + 0x38000000u;
+        bits |= sign;
+        memcpy(&out[i], &bits, 4);
+    }
+}

@@ -1,0 +1,843 @@
+// srt_ctx.cu — context, memory plan and orchestration behind the tier-B C ABI (include/srt_b200.h).
+// One context per GPU and per (n_stems, T, F) configuration; all work is enqueued on one CUDA
+// stream.  No CPU compute path exists: if the device or the kernels are unavailable the calls
+// return SRT_ERR_CUDA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/srt_b200.h"
+#include "srt_kernels.cuh"
+#include "srt_plan.h"
+
+using namespace srt;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(SRT_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* srt_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------
+// driver entry point for TMA descriptors (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// activation tensor [n][H][W][C] fp32 -> 4-D map, box {32, tw, th, nb}, 128B swizzle, zero OOB fill
+static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int N, int tw, int th, int nb)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kKB, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d N=%d box=%d,%d,%d", (int)r, C, W, H, N, tw, th, nb);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static const int kEnc[7] = {2, 16, 32, 64, 128, 256, 512};
+static const int kDecOut[6] = {256, 128, 64, 32, 16, 1};
+
+struct Span {
+    int cat;
+    cudaEvent_t a, b;
+};
+
+struct srt_ctx {
+    srt_config cfg{};
+    int S = 0, T = 0, F = 0, B = 0, NB = 0;   // B = U-Net batch capacity, NB = batch images capacity
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int act_enc[8]{}, act_dec[8]{};
+    std::vector<void*> allocs;
+    // tables
+    float *d_window = nullptr, *d_postwin = nullptr, *d_lut = nullptr;
+    float2* d_twiddle = nullptr;
+    // weights
+    float *d_w1 = nullptr, *d_b1 = nullptr, *d_s1 = nullptr, *d_o1 = nullptr;          // down1
+    float *d_w6 = nullptr, *d_b6 = nullptr, *d_s6 = nullptr, *d_o6 = nullptr;          // up6
+    float *d_w7 = nullptr, *d_b7 = nullptr;                                            // up7
+    std::vector<LayerPlan> plans;
+    std::vector<ConvParams> conv;   // 10 tensor-core layers
+    // activations
+    float* E[7]{};    // E[1..6] raw skips (NHWC)
+    float* A[6]{};    // A[1..5] activated, space-to-depth
+    float* U[7]{};    // U[1..5] decoder outputs (NHWC), U[6] = up6 output [n][T][F]
+    // batch buffers
+    float* d_mag = nullptr;       // [NB][T][F][2]
+    float4* d_spec = nullptr;     // [NB][T][2049]
+    float* d_mask = nullptr;      // [S][NB][T][F][2]
+    float2* d_frames = nullptr;   // [max(S,1)][B][T][4096]
+    // per-call metadata (device + pinned host mirror)
+    uint8_t *d_meta = nullptr, *h_meta = nullptr;
+    size_t meta_cap = 0;
+    // staging for the host-pointer API
+    float *d_pcm = nullptr, *d_out = nullptr;
+    size_t pcm_cap = 0, out_cap = 0;
+    float *d_xin = nullptr;       // unet_host staging
+    // bookkeeping
+    long long launches = 0;
+    bool timing = false;
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    int last_Bv = 0;
+};
+
+template <class Tp>
+static int dalloc(srt_ctx* c, Tp** p, size_t count)
+{
+    void* q = nullptr;
+    if (count == 0) count = 1;
+    CK(cudaMalloc(&q, count * sizeof(Tp)));
+    c->allocs.push_back(q);
+    *p = (Tp*)q;
+    return 0;
+}
+template <class Tp>
+static int upload(srt_ctx* c, Tp** p, const std::vector<Tp>& h)
+{
+    int r = dalloc(c, p, h.size());
+    if (r) return r;
+    CK(cudaMemcpy(*p, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static cudaEvent_t get_event(srt_ctx* c)
+{
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+struct Timed {
+    srt_ctx* c;
+    Span sp;
+    bool on;
+    Timed(srt_ctx* c_, int cat) : c(c_), on(c_->timing)
+    {
+        if (on) {
+            sp.cat = cat;
+            sp.a = get_event(c);
+            sp.b = get_event(c);
+            cudaEventRecord(sp.a, c->stream);
+        }
+    }
+    ~Timed()
+    {
+        if (on) {
+            cudaEventRecord(sp.b, c->stream);
+            c->spans.push_back(sp);
+        }
+    }
+};
+
+extern "C" void srt_half_to_float(const uint16_t* in, float* out, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t h = in[i];
+        uint32_t bits = ((h & 0x7c00u) == 0) ? 0u : (((h & 0x7fffu) << 13) + 0x38000000u);
+        bits |= (h & 0x8000u) << 16;
+        std::memcpy(&out[i], &bits, 4);
+    }
+}
+
+static size_t act_floats(const srt_ctx* c, int level, int ch)   // tensor at resolution T>>level
+{
+    return (size_t)c->S * c->B * (c->T >> level) * (c->F >> level) * ch;
+}
+
+extern "C" void srt_destroy(srt_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->d_meta) cudaFree(c->d_meta);
+    if (c->h_meta) cudaFreeHost(c->h_meta);
+    if (c->d_pcm) cudaFree(c->d_pcm);
+    if (c->d_out) cudaFree(c->d_out);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
+{
+    const int S = c->S, T = c->T, F = c->F;
+    // ---- transform tables (InitSTFT, stftFix.c:302-312), computed in double like the reference
+    {
+        std::vector<float> win(kFFT), post(kFFT);
+        std::vector<float2> tw(kFFT);
+        const double w = 6.283185307179586476925286766559 / kFFT;
+        for (int i = 0; i < kFFT; i++) {
+            const float rc = (float)((1.0 / kFFT) * (0.5 * (1.0 - cos(w * (i + 0.5)))));   // LLraisedCosTblFloat
+            win[i] = rc;                                                                     // = 2 * mPreWindow
+            post[i] = rc * ((float)kFFT * ((1.0f / 2.0f) / (3.0f / 8.0f))) * 0.5f;           // mPostWindow
+            tw[i] = make_float2((float)cos(w * i), (float)-sin(w * i));
+        }
+        int r;
+        if ((r = upload(c, &c->d_window, win))) return r;
+        if ((r = upload(c, &c->d_postwin, post))) return r;
+        if ((r = upload(c, &c->d_twiddle, tw))) return r;
+        if (c->cfg.flavour == 0) {
+            std::vector<float> lut(1026);   // fastSigmoid's table regenerated: sigma(-7 + i*14/1024) to 8 decimals
+            for (int i = 0; i <= 1024; i++) {
+                const double s = 1.0 / (1.0 + exp(-(-7.0 + i * (14.0 / 1024.0))));
+                lut[i] = (float)(floor(s * 1e8 + 0.5) / 1e8);
+            }
+            lut[1025] = 1.0f;
+            if ((r = upload(c, &c->d_lut, lut))) return r;
+        }
+    }
+    int r;
+    // ---- batch buffers
+    if ((r = dalloc(c, &c->d_spec, (size_t)c->NB * T * kBins))) return r;
+    if ((r = dalloc(c, &c->d_frames, (size_t)(S ? S : 1) * c->B * T * kFFT))) return r;
+    if (S == 0) return 0;
+    if ((r = dalloc(c, &c->d_mag, (size_t)c->NB * T * F * 2))) return r;
+    if ((r = dalloc(c, &c->d_mask, (size_t)S * c->NB * T * F * 2))) return r;
+    if ((r = dalloc(c, &c->d_xin, (size_t)c->B * T * F * 2))) return r;
+    // ---- activations
+    for (int i = 1; i <= 6; i++)
+        if ((r = dalloc(c, &c->E[i], act_floats(c, i, kEnc[i])))) return r;
+    for (int i = 1; i <= 5; i++)
+        if ((r = dalloc(c, &c->A[i], act_floats(c, i, kEnc[i])))) return r;
+    for (int d = 1; d <= 5; d++)
+        if ((r = dalloc(c, &c->U[d], act_floats(c, 6 - d, kDecOut[d - 1])))) return r;
+    if ((r = dalloc(c, &c->U[6], act_floats(c, 0, 1)))) return r;
+    // ---- weights
+    const CoeffLayout cl = coeff_layout();
+    for (int s = 0; s < S; s++) {
+        const bool elu = modes[s] != 0;
+        c->act_enc[s] = elu ? (c->cfg.flavour ? ACT_ELU : ACT_ELU_CLAMP) : ACT_LEAKY;
+        c->act_dec[s] = elu ? (c->cfg.flavour ? ACT_ELU : ACT_ELU_CLAMP) : ACT_RELU;
+    }
+    {
+        std::vector<float> w1((size_t)S * 800), b1(S * 16), s1(S * 16), o1(S * 16);
+        std::vector<float> w6((size_t)S * 800), b6(S), s6(S), o6(S), w7(S * 32), b7(S * 2);
+        for (int s = 0; s < S; s++) {
+            const float* k = coeffs[s];
+            std::memcpy(&w1[(size_t)s * 800], k + cl.down_w[0], 800 * 4);
+            std::memcpy(&b1[s * 16], k + cl.down_b[0], 16 * 4);
+            std::memcpy(&o1[s * 16], k + cl.down_bn[0], 16 * 4);        // [0,C) offset
+            std::memcpy(&s1[s * 16], k + cl.down_bn[0] + 16, 16 * 4);   // [C,2C) scale (spleeter.c:188)
+            std::memcpy(&w6[(size_t)s * 800], k + cl.up_w[5], 800 * 4);
+            b6[s] = k[cl.up_b[5]];
+            o6[s] = k[cl.up_bn[5]];
+            s6[s] = k[cl.up_bn[5] + 1];
+            std::memcpy(&w7[s * 32], k + cl.w7, 32 * 4);
+            std::memcpy(&b7[s * 2], k + cl.b7, 2 * 4);
+        }
+        if ((r = upload(c, &c->d_w1, w1)) || (r = upload(c, &c->d_b1, b1)) || (r = upload(c, &c->d_s1, s1)) || (r = upload(c, &c->d_o1, o1))) return r;
+        if ((r = upload(c, &c->d_w6, w6)) || (r = upload(c, &c->d_b6, b6)) || (r = upload(c, &c->d_s6, s6)) || (r = upload(c, &c->d_o6, o6))) return r;
+        if ((r = upload(c, &c->d_w7, w7)) || (r = upload(c, &c->d_b7, b7))) return r;
+    }
+    // ---- tensor-core layers
+    c->plans = build_plans(NetGeom{T, F}, c->B);
+    c->conv.resize(c->plans.size());
+    for (size_t li = 0; li < c->plans.size(); li++) {
+        const LayerPlan& L = c->plans[li];
+        ConvParams& p = c->conv[li];
+        std::memset(&p, 0, sizeof p);
+        // weights + epilogue vectors
+        std::vector<float> wpk((size_t)S * L.w_floats_per_stem), bias((size_t)S * L.cout), sc((size_t)S * L.cout, 1.0f), of((size_t)S * L.cout, 0.0f);
+        for (int s = 0; s < S; s++) {
+            pack_layer(L, coeffs[s], &wpk[(size_t)s * L.w_floats_per_stem]);
+            const float* k = coeffs[s];
+            const size_t bo = L.transposed ? cl.up_b[L.index - 5] : cl.down_b[L.index + 1];
+            const size_t bn = L.transposed ? cl.up_bn[L.index - 5] : cl.down_bn[L.index + 1];
+            std::memcpy(&bias[(size_t)s * L.cout], k + bo, L.cout * 4);
+            if (L.transposed || L.index < 4) {
+                std::memcpy(&of[(size_t)s * L.cout], k + bn, L.cout * 4);
+                std::memcpy(&sc[(size_t)s * L.cout], k + bn + L.cout, L.cout * 4);
+            }
+        }
+        float *dw, *db, *ds, *dofs;
+        if ((r = upload(c, &dw, wpk)) || (r = upload(c, &db, bias)) || (r = upload(c, &ds, sc)) || (r = upload(c, &dofs, of))) return r;
+        // k-block tables
+        std::vector<KBlock> kb;
+        for (int ph = 0; ph < L.phases; ph++) {
+            p.kb_off[ph] = (int)kb.size();
+            p.nkb[ph] = (int)L.kb[ph].size();
+            p.w_phase_off[ph] = L.w_phase_off[ph];
+            kb.insert(kb.end(), L.kb[ph].begin(), L.kb[ph].end());
+        }
+        KBlock* dkb;
+        if ((r = upload(c, &dkb, kb))) return r;
+        p.kb = dkb;
+        p.w = dw;
+        p.w_stem_stride = L.w_floats_per_stem;
+        p.bias = db;
+        p.bn_scale = ds;
+        p.bn_offset = dofs;
+        p.n_tile = L.n_tile;
+        p.n_tiles = L.n_tiles;
+        p.phases = L.phases;
+        p.Hs = L.Hs;
+        p.Ws = L.Ws;
+        p.B = c->B;
+        p.S = S;
+        p.tw = L.tw;
+        p.th = L.th;
+        p.nb = L.nb;
+        p.tiles_x = (L.Ws + L.tw - 1) / L.tw;
+        p.tiles_y = (L.Hs + L.th - 1) / L.th;
+        p.cout = L.cout;
+        for (int s = 0; s < S; s++) p.act[s] = L.transposed ? c->act_dec[s] : c->act_enc[s];
+        // sources and destinations
+        const float* src[2] = {nullptr, nullptr};
+        if (!L.transposed) {
+            const int i = L.index + 1;          // input = activated output of down{i}
+            src[0] = c->A[i];
+            p.mode = (L.index == 4) ? 1 : 0;
+            p.out_raw = c->E[i + 1];
+            p.out_act = (L.index == 4) ? nullptr : c->A[i + 1];
+            p.round_raw = 1;                    // E2..E6 feed decoder tensor-core layers
+            p.round_act = 1;
+        } else {
+            const int d = L.index - 5;          // up{d+1}
+            if (d == 0) src[0] = c->E[6];
+            else { src[0] = c->E[6 - d]; src[1] = c->U[d]; }
+            p.mode = 2;
+            p.out_dec = c->U[d + 1];
+            p.round_act = (d < 4) ? 1 : 0;      // up5 feeds the SIMT up6 kernel: keep fp32
+        }
+        for (int q = 0; q < L.nsrc; q++) {
+            p.src_ptr[q] = src[q];
+            p.src_C[q] = L.src[q].C;
+            if ((r = make_tmap(&p.tmap[q], src[q], L.src[q].C, L.src[q].W, L.src[q].H, S * c->B, L.tw, L.th, L.nb))) return r;
+        }
+        if (L.nsrc == 1) p.tmap[1] = p.tmap[0];
+    }
+    return 0;
+}
+
+extern "C" int srt_create(const srt_config* cfg, const float* const* coeffs, const int* stem_modes, srt_ctx** out)
+{
+    if (!cfg || !out) return fail(SRT_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->n_stems < 0 || cfg->n_stems > SRT_MAX_STEMS) return fail(SRT_ERR_ARG, "n_stems %d out of range", cfg->n_stems);
+    if (cfg->n_stems > 0 && (!coeffs || !stem_modes)) return fail(SRT_ERR_ARG, "weights missing");
+    if (cfg->time_step < 1 || cfg->max_images < 1) return fail(SRT_ERR_ARG, "time_step/max_images must be positive");
+    if (cfg->n_stems > 0) {
+        // initSpleeter needs six halvings (spleeter.c:113-119); the CLI clamps F to [512, 2048] (main.c:733-748)
+        if (cfg->time_step % 64 || cfg->bin_limit % 64 || cfg->bin_limit < 64 || cfg->bin_limit > 2048)
+            return fail(SRT_ERR_ARG, "time_step (%d) and bin_limit (%d) must be multiples of 64, bin_limit <= 2048", cfg->time_step, cfg->bin_limit);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SRT_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(SRT_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(SRT_ERR_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", cfg->device, prop.major, prop.minor);
+    srt_ctx* c = new srt_ctx();
+    c->cfg = *cfg;
+    c->S = cfg->n_stems;
+    c->T = cfg->time_step;
+    c->F = cfg->n_stems ? cfg->bin_limit : 0;
+    c->B = cfg->max_images;
+    c->NB = cfg->max_batch_images > cfg->max_images ? cfg->max_batch_images : cfg->max_images;
+    if (cfg->cuda_stream) c->stream = (cudaStream_t)cfg->cuda_stream;
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail(SRT_ERR_CUDA, "stream creation failed"); }
+        c->own_stream = true;
+    }
+    int r = build(c, coeffs, stem_modes);
+    if (r == 0 && cudaDeviceSynchronize() != cudaSuccess) r = fail(SRT_ERR_CUDA, "context build: %s", cudaGetErrorString(cudaGetLastError()));
+    if (r) { std::string keep = g_err; srt_destroy(c); g_err = keep; return r; }
+    *out = c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// U-Net on Bv images whose magnitudes sit at d_mag (layout [Bv][T][F][2]); masks go to
+// mask_base[s][mask_img0 + b] with `mask_stride` images between stems.
+// ------------------------------------------------------------------------------------------
+static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, int mask_stride, int mask_img0)
+{
+    const int S = c->S;
+    c->last_Bv = Bv;
+    {
+        Timed t(c, 10);
+        Down1Params p{};
+        p.mag = d_mag; p.w = c->d_w1; p.bias = c->d_b1; p.bn_scale = c->d_s1; p.bn_offset = c->d_o1;
+        p.out_raw = c->E[1]; p.out_act = c->A[1];
+        p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
+        for (int s = 0; s < S; s++) p.act[s] = c->act_enc[s];
+        launch_down1(p, c->stream);
+        c->launches++;
+    }
+    for (size_t li = 0; li < c->conv.size(); li++) {
+        Timed t(c, (int)li);
+        ConvParams& p = c->conv[li];
+        p.Bv = Bv;
+        p.tiles_n = (Bv + p.nb - 1) / p.nb;
+        if (c->cfg.conv_impl == 1) launch_conv_simt(p, c->stream);
+        else launch_conv_tc(p, c->stream);
+        c->launches++;
+    }
+    {
+        Timed t(c, 11);
+        Up6Params p{};
+        p.skip = c->E[1]; p.up = c->U[5]; p.w = c->d_w6; p.bias = c->d_b6; p.bn_scale = c->d_s6; p.bn_offset = c->d_o6;
+        p.out = c->U[6];
+        p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
+        for (int s = 0; s < S; s++) p.act[s] = c->act_dec[s];
+        launch_up6(p, c->stream);
+        c->launches++;
+    }
+    {
+        Timed t(c, 12);
+        Up7Params p{};
+        p.in = c->U[6]; p.w = c->d_w7; p.bias = c->d_b7; p.lut = c->d_lut; p.mask = mask_base;
+        p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
+        p.mask_stem_stride = mask_stride; p.mask_img0 = mask_img0;
+        launch_up7(p, c->stream);
+        c->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SRT_ERR_CUDA, "U-Net launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static void reset_spans(srt_ctx* c)
+{
+    c->spans.clear();
+    c->ev_used = 0;
+}
+
+extern "C" int srt_unet_device(srt_ctx* c, const float* d_mag, int n_img, float* d_mask)
+{
+    if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
+    if (n_img < 1 || n_img > c->B) return fail(SRT_ERR_CAPACITY, "n_img %d exceeds max_images %d", n_img, c->B);
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    return run_unet(c, d_mag, n_img, d_mask, n_img, 0);
+}
+
+extern "C" int srt_unet_host(srt_ctx* c, const float* x, int n_img, float* y)
+{
+    if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
+    if (n_img < 1 || n_img > c->B) return fail(SRT_ERR_CAPACITY, "n_img %d exceeds max_images %d", n_img, c->B);
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    const size_t P = (size_t)c->T * c->F;
+    std::vector<float> xi((size_t)n_img * P * 2);
+    for (int b = 0; b < n_img; b++)
+        for (size_t i = 0; i < P; i++) {
+            xi[((size_t)b * P + i) * 2 + 0] = x[((size_t)b * 2 + 0) * P + i];
+            xi[((size_t)b * P + i) * 2 + 1] = x[((size_t)b * 2 + 1) * P + i];
+        }
+    CK(cudaMemcpyAsync(c->d_xin, xi.data(), xi.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    int r = run_unet(c, c->d_xin, n_img, c->d_mask, c->NB, 0);
+    if (r) return r;
+    std::vector<float> mi((size_t)n_img * P * 2);
+    for (int s = 0; s < c->S; s++) {
+        CK(cudaMemcpyAsync(mi.data(), c->d_mask + (size_t)s * c->NB * P * 2, mi.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int b = 0; b < n_img; b++)
+            for (size_t i = 0; i < P; i++) {
+                y[(((size_t)s * n_img + b) * 2 + 0) * P + i] = mi[((size_t)b * P + i) * 2 + 0];
+                y[(((size_t)s * n_img + b) * 2 + 1) * P + i] = mi[((size_t)b * P + i) * 2 + 1];
+            }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// full path
+// ------------------------------------------------------------------------------------------
+struct BatchMeta {
+    std::vector<int> n, nfr, img0;
+    std::vector<ImgDesc> imgs;
+    int total = 0;
+    size_t max_n = 0;
+};
+
+static size_t padded_len(size_t n) { return (size_t)kFFT * ((n + kFFT - 1) / kFFT) + 2 * kFFT; }   // main.c:762-763
+
+static int ensure_meta(srt_ctx* c, size_t bytes)
+{
+    if (bytes <= c->meta_cap) return 0;
+    if (c->d_meta) cudaFree(c->d_meta);
+    if (c->h_meta) cudaFreeHost(c->h_meta);
+    c->meta_cap = bytes * 2 + 4096;
+    CK(cudaMalloc((void**)&c->d_meta, c->meta_cap));
+    CK(cudaMallocHost((void**)&c->h_meta, c->meta_cap));
+    return 0;
+}
+
+static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* const* d_pcmR, const size_t* n_samples,
+                         int n_streams, const float* unaffected, float* const* d_out, int front_pad)
+{
+    const int T = c->T, S = c->S;
+    BatchMeta m;
+    for (int i = 0; i < n_streams; i++) {
+        if (n_samples[i] == 0 || n_samples[i] > (size_t)1 << 30) return fail(SRT_ERR_ARG, "stream %d: bad length", i);
+        const int nfr = (int)(padded_len(n_samples[i]) / kHop);
+        const int tiles = (nfr + T - 1) / T;
+        if (tiles > c->B) return fail(SRT_ERR_CAPACITY, "stream %d needs %d tiles > max_images %d", i, tiles, c->B);
+        m.n.push_back((int)n_samples[i]);
+        m.nfr.push_back(nfr);
+        m.img0.push_back(m.total);
+        for (int j = 0; j < tiles; j++) m.imgs.push_back(ImgDesc{i, j * T});
+        m.total += tiles;
+        if (n_samples[i] > m.max_n) m.max_n = n_samples[i];
+    }
+    if (m.total > c->NB) return fail(SRT_ERR_CAPACITY, "batch needs %d tiles > max_batch_images %d", m.total, c->NB);
+    // ---- metadata block: [pcmL ptrs][pcmR ptrs][out ptrs][n][nfr][img0][imgs]
+    const size_t o_pl = 0, o_pr = o_pl + 8 * (size_t)n_streams, o_out = o_pr + 8 * (size_t)n_streams;
+    const size_t o_n = o_out + 8 * (size_t)n_streams * S * 2, o_nfr = o_n + 4 * (size_t)n_streams, o_i0 = o_nfr + 4 * (size_t)n_streams;
+    const size_t o_img = (o_i0 + 4 * (size_t)n_streams + 7) & ~(size_t)7, total_b = o_img + sizeof(ImgDesc) * m.imgs.size();
+    int r = ensure_meta(c, total_b);
+    if (r) return r;
+    CK(cudaStreamSynchronize(c->stream));   // the pinned mirror may still be in flight from the previous call
+    std::memcpy(c->h_meta + o_pl, d_pcmL, 8 * (size_t)n_streams);
+    std::memcpy(c->h_meta + o_pr, d_pcmR, 8 * (size_t)n_streams);
+    std::memcpy(c->h_meta + o_out, d_out, 8 * (size_t)n_streams * S * 2);
+    std::memcpy(c->h_meta + o_n, m.n.data(), 4 * (size_t)n_streams);
+    std::memcpy(c->h_meta + o_nfr, m.nfr.data(), 4 * (size_t)n_streams);
+    std::memcpy(c->h_meta + o_i0, m.img0.data(), 4 * (size_t)n_streams);
+    std::memcpy(c->h_meta + o_img, m.imgs.data(), sizeof(ImgDesc) * m.imgs.size());
+    CK(cudaMemcpyAsync(c->d_meta, c->h_meta, total_b, cudaMemcpyHostToDevice, c->stream));
+    const ImgDesc* d_imgs = (const ImgDesc*)(c->d_meta + o_img);
+    const int* d_n = (const int*)(c->d_meta + o_n);
+    const int* d_nfr = (const int*)(c->d_meta + o_nfr);
+    // ---- STFT + magnitude for every tile of the batch
+    {
+        Timed t(c, 13);
+        StftParams p{};
+        p.pcmL = (const float* const*)(c->d_meta + o_pl);
+        p.pcmR = (const float* const*)(c->d_meta + o_pr);
+        p.n_samples = d_n; p.n_frames = d_nfr; p.imgs = d_imgs;
+        p.window = c->d_window; p.twiddle = c->d_twiddle;
+        p.spec = c->d_spec; p.mag = c->d_mag;
+        p.T = T; p.F = c->F; p.n_img = m.total; p.front_pad = front_pad;
+        launch_stft(p, c->stream);
+        c->launches++;
+    }
+    // ---- U-Net, max_images tiles per pass
+    for (int i0 = 0; i0 < m.total; i0 += c->B) {
+        const int Bv = std::min(c->B, m.total - i0);
+        if ((r = run_unet(c, c->d_mag + (size_t)i0 * T * c->F * 2, Bv, c->d_mask, c->NB, i0))) return r;
+    }
+    // ---- mask * spectrum -> inverse FFT -> OLA, in groups of whole streams that fit the scratch
+    int s0 = 0;
+    while (s0 < n_streams) {
+        int s1 = s0, imgs = 0;
+        size_t gmax = 0;
+        while (s1 < n_streams) {
+            const int tiles = (m.nfr[s1] + T - 1) / T;
+            if (imgs + tiles > c->B) break;
+            imgs += tiles;
+            gmax = std::max(gmax, (size_t)m.n[s1]);
+            s1++;
+        }
+        {
+            Timed t(c, 14);
+            IstftParams p{};
+            p.spec = c->d_spec; p.mask = c->d_mask; p.imgs = d_imgs; p.n_frames = d_nfr;
+            p.postwin = c->d_postwin; p.twiddle = c->d_twiddle; p.frames_out = c->d_frames;
+            for (int s = 0; s < S; s++) p.unaffected[s] = unaffected ? unaffected[s] : 0.1f;
+            p.T = T; p.F = c->F; p.S = S;
+            p.img_first = m.img0[s0]; p.n_img = imgs;
+            p.mask_stem_stride = c->NB; p.frames_stem_stride = c->B;
+            launch_istft(p, c->stream);
+            c->launches++;
+        }
+        {
+            Timed t(c, 15);
+            OlaParams p{};
+            p.frames = c->d_frames; p.stream_img0 = (const int*)(c->d_meta + o_i0); p.n_frames = d_nfr; p.n_samples = d_n;
+            p.out = (float* const*)(c->d_meta + o_out);
+            p.T = T; p.S = S; p.stream_first = s0; p.n_streams = s1 - s0; p.img_first = m.img0[s0];
+            p.frames_stem_stride = c->B; p.max_samples = (int)gmax; p.front_pad = front_pad;
+            launch_ola(p, c->stream);
+            c->launches++;
+        }
+        s0 = s1;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SRT_ERR_CUDA, "separate launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int srt_separate_device(srt_ctx* c, const float* const* d_pcmL, const float* const* d_pcmR, const size_t* n_samples,
+                                   int n_streams, const float* unaffected, float* const* d_stems_out)
+{
+    if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
+    if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    return separate_core(c, d_pcmL, d_pcmR, n_samples, n_streams, unaffected, d_stems_out, kFFT);
+}
+
+extern "C" int srt_separate_batch(srt_ctx* c, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
+                                  int n_streams, const float* unaffected, float* const* stems_out)
+{
+    if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
+    if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    size_t tot = 0;
+    for (int i = 0; i < n_streams; i++) tot += (n_samples[i] + 3) & ~(size_t)3;
+    if (tot * 2 > c->pcm_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->d_pcm) cudaFree(c->d_pcm);
+        c->pcm_cap = tot * 2;
+        CK(cudaMalloc((void**)&c->d_pcm, c->pcm_cap * 4));
+    }
+    if (tot * 2 * c->S > c->out_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->d_out) cudaFree(c->d_out);
+        c->out_cap = tot * 2 * c->S;
+        CK(cudaMalloc((void**)&c->d_out, c->out_cap * 4));
+    }
+    std::vector<const float*> dl(n_streams), dr(n_streams);
+    std::vector<float*> dout((size_t)n_streams * c->S * 2);
+    size_t off = 0;
+    {
+        Timed t(c, 16);
+        for (int i = 0; i < n_streams; i++) {
+            const size_t n = n_samples[i], np = (n + 3) & ~(size_t)3;
+            dl[i] = c->d_pcm + off * 2;
+            dr[i] = c->d_pcm + off * 2 + np;
+            CK(cudaMemcpyAsync((void*)dl[i], pcmL[i], n * 4, cudaMemcpyHostToDevice, c->stream));
+            CK(cudaMemcpyAsync((void*)dr[i], pcmR[i], n * 4, cudaMemcpyHostToDevice, c->stream));
+            for (int q = 0; q < c->S * 2; q++) dout[(size_t)i * c->S * 2 + q] = c->d_out + off * 2 * c->S + (size_t)q * np;
+            off += np;
+        }
+    }
+    int r = separate_core(c, dl.data(), dr.data(), n_samples, n_streams, unaffected, dout.data(), kFFT);
+    if (r) return r;
+    {
+        Timed t(c, 17);
+        for (int i = 0; i < n_streams; i++)
+            for (int q = 0; q < c->S * 2; q++)
+                CK(cudaMemcpyAsync(stems_out[(size_t)i * c->S * 2 + q], dout[(size_t)i * c->S * 2 + q], n_samples[i] * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// transforms for the tier-A shims (stft()/istft(), stftFix.c:363-579)
+// ------------------------------------------------------------------------------------------
+extern "C" size_t srt_stft_rows(size_t n) { return (n + kHop - 1) / kHop; }
+
+extern "C" int srt_stft_host(srt_ctx* c, const float* L, const float* R, size_t n, float* reL, float* imL, float* reR, float* imR)
+{
+    if (!c) return fail(SRT_ERR_STATE, "null context");
+    if (n < (size_t)kFFT) return fail(SRT_ERR_ARG, "stft needs at least 4096 samples");
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    const size_t rows = srt_stft_rows(n);
+    const int computed = (int)((n - kFFT + kHop / 4) / kHop) + 1;   // stftFix.c:377 + the final frame (:460-493)
+    const int cap = c->NB * c->T;                                    // rows the spectrum buffer holds
+    std::vector<float4> hs((size_t)std::min<size_t>(cap, rows) * kBins);
+    // device staging for the PCM
+    const size_t np = (n + 3) & ~(size_t)3;
+    if (np * 2 > c->pcm_cap) {
+        if (c->d_pcm) cudaFree(c->d_pcm);
+        c->pcm_cap = np * 2;
+        CK(cudaMalloc((void**)&c->d_pcm, c->pcm_cap * 4));
+    }
+    CK(cudaMemcpyAsync(c->d_pcm, L, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_pcm + np, R, n * 4, cudaMemcpyHostToDevice, c->stream));
+    for (size_t q = 0; q < rows * kFFT; q++) reL[q] = imL[q] = reR[q] = imR[q] = 0.0f;
+    // process in slabs of `cap` rows, each row its own single-frame "image"
+    for (size_t r0 = 0; r0 < (size_t)computed; r0 += cap) {
+        const int nr = (int)std::min<size_t>(cap, computed - r0);
+        const size_t o_pl = 0, o_pr = 8, o_n = 16, o_nfr = 20, o_img = 24, total_b = o_img + sizeof(ImgDesc) * nr;
+        int rr = ensure_meta(c, total_b);
+        if (rr) return rr;
+        CK(cudaStreamSynchronize(c->stream));
+        const float* pl = c->d_pcm;
+        const float* pr = c->d_pcm + np;
+        const int ni = (int)n, nf = computed;
+        std::memcpy(c->h_meta + o_pl, &pl, 8);
+        std::memcpy(c->h_meta + o_pr, &pr, 8);
+        std::memcpy(c->h_meta + o_n, &ni, 4);
+        std::memcpy(c->h_meta + o_nfr, &nf, 4);
+        ImgDesc* im = (ImgDesc*)(c->h_meta + o_img);
+        for (int i = 0; i < nr; i++) im[i] = ImgDesc{0, (int)r0 + i};
+        CK(cudaMemcpyAsync(c->d_meta, c->h_meta, total_b, cudaMemcpyHostToDevice, c->stream));
+        StftParams p{};
+        p.pcmL = (const float* const*)(c->d_meta + o_pl);
+        p.pcmR = (const float* const*)(c->d_meta + o_pr);
+        p.n_samples = (const int*)(c->d_meta + o_n);
+        p.n_frames = (const int*)(c->d_meta + o_nfr);
+        p.imgs = (const ImgDesc*)(c->d_meta + o_img);
+        p.window = c->d_window; p.twiddle = c->d_twiddle; p.spec = c->d_spec; p.mag = nullptr;
+        p.T = 1; p.F = 0; p.n_img = nr; p.front_pad = 0;
+        launch_stft(p, c->stream);
+        c->launches++;
+        CK(cudaMemcpyAsync(hs.data(), c->d_spec, (size_t)nr * kBins * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < nr; i++)
+            for (int k = 0; k < kBins; k++) {
+                const float4 v = hs[(size_t)i * kBins + k];
+                const size_t q = (r0 + i) * kFFT + k;
+                reL[q] = v.x; imL[q] = v.y; reR[q] = v.z; imR[q] = v.w;
+            }
+    }
+    return 0;
+}
+
+extern "C" int srt_istft_host(srt_ctx* c, const float* reL, const float* imL, const float* reR, const float* imR, size_t frames,
+                              float* outL, float* outR)
+{
+    if (!c) return fail(SRT_ERR_STATE, "null context");
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    const size_t out_n = frames * kHop + (kFFT - kHop);
+    const size_t cap = (size_t)c->B * c->T;   // frames the scratch holds
+    if (frames > cap || frames > (size_t)c->NB * c->T) return fail(SRT_ERR_CAPACITY, "istft of %zu frames exceeds context capacity %zu", frames, cap);
+    std::vector<float4> hs(frames * kBins);
+    for (size_t f = 0; f < frames; f++)
+        for (int k = 0; k < kBins; k++) hs[f * kBins + k] = make_float4(reL[f * kFFT + k], imL[f * kFFT + k], reR[f * kFFT + k], imR[f * kFFT + k]);
+    if (out_n * 2 > c->out_cap) {
+        if (c->d_out) cudaFree(c->d_out);
+        c->out_cap = out_n * 2;
+        CK(cudaMalloc((void**)&c->d_out, c->out_cap * 4));
+    }
+    const size_t o_out = 0, o_n = 16, o_nfr = 20, o_i0 = 24, o_img = 32, total_b = o_img + sizeof(ImgDesc) * frames;
+    int r = ensure_meta(c, total_b);
+    if (r) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    float* po[2] = {c->d_out, c->d_out + out_n};
+    const int ni = (int)out_n, nf = (int)frames, i0 = 0;
+    std::memcpy(c->h_meta + o_out, po, 16);
+    std::memcpy(c->h_meta + o_n, &ni, 4);
+    std::memcpy(c->h_meta + o_nfr, &nf, 4);
+    std::memcpy(c->h_meta + o_i0, &i0, 4);
+    ImgDesc* im = (ImgDesc*)(c->h_meta + o_img);
+    for (size_t i = 0; i < frames; i++) im[i] = ImgDesc{0, (int)i};
+    CK(cudaMemcpyAsync(c->d_meta, c->h_meta, total_b, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_spec, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    IstftParams p{};
+    p.spec = c->d_spec; p.mask = nullptr; p.imgs = (const ImgDesc*)(c->d_meta + o_img); p.n_frames = (const int*)(c->d_meta + o_nfr);
+    p.postwin = c->d_postwin; p.twiddle = c->d_twiddle; p.frames_out = c->d_frames;
+    p.T = 1; p.F = 0; p.S = 1; p.img_first = 0; p.n_img = (int)frames; p.mask_stem_stride = 0; p.frames_stem_stride = (int)cap;
+    launch_istft(p, c->stream);
+    OlaParams q{};
+    q.frames = c->d_frames; q.stream_img0 = (const int*)(c->d_meta + o_i0); q.n_frames = (const int*)(c->d_meta + o_nfr);
+    q.n_samples = (const int*)(c->d_meta + o_n); q.out = (float* const*)(c->d_meta + o_out);
+    q.T = 1; q.S = 1; q.stream_first = 0; q.n_streams = 1; q.img_first = 0; q.frames_stem_stride = (int)cap; q.max_samples = (int)out_n; q.front_pad = 0;
+    launch_ola(q, c->stream);
+    c->launches += 2;
+    CK(cudaMemcpyAsync(outL, c->d_out, out_n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(outR, c->d_out + out_n, out_n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------
+extern "C" long long srt_launch_count(const srt_ctx* c) { return c ? c->launches : 0; }
+extern "C" int srt_set_timing(srt_ctx* c, int enable)
+{
+    if (!c) return SRT_ERR_STATE;
+    c->timing = enable != 0;
+    return 0;
+}
+extern "C" int srt_last_timing(const srt_ctx* c, int which, float* ms_out)
+{
+    if (!c || !ms_out) return SRT_ERR_ARG;
+    cudaStreamSynchronize(c->stream);
+    float tot = 0.f;
+    for (const Span& s : c->spans)
+        if (s.cat == which) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) tot += ms;
+        }
+    *ms_out = tot;
+    return 0;
+}
+extern "C" int srt_synchronize(srt_ctx* c)
+{
+    if (!c) return SRT_ERR_STATE;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+extern "C" void* srt_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void srt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" long long srt_debug_tensor(srt_ctx* c, const char* name, float* dst, size_t max_floats)
+{
+    if (!c || !name || c->S == 0) return fail(SRT_ERR_STATE, "no context");
+    const float* src = nullptr;
+    int level = 0, ch = 0;
+    int idx = name[strlen(name) - 1] - '0';
+    if (!strncmp(name, "skip", 4) && idx >= 1 && idx <= 6) { src = c->E[idx]; level = idx; ch = kEnc[idx]; }
+    else if (!strncmp(name, "up", 2) && idx >= 1 && idx <= 5) { src = c->U[idx]; level = 6 - idx; ch = kDecOut[idx - 1]; }
+    else if (!strcmp(name, "up6")) { src = c->U[6]; level = 0; ch = 1; }
+    else return fail(SRT_ERR_ARG, "unknown tensor %s", name);
+    const int H = c->T >> level, W = c->F >> level, Bv = c->last_Bv;
+    const size_t per = (size_t)H * W * ch, need = per * c->S * Bv;
+    if (need > max_floats) return fail(SRT_ERR_CAPACITY, "buffer too small");
+    std::vector<float> h(per);
+    CK(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < c->S; s++)
+        for (int b = 0; b < Bv; b++) {
+            CK(cudaMemcpy(h.data(), src + ((size_t)s * c->B + b) * per, per * 4, cudaMemcpyDeviceToHost));
+            float* d = dst + ((size_t)s * Bv + b) * per;
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++)
+                    for (int k = 0; k < ch; k++) d[((size_t)k * H + y) * W + x] = h[((size_t)y * W + x) * ch + k];
+        }
+    return (long long)need;
+}

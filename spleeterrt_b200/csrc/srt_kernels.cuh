@@ -1,0 +1,153 @@
+// srt_kernels.cuh — parameter blocks shared by the host orchestration and the CUDA kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "srt_plan.h"
+
+namespace srt {
+
+// ---------------------------------------------------------------------------------------
+// Gather-GEMM layer launch parameters (tcgen05 kernel and SIMT verification kernel).
+// Image index n runs over S stems x B images, stem-major: n = s*B + b.
+// ---------------------------------------------------------------------------------------
+struct alignas(64) ConvParams {
+    CUtensorMap tmap[2];          // source activation tensors, dims {C, W, H, S*B}, box {32, tw, th, nb}, SW128
+    const float* src_ptr[2];      // same tensors as raw pointers (SIMT verification path)
+    int src_C[2];
+    const KBlock* kb;             // all phases back to back
+    int kb_off[4], nkb[4];
+    const float* w;               // packed weights, stem 0
+    size_t w_stem_stride;         // floats between stems
+    size_t w_phase_off[4];
+    int n_tile, n_tiles, phases;
+    int Hs, Ws;                   // tile-space extent
+    int B;                        // images per stem in the buffer layout (capacity)
+    int Bv;                       // images per stem actually present in this launch
+    int S;                        // stems
+    int tw, th, nb;
+    int tiles_x, tiles_y, tiles_n;
+    int cout;
+    // epilogue (Executable/spleeter.c:182-190 encoder, :240-247 decoder)
+    const float* bias;            // [S][cout]
+    const float* bn_scale;        // [S][cout]
+    const float* bn_offset;       // [S][cout]
+    int act[8];                   // srt::Act per stem (stemMode, spleeter.c:130-139)
+    int mode;                     // 0 encoder (raw + activated), 1 encoder last (raw only), 2 decoder
+    float* out_raw;               // encoder: NHWC [n][Hs][Ws][cout]   (conv + bias, the skip)
+    float* out_act;               // encoder: S2D  [n][Hs/2][Ws/2][4*cout]  act(scale*v+offset)
+    float* out_dec;               // decoder: NHWC [n][2Hs][2Ws][cout]  scale*act(v)+offset
+    int round_raw, round_act;     // round stored values to TF32 (consumer is a tensor-core layer)
+};
+
+// ---------------------------------------------------------------------------------------
+// SIMT edge layers
+// ---------------------------------------------------------------------------------------
+struct Down1Params {              // 5x5 s2 conv 2->16 on the magnitude image, spleeter.c:181-190
+    const float* mag;             // [B][T][F][2]
+    const float* w;               // [S][16][2][5][5] (reference order)
+    const float* bias;            // [S][16]
+    const float* bn_scale;        // [S][16]
+    const float* bn_offset;       // [S][16]
+    float* out_raw;               // [S*B][T/2][F/2][16]
+    float* out_act;               // S2D [S*B][T/4][F/4][64], TF32-rounded
+    int T, F, B, Bv, S;
+    int act[8];
+};
+
+struct Up6Params {                // 5x5 s2 transposed conv 32->1 + act + BN, spleeter.c:289-294
+    const float* skip;            // conv1 raw  [S*B][T/2][F/2][16]
+    const float* up;              // up5 output [S*B][T/2][F/2][16]
+    const float* w;               // [S][32][25]  (cin, kh*5+kw)
+    const float* bias;            // [S]
+    const float* bn_scale;        // [S]
+    const float* bn_offset;       // [S]
+    float* out;                   // [S*B][T][F]
+    int T, F, B, Bv, S;
+    int act[8];
+};
+
+struct Up7Params {                // 4x4 dilation-2 conv 1->2 + bias + sigmoid, spleeter.c:295-300
+    const float* in;              // [S*B][T][F]
+    const float* w;               // [S][2][16]
+    const float* bias;            // [S][2]
+    const float* lut;             // 1026-entry sigmoid table (Executable flavour) or nullptr (exact)
+    float* mask;                  // [S][mask_stem_stride images][T][F][2], first image of this launch = mask_img0
+    int T, F, B, Bv, S;
+    int mask_stem_stride, mask_img0;
+};
+
+// ---------------------------------------------------------------------------------------
+// Transforms
+// ---------------------------------------------------------------------------------------
+struct ImgDesc {                  // one T-frame tile of one stream
+    int stream;
+    int f0;                       // first frame of the tile within the stream
+};
+
+struct StftParams {
+    const float* const* pcmL;     // per stream device pointers (unpadded samples)
+    const float* const* pcmR;
+    const int* n_samples;         // per stream
+    const int* n_frames;          // per stream: padded_len / 1024 (stftFix.c:367)
+    const ImgDesc* imgs;          // [n_img]
+    const float* window;          // hann(i+1/2)/4096
+    const float2* twiddle;        // exp(-2 pi i m / 4096)
+    float4* spec;                 // [n_img][T][2049] (reL, imL, reR, imR) in the reference's convention
+    float* mag;                   // [n_img][T][F][2]
+    int T, F, n_img;
+    int front_pad;                // 4096 zeros in front (main.c:767) or 0 (raw stft())
+};
+
+struct IstftParams {
+    const float4* spec;           // [all images][T][2049]
+    const float* mask;            // [S][mask_stem_stride images][T][F][2] or nullptr (no masking)
+    const ImgDesc* imgs;          // [all images]
+    const int* n_frames;          // per stream
+    const float* postwin;         // (2/3) hann(i+1/2)
+    const float2* twiddle;
+    float2* frames_out;           // scratch [S][frames_stem_stride images][T][4096] (l, r) windowed time frames
+    float unaffected[8];          // per stem weight for bins >= F (main.c:486-493, Spleeter4Stems.c:73,281)
+    int T, F, S;
+    int img_first, n_img;         // images [img_first, img_first + n_img) are processed; scratch index is relative
+    int mask_stem_stride, frames_stem_stride;
+};
+
+struct OlaParams {
+    const float2* frames;         // scratch, see IstftParams
+    const int* stream_img0;       // per stream: first image index (global)
+    const int* n_frames;          // per stream
+    const int* n_samples;         // per stream
+    float* const* out;            // [stream][S*2] device pointers to planar outputs of n_samples
+    int T, S;
+    int stream_first, n_streams;  // streams [stream_first, stream_first + n_streams)
+    int img_first;                // first image of the scratch
+    int frames_stem_stride;
+    int max_samples;
+    int front_pad;
+};
+
+// launchers (defined in the .cu files)
+void launch_conv_tc(const ConvParams& p, cudaStream_t st);
+void launch_conv_simt(const ConvParams& p, cudaStream_t st);
+void launch_down1(const Down1Params& p, cudaStream_t st);
+void launch_up6(const Up6Params& p, cudaStream_t st);
+void launch_up7(const Up7Params& p, cudaStream_t st);
+void launch_stft(const StftParams& p, cudaStream_t st);
+void launch_istft(const IstftParams& p, cudaStream_t st);
+void launch_ola(const OlaParams& p, cudaStream_t st);
+size_t conv_tc_smem_bytes(int n_tile, int* stages_out);
+
+__device__ __forceinline__ float apply_act(int act, float x)
+{
+    switch (act) {
+    case ACT_LEAKY: return x >= 0.0f ? x : 0.2f * x;                          // spleeter.c:43-46
+    case ACT_RELU: return x >= 0.0f ? x : 0.0f;                               // spleeter.c:47-50
+    case ACT_ELU_CLAMP: return x >= 0.0f ? x : (x < -15.0f ? -1.0f : expf(x) - 1.0f);   // spleeter.c:51-56
+    case ACT_ELU: return x >= 0.0f ? x : expf(x) - 1.0f;                      // VST/Source/spleeter.c:74-77
+    default: return x;
+    }
+}
+
+}  // namespace srt

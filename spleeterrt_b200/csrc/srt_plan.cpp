@@ -1,0 +1,196 @@
+// srt_plan.cpp — see srt_plan.h.  Plain host C++.
+#include "srt_plan.h"
+
+#include <cstring>
+
+namespace srt {
+
+static const int kEnc[7] = {2, 16, 32, 64, 128, 256, 512};
+static const int kDecIn[6] = {512, 512, 256, 128, 64, 32};
+static const int kDecOut[6] = {256, 128, 64, 32, 16, 1};
+
+CoeffLayout coeff_layout()
+{
+    CoeffLayout L{};
+    size_t p = 0;
+    for (int i = 0; i < 6; i++) {
+        L.down_w[i] = p; p += (size_t)25 * kEnc[i] * kEnc[i + 1];
+        L.down_b[i] = p; p += kEnc[i + 1];
+        L.down_bn[i] = p;
+        if (i < 5) p += 2 * kEnc[i + 1];
+    }
+    for (int i = 0; i < 6; i++) {
+        L.up_w[i] = p; p += (size_t)25 * kDecIn[i] * kDecOut[i];
+        L.up_b[i] = p; p += kDecOut[i];
+        L.up_bn[i] = p; p += 2 * kDecOut[i];
+    }
+    L.w7 = p; p += 32;
+    L.b7 = p; p += 2;
+    return L;
+}
+
+float round_tf32(float x)
+{
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;   // inf / nan untouched
+    u = (u + 0x1000u) & ~0x1fffu;                      // round to nearest, ties away (cvt.rna.tf32)
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+static void choose_tile(int W, int H, int n_img, int& tw, int& th, int& nb)
+{
+    long best = -1;
+    for (int w = 128; w >= 1; w >>= 1)
+        for (int h = 128 / w; h >= 1; h >>= 1) {
+            int b = 128 / (w * h);
+            long cost = (long)ceil_div(W, w) * w * ceil_div(H, h) * h * ceil_div(n_img, b) * b;
+            if (best < 0 || cost < best) { best = cost; tw = w; th = h; nb = b; }
+        }
+}
+
+// stride-2 tap kh of the encoder -> (S2D row offset, row parity):  input row 2*oh + kh - 1
+static void enc_tap(int k, int& d, int& par)
+{
+    static const int dd[5] = {-1, 0, 0, 1, 1}, pp[5] = {1, 0, 1, 0, 1};
+    d = dd[k];
+    par = pp[k];
+}
+
+// transposed-conv taps for output parity `par`: output o = 2h + kh - 1 (im2col_dilated.c:57-58)
+static int dec_taps(int par, int kh[3], int dy[3])
+{
+    if (par == 0) { kh[0] = 1; dy[0] = 0; kh[1] = 3; dy[1] = -1; return 2; }
+    kh[0] = 0; dy[0] = 1; kh[1] = 2; dy[1] = 0; kh[2] = 4; dy[2] = -1;
+    return 3;
+}
+
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img)
+{
+    std::vector<LayerPlan> plans;
+    // ---- encoder: down2 .. down6 --------------------------------------------------------
+    for (int i = 1; i <= 5; i++) {
+        LayerPlan L{};
+        L.index = i - 1;
+        L.transposed = false;
+        L.cin = kEnc[i];
+        L.cout = kEnc[i + 1];
+        L.Hs = g.T >> (i + 1);
+        L.Ws = g.F >> (i + 1);
+        L.phases = 1;
+        L.nsrc = 1;
+        L.src[0] = SrcDesc{4 * L.cin, L.Ws, L.Hs};
+        L.n_tile = L.cout > 256 ? 256 : L.cout;
+        L.n_tiles = L.cout / L.n_tile;
+        choose_tile(L.Ws, L.Hs, n_img, L.tw, L.th, L.nb);
+        if (L.cin >= 32) {
+            for (int kh = 0; kh < 5; kh++)
+                for (int kw = 0; kw < 5; kw++) {
+                    int dy, py, dx, px;
+                    enc_tap(kh, dy, py);
+                    enc_tap(kw, dx, px);
+                    for (int c0 = 0; c0 < L.cin; c0 += kKB) {
+                        L.kb[0].push_back(KBlock{0, (int8_t)dy, (int8_t)dx, 0, (py * 2 + px) * L.cin + c0});
+                        for (int j = 0; j < kKB; j++) L.kelem[0].push_back(KElem{c0 + j, (int8_t)kh, (int8_t)kw});
+                    }
+                }
+        } else {
+            // cin == 16: the two column parities of one S2D pixel are 32 contiguous channels, so
+            // taps (kw=1,kw=2) and (kw=3,kw=4) pair up; kw=0 pairs with a zero slab.
+            for (int kh = 0; kh < 5; kh++) {
+                int dy, py;
+                enc_tap(kh, dy, py);
+                for (int xg = -1; xg <= 1; xg++) {
+                    const int kwA = 2 * xg + 1, kwB = 2 * xg + 2;   // px = 0 slab, px = 1 slab
+                    L.kb[0].push_back(KBlock{0, (int8_t)dy, (int8_t)xg, 0, py * 2 * L.cin});
+                    for (int j = 0; j < kKB; j++) {
+                        const int kw = j < 16 ? kwA : kwB;
+                        const int c = j & 15;
+                        L.kelem[0].push_back(kw < 0 ? KElem{-1, 0, 0} : KElem{c, (int8_t)kh, (int8_t)kw});
+                    }
+                }
+            }
+        }
+        plans.push_back(L);
+    }
+    // ---- decoder: up1 .. up5 ------------------------------------------------------------
+    for (int d = 0; d < 5; d++) {
+        LayerPlan L{};
+        L.index = 5 + d;
+        L.transposed = true;
+        L.cin = kDecIn[d];
+        L.cout = kDecOut[d];
+        L.Hs = g.T >> (6 - d);
+        L.Ws = g.F >> (6 - d);
+        L.phases = 4;
+        if (d == 0) {
+            L.nsrc = 1;
+            L.src[0] = SrcDesc{512, L.Ws, L.Hs};
+        } else {
+            L.nsrc = 2;
+            L.src[0] = SrcDesc{L.cin / 2, L.Ws, L.Hs};   // skip (raw conv + bias)
+            L.src[1] = SrcDesc{L.cin / 2, L.Ws, L.Hs};   // previous decoder output
+        }
+        L.n_tile = L.cout;
+        L.n_tiles = 1;
+        choose_tile(L.Ws, L.Hs, n_img, L.tw, L.th, L.nb);
+        for (int po = 0; po < 2; po++)
+            for (int qo = 0; qo < 2; qo++) {
+                const int p = po * 2 + qo;
+                int khs[3], dys[3], kws[3], dxs[3];
+                const int nh = dec_taps(po, khs, dys), nw = dec_taps(qo, kws, dxs);
+                for (int a = 0; a < nh; a++)
+                    for (int b = 0; b < nw; b++)
+                        for (int s = 0; s < L.nsrc; s++)
+                            for (int c0 = 0; c0 < L.src[s].C; c0 += kKB) {
+                                L.kb[p].push_back(KBlock{(int8_t)s, (int8_t)dys[a], (int8_t)dxs[b], 0, c0});
+                                const int base = (s ? L.src[0].C : 0) + c0;
+                                for (int j = 0; j < kKB; j++)
+                                    L.kelem[p].push_back(KElem{base + j, (int8_t)khs[a], (int8_t)kws[b]});
+                            }
+            }
+        plans.push_back(L);
+    }
+    for (auto& L : plans) {
+        size_t off = 0;
+        for (int p = 0; p < L.phases; p++) {
+            L.w_phase_off[p] = off;
+            off += (size_t)L.n_tiles * L.kb[p].size() * L.n_tile * kKB;
+        }
+        L.w_floats_per_stem = off;
+    }
+    return plans;
+}
+
+void pack_layer(const LayerPlan& L, const float* coeff, float* out)
+{
+    const CoeffLayout cl = coeff_layout();
+    const float* w = coeff + (L.transposed ? cl.up_w[L.index - 5] : cl.down_w[L.index + 1]);
+    for (int p = 0; p < L.phases; p++) {
+        const size_t nkb = L.kb[p].size();
+        for (int nt = 0; nt < L.n_tiles; nt++)
+            for (size_t kb = 0; kb < nkb; kb++) {
+                float* blk = out + L.w_phase_off[p] + ((size_t)nt * nkb + kb) * L.n_tile * kKB;
+                for (int n = 0; n < L.n_tile; n++) {
+                    const int o = nt * L.n_tile + n;
+                    for (int j = 0; j < kKB; j++) {
+                        const KElem e = L.kelem[p][kb * kKB + j];
+                        float v = 0.0f;
+                        if (e.cin >= 0) {
+                            const size_t idx = L.transposed
+                                ? (((size_t)e.cin * L.cout + o) * 5 + e.kh) * 5 + e.kw      // [I][O][kh][kw]
+                                : (((size_t)o * L.cin + e.cin) * 5 + e.kh) * 5 + e.kw;     // [O][I][kh][kw]
+                            v = round_tf32(w[idx]);
+                        }
+                        blk[swz128_index(n, j)] = v;
+                    }
+                }
+            }
+    }
+}
+
+}  // namespace srt

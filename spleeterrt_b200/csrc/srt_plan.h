@@ -1,0 +1,100 @@
+// srt_plan.h — host-side description of the U-Net as a sequence of "gather-GEMM" layers.
+//
+// Every 5x5 stride-2 convolution (Executable/spleeter.c:96-100, im2col_dilated.c:10-33) and
+// every 5x5 stride-2 transposed convolution (spleeter.c:73-78, im2col_dilated.c:42-65) of
+// the reference is re-expressed as   D[pixel, cout] = sum over k-blocks  A_kb[pixel, 32] * W_kb[cout, 32]^T
+// where each k-block is one 32-channel slab of the input read at a whole-pixel offset
+// (dy, dx) of a *stride-1* window:
+//   * encoder layers read their input in space-to-depth form (a 2x2 block of input pixels is
+//     one "S2D pixel" with 4*Cin channels), which turns the stride-2 taps into stride-1 taps;
+//   * decoder layers are split in the 4 output-pixel parities ("phases"), each of which is a
+//     stride-1 convolution with 2 or 3 taps per axis over [skip | up] (never concatenated).
+// The same tables drive the tcgen05 kernel, the SIMT verification kernel and the CPU model
+// used by the host-logic tests.  Plain C++ (no CUDA) so it can be unit-tested on the CPU.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#if defined(__CUDACC__)
+#define SRT_HD __host__ __device__
+#else
+#define SRT_HD
+#endif
+
+namespace srt {
+
+constexpr int kFFT = 4096;
+constexpr int kHop = 1024;
+constexpr int kBins = 2049;
+constexpr int kCoeffFloats = 9822725;   // sizeof(spleeterCoeff)/4, Executable/spleeter.h:5-31
+constexpr int kKB = 32;                 // channels per k-block (= one 128-byte swizzle row of fp32)
+constexpr int kTileM = 128;             // pixels per CTA tile (UMMA M)
+
+enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_ELU_CLAMP = 3, ACT_ELU = 4 };
+
+// One k-block: which source tensor, which whole-pixel offset, which channel offset.
+struct KBlock {
+    int8_t src;      // 0 or 1 (decoder: 0 = skip tensor, 1 = up tensor)
+    int8_t dy, dx;   // offset in tile-space pixels
+    int8_t pad;
+    int32_t c_off;   // channel coordinate in the source tensor (multiple of 32, or of 16 for paired taps)
+};
+
+// For the weight packer: where k-element j of a k-block comes from.
+struct KElem {
+    int32_t cin;     // input channel in the reference's (concatenated) numbering, -1 = zero
+    int8_t kh, kw;
+};
+
+struct SrcDesc {     // a source activation tensor as the TMA sees it: [n][H][W][C] fp32
+    int C, W, H;
+};
+
+struct LayerPlan {
+    // identity
+    int index;            // 0..4 = down2..down6, 5..9 = up1..up5
+    bool transposed;
+    int cin, cout;        // reference channel counts (cin = concatenated for the decoder)
+    // tile space: encoder = output pixels, decoder = input-resolution pixels (per phase)
+    int Hs, Ws;
+    int tw, th, nb;       // tile = nb images x th rows x tw cols, product 128
+    int n_tile;           // UMMA N per CTA
+    int n_tiles;          // cout / n_tile
+    int phases;           // 1 or 4
+    int nsrc;
+    SrcDesc src[2];
+    std::vector<KBlock> kb[4];          // per phase
+    std::vector<KElem> kelem[4];        // per phase, 32 per k-block
+    // weights blob: [phase][n_tile_idx][kb][n_tile*32 floats], pre-swizzled (see pack_layer)
+    size_t w_floats_per_stem;
+    size_t w_phase_off[4];              // float offset of each phase inside the per-stem blob
+};
+
+struct NetGeom {
+    int T, F;             // image height (time frames) and width (frequency bins), multiples of 64
+};
+
+// Offsets (in floats) into one spleeterCoeff blob.
+struct CoeffLayout {
+    size_t down_w[6], down_b[6], down_bn[6];   // down_bn[5] unused (no BN on down6)
+    size_t up_w[6], up_b[6], up_bn[6];
+    size_t w7, b7;
+};
+CoeffLayout coeff_layout();
+
+// Build the 10 tensor-core layers for a T x F image and a batch of n_img images per launch.
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img);
+
+// Pack one stem's weights for a layer into the k-block-major, 128B-swizzled layout the MMA
+// B operand is read from.  `coeff` is one spleeterCoeff blob.  Values are rounded to TF32
+// (round-to-nearest, ties away) so fp32 `.dat` weights behave like cvt.rna; fp16-origin
+// weights are exactly representable and pass through unchanged.
+void pack_layer(const LayerPlan& L, const float* coeff, float* out);
+
+float round_tf32(float x);
+
+// index of (row n, k-element j) inside a swizzled [rows][32] fp32 block
+SRT_HD inline int swz128_index(int row, int j) { return row * 32 + ((((j >> 2) ^ (row & 7)) << 2) | (j & 3)); }
+
+}  // namespace srt

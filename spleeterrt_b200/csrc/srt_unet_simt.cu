@@ -1,0 +1,269 @@
+// srt_unet_simt.cu — the HBM-bound edge layers of the U-Net as SIMT kernels (down1, up6, up7)
+// plus a slow SIMT evaluation of the gather-GEMM layers that consumes exactly the same
+// tables / packed weights / activation layouts as the tcgen05 kernel.  The latter is a
+// verification aid (SRT_CONV_IMPL=simt), not a CPU fallback: everything here runs on the GPU.
+#include "srt_epilogue.cuh"
+#include "srt_kernels.cuh"
+#include "srt_ptx.cuh"
+
+namespace srt {
+
+// =========================================================================================
+// SIMT gather-GEMM (verification path)
+// =========================================================================================
+__global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ ConvParams p)
+{
+    const int m = threadIdx.x;
+    const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+    const int nt = blockIdx.y % p.n_tiles, phase = blockIdx.y / p.n_tiles;
+    const int s = blockIdx.z / p.tiles_n, tz = blockIdx.z % p.tiles_n;
+    const int x = m % p.tw, y = (m / p.tw) % p.th, nn = m / (p.tw * p.th);
+    const int X = tx * p.tw + x, Y = ty * p.th + y, b = tz * p.nb + nn;
+    const bool valid = X < p.Ws && Y < p.Hs && b < p.Bv;
+    const int n = s * p.B + b;
+    const KBlock* kbt = p.kb + p.kb_off[phase];
+    const int nkb = p.nkb[phase];
+    const float* wbase = p.w + (size_t)s * p.w_stem_stride + p.w_phase_off[phase] + (size_t)nt * nkb * p.n_tile * kKB;
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+        for (int k = 0; k < nkb; k++) {
+            const KBlock kb = kbt[k];
+            const int yy = Y + kb.dy, xx = X + kb.dx;
+            if (!valid || yy < 0 || yy >= p.Hs || xx < 0 || xx >= p.Ws) continue;   // zero padding
+            const int C = p.src_C[kb.src];
+            const float* a = p.src_ptr[kb.src] + (((size_t)n * p.Hs + yy) * p.Ws + xx) * C + kb.c_off;
+            const float* wb = wbase + (size_t)k * p.n_tile * kKB;
+            for (int j = 0; j < kKB; j++) {
+                const float av = a[j];
+#pragma unroll
+                for (int i = 0; i < 16; i++) acc[i] = fmaf(av, wb[swz128_index(c0 + i, j)], acc[i]);
+            }
+        }
+        if (valid) epilogue16(p, s, n, Y, X, phase, nt * p.n_tile + c0, acc);
+    }
+}
+
+void launch_conv_simt(const ConvParams& p, cudaStream_t st)
+{
+    dim3 grid(p.tiles_x * p.tiles_y, p.n_tiles * p.phases, p.S * p.tiles_n);
+    conv_simt_kernel<<<grid, 128, 0, st>>>(p);
+}
+
+// =========================================================================================
+// down1: 5x5 stride-2 conv, 2 -> 16 channels, on the magnitude image (spleeter.c:181-190).
+// Input row 2*oh + kh - 1, col 2*ow + kw - 1 (im2col_dilated.c:19-27).  Writes the raw skip
+// (conv + bias, fp32) and the activated feature in space-to-depth form, TF32-rounded, which is
+// what down2's tensor-core kernel reads.
+// =========================================================================================
+constexpr int D1_TW = 32, D1_TH = 8;
+constexpr int D1_PW = 2 * D1_TW + 3, D1_PH = 2 * D1_TH + 3;
+
+__global__ void __launch_bounds__(D1_TW* D1_TH) down1_kernel(const Down1Params p)
+{
+    __shared__ float2 patch[D1_PH][D1_PW + 1];
+    __shared__ __align__(16) float wsm[25 * 2 * 16];   // [tap][cin][cout]
+    const int s = blockIdx.z / p.Bv, b = blockIdx.z % p.Bv, n = s * p.B + b;
+    const int Ho = p.T / 2, Wo = p.F / 2;
+    const int ow0 = blockIdx.x * D1_TW, oh0 = blockIdx.y * D1_TH;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 800; i += blockDim.x) {
+        const int o = i & 15, c = (i >> 4) & 1, tap = i >> 5;
+        wsm[i] = p.w[((size_t)s * 16 + o) * 50 + c * 25 + tap];   // reference layout [O][I][kh][kw]
+    }
+    const float2* img = reinterpret_cast<const float2*>(p.mag) + (size_t)b * p.T * p.F;
+    for (int i = tid; i < D1_PH * D1_PW; i += blockDim.x) {
+        const int r = i / D1_PW, c = i % D1_PW;
+        const int ih = 2 * oh0 - 1 + r, iw = 2 * ow0 - 1 + c;
+        float2 v = make_float2(0.f, 0.f);
+        if (ih >= 0 && ih < p.T && iw >= 0 && iw < p.F) v = img[(size_t)ih * p.F + iw];
+        patch[r][c] = v;
+    }
+    __syncthreads();
+    const int tx = tid % D1_TW, ty = tid / D1_TW;
+    const int ow = ow0 + tx, oh = oh0 + ty;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+#pragma unroll
+    for (int kh = 0; kh < 5; kh++)
+#pragma unroll
+        for (int kw = 0; kw < 5; kw++) {
+            const float2 v = patch[2 * ty + kh][2 * tx + kw];
+            const float4* wl = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 0) * 16]);
+            const float4* wr = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 1) * 16]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 a = wl[q], c = wr[q];
+                acc[4 * q + 0] = fmaf(a.x, v.x, fmaf(c.x, v.y, acc[4 * q + 0]));
+                acc[4 * q + 1] = fmaf(a.y, v.x, fmaf(c.y, v.y, acc[4 * q + 1]));
+                acc[4 * q + 2] = fmaf(a.z, v.x, fmaf(c.z, v.y, acc[4 * q + 2]));
+                acc[4 * q + 3] = fmaf(a.w, v.x, fmaf(c.w, v.y, acc[4 * q + 3]));
+            }
+        }
+    if (ow >= Wo || oh >= Ho) return;
+    float raw[16], av[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float t = acc[i] + p.bias[s * 16 + i];
+        raw[i] = t;
+        av[i] = ptx::rna_tf32(apply_act(p.act[s], p.bn_scale[s * 16 + i] * t + p.bn_offset[s * 16 + i]));
+    }
+    float4* d0 = reinterpret_cast<float4*>(p.out_raw + (((size_t)n * Ho + oh) * Wo + ow) * 16);
+    float4* d1 = reinterpret_cast<float4*>(
+        p.out_act + ((((size_t)n * (Ho / 2) + oh / 2) * (Wo / 2) + ow / 2) * 4 + (oh & 1) * 2 + (ow & 1)) * 16);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        d0[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
+        d1[q] = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
+    }
+}
+
+void launch_down1(const Down1Params& p, cudaStream_t st)
+{
+    dim3 grid((p.F / 2 + D1_TW - 1) / D1_TW, (p.T / 2 + D1_TH - 1) / D1_TH, p.S * p.Bv);
+    down1_kernel<<<grid, D1_TW * D1_TH, 0, st>>>(p);
+}
+
+// =========================================================================================
+// up6: 5x5 stride-2 transposed conv, [skip1 | up5] (32 ch) -> 1 ch, then act, then BN
+// (spleeter.c:289-294).  Output (2h+kh-1, 2w+kw-1) (im2col_dilated.c:57-58, 37-40).
+// One thread per input-resolution pixel produces its 2x2 output block.
+// =========================================================================================
+constexpr int U6_TW = 32, U6_TH = 8;
+constexpr int U6_PW = U6_TW + 2, U6_PH = U6_TH + 2, U6_PS = U6_PW + 1;
+
+__global__ void __launch_bounds__(U6_TW* U6_TH) up6_kernel(const Up6Params p)
+{
+    extern __shared__ float u6_smem[];
+    float* patch = u6_smem;                          // [32][U6_PH][U6_PS]
+    float* wsm = u6_smem + 32 * U6_PH * U6_PS;       // [32][25] (+pad)
+    const int s = blockIdx.z / p.Bv, n = s * p.B + blockIdx.z % p.Bv;
+    const int H = p.T / 2, W = p.F / 2;
+    const int x0 = blockIdx.x * U6_TW, y0 = blockIdx.y * U6_TH;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 32 * 25; i += blockDim.x) wsm[i] = p.w[(size_t)s * 800 + i];
+    // fill the patch: 16 channels from the skip, 16 from up5; one float4 per (pixel, quarter)
+    for (int i = tid; i < U6_PH * U6_PW * 8; i += blockDim.x) {
+        const int q = i & 7, pix = i >> 3;
+        const int r = pix / U6_PW, c = pix % U6_PW;
+        const int yy = y0 - 1 + r, xx = x0 - 1 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float* src = (q < 4 ? p.skip : p.up) + (((size_t)n * H + yy) * W + xx) * 16 + (q & 3) * 4;
+            v = *reinterpret_cast<const float4*>(src);
+        }
+        const int ch = q * 4;
+        patch[((ch + 0) * U6_PH + r) * U6_PS + c] = v.x;
+        patch[((ch + 1) * U6_PH + r) * U6_PS + c] = v.y;
+        patch[((ch + 2) * U6_PH + r) * U6_PS + c] = v.z;
+        patch[((ch + 3) * U6_PH + r) * U6_PS + c] = v.w;
+    }
+    __syncthreads();
+    const int tx = tid % U6_TW, ty = tid / U6_TW;
+    float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+    for (int c = 0; c < 32; c++) {
+        float nb[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) nb[a][b] = patch[(c * U6_PH + ty + a) * U6_PS + tx + b];   // (dy,dx) = (a-1,b-1)
+        const float* w = wsm + c * 25;
+        // output row parity 0: kh=1 (dy=0), kh=3 (dy=-1); parity 1: kh=0 (dy=+1), kh=2 (dy=0), kh=4 (dy=-1)
+        // same for columns.  w index = kh*5 + kw.
+#define TAP(kh, kw, dy, dx) (w[(kh) * 5 + (kw)] * nb[(dy) + 1][(dx) + 1])
+        o00 += TAP(1, 1, 0, 0) + TAP(1, 3, 0, -1) + TAP(3, 1, -1, 0) + TAP(3, 3, -1, -1);
+        o01 += TAP(1, 0, 0, 1) + TAP(1, 2, 0, 0) + TAP(1, 4, 0, -1) + TAP(3, 0, -1, 1) + TAP(3, 2, -1, 0) + TAP(3, 4, -1, -1);
+        o10 += TAP(0, 1, 1, 0) + TAP(0, 3, 1, -1) + TAP(2, 1, 0, 0) + TAP(2, 3, 0, -1) + TAP(4, 1, -1, 0) + TAP(4, 3, -1, -1);
+        o11 += TAP(0, 0, 1, 1) + TAP(0, 2, 1, 0) + TAP(0, 4, 1, -1) + TAP(2, 0, 0, 1) + TAP(2, 2, 0, 0) + TAP(2, 4, 0, -1) +
+               TAP(4, 0, -1, 1) + TAP(4, 2, -1, 0) + TAP(4, 4, -1, -1);
+#undef TAP
+    }
+    const int X = x0 + tx, Y = y0 + ty;
+    if (X >= W || Y >= H) return;
+    const float bias = p.bias[s], sc = p.bn_scale[s], of = p.bn_offset[s];
+    float2 r0, r1;
+    r0.x = sc * apply_act(p.act[s], o00 + bias) + of;
+    r0.y = sc * apply_act(p.act[s], o01 + bias) + of;
+    r1.x = sc * apply_act(p.act[s], o10 + bias) + of;
+    r1.y = sc * apply_act(p.act[s], o11 + bias) + of;
+    float* dst = p.out + ((size_t)n * p.T + 2 * Y) * p.F + 2 * X;
+    *reinterpret_cast<float2*>(dst) = r0;
+    *reinterpret_cast<float2*>(dst + p.F) = r1;
+}
+
+void launch_up6(const Up6Params& p, cudaStream_t st)
+{
+    dim3 grid((p.F / 2 + U6_TW - 1) / U6_TW, (p.T / 2 + U6_TH - 1) / U6_TH, p.S * p.Bv);
+    const size_t smem = (32 * U6_PH * U6_PS + 32 * 25) * sizeof(float);
+    up6_kernel<<<grid, U6_TW * U6_TH, smem, st>>>(p);
+}
+
+// =========================================================================================
+// up7: 4x4, dilation 2, stride 1 conv 1 -> 2 (rows t + 2kh - 3, cols f + 2kw - 3; spleeter.c:156,295)
+// + bias + sigmoid (LUT flavour spleeter.c:29-42 or exact VST/Source/spleeter.c:56-65).
+// =========================================================================================
+constexpr int U7_TW = 64, U7_TH = 8;
+
+__device__ __forceinline__ float sigmoid_lut(const float* __restrict__ tbl, float x)
+{
+    // Same float operations, in the same order, as fastSigmoid (spleeter.c:30-42).
+    const float step = 0.01367188f;
+    if (x > 7.0f) return 1.0f;
+    if (x < -7.0f) return 0.0f;
+    const int idx = (int)(short)__fdiv_rn(__fadd_rn(x, 7.0f), step);
+    const float x1 = __fadd_rn(-7.0f, __fmul_rn(step, (float)idx));
+    const float t0 = __ldg(tbl + idx), t1 = __ldg(tbl + idx + 1);
+    const float den = __fsub_rn(__fadd_rn(-7.0f, __fmul_rn(step, (float)(idx + 1))), x1);
+    return __fadd_rn(t0, __fmul_rn(__fdiv_rn(__fsub_rn(t1, t0), den), __fsub_rn(x, x1)));
+}
+
+__global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const Up7Params p)
+{
+    __shared__ float tile[U7_TH + 6][U7_TW + 6 + 2];
+    __shared__ float wsm[32 + 2];
+    const int s = blockIdx.z / p.Bv, b = blockIdx.z % p.Bv, n = s * p.B + b;
+    const int f0 = blockIdx.x * U7_TW, t0 = blockIdx.y * U7_TH;
+    const int tid = threadIdx.x;
+    if (tid < 32) wsm[tid] = p.w[s * 32 + tid];
+    if (tid < 2) wsm[32 + tid] = p.bias[s * 2 + tid];
+    const float* img = p.in + (size_t)n * p.T * p.F;
+    for (int i = tid; i < (U7_TH + 6) * (U7_TW + 6); i += blockDim.x) {
+        const int r = i / (U7_TW + 6), c = i % (U7_TW + 6);
+        const int t = t0 - 3 + r, f = f0 - 3 + c;
+        tile[r][c] = (t >= 0 && t < p.T && f >= 0 && f < p.F) ? img[(size_t)t * p.F + f] : 0.0f;
+    }
+    __syncthreads();
+    const int tx = tid % U7_TW, ty = tid / U7_TW;
+    const int f = f0 + tx, t = t0 + ty;
+    if (f >= p.F || t >= p.T) return;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 4; kh++)
+#pragma unroll
+        for (int kw = 0; kw < 4; kw++) {
+            const float v = tile[ty + 2 * kh][tx + 2 * kw];
+            a0 = fmaf(wsm[kh * 4 + kw], v, a0);
+            a1 = fmaf(wsm[16 + kh * 4 + kw], v, a1);
+        }
+    a0 += wsm[32];
+    a1 += wsm[33];
+    float2 m;
+    if (p.lut) {
+        m.x = sigmoid_lut(p.lut, a0);
+        m.y = sigmoid_lut(p.lut, a1);
+    } else {
+        m.x = a0 >= 0.f ? 1.0f / (1.0f + expf(-a0)) : expf(a0) / (1.0f + expf(a0));
+        m.y = a1 >= 0.f ? 1.0f / (1.0f + expf(-a1)) : expf(a1) / (1.0f + expf(a1));
+    }
+    reinterpret_cast<float2*>(p.mask)[(((size_t)s * p.mask_stem_stride + p.mask_img0 + b) * p.T + t) * p.F + f] = m;
+}
+
+void launch_up7(const Up7Params& p, cudaStream_t st)
+{
+    dim3 grid((p.F + U7_TW - 1) / U7_TW, (p.T + U7_TH - 1) / U7_TH, p.S * p.Bv);
+    up7_kernel<<<grid, U7_TW * U7_TH, 0, st>>>(p);
+}
+
+}  // namespace srt
