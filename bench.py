@@ -1,0 +1,308 @@
+#!/usr/bin/env python3
+"""bench.py — 4-stem 44.1 kHz stereo separation throughput on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU path (oracle/_ref)
+
+A step = one pass of the whole hot path (STFT framer -> 4 U-Nets -> mask*spectrum -> iSTFT/OLA)
+over a batch of `--streams` synthetic 10 s stereo streams per GPU (T=512, F=1024: BASELINE.json
+configs[1] shape, batched as configs[2] does).  `value` is device-resident throughput (inputs in
+HBM when the clock starts), `e2e` goes through the host-pointer C-ABI call with pinned host
+buffers, H2D and D2H inside the timed region.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SECONDS = 10.0
+N_SAMPLES = 441000
+T, F = 512, 1024
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def start(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.th:
+            self.th.join(timeout=6)
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=0)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def reference_arm(args, rank):
+    """The reference's own CPU implementation of the path (oracle/_ref build of the reference's C
+    sources, naive CPU_GEMM backend), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    have_ref = O.have_ref()
+    nets = O.four_stem_weights()
+    L, R = O.synth_pcm(0, n=N_SAMPLES)
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+
+    def step():
+        if have_ref:
+            return O.ref_exec().separate(nets, L, R, T, F, unaffected=0.1)
+        return O.separate(nets, L, R, T, F, unaffected=0.1)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    frames = N_SAMPLES and (4096 * ((N_SAMPLES + 4095) // 4096) + 8192) // 1024
+    rtf = SECONDS / dt
+    kind = "reference" if have_ref else "port"
+    line = {"impl": "reference", "metric": "realtime_factor_4stem_44k1_stereo", "value": rtf, "unit": "x_realtime",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "frames_per_sec": frames / dt,
+            "config": {"workload": "4-stem 44.1kHz stereo, T=512 F=1024, one 10 s stream per step (bounded sample of the GPU arm's batch)",
+                       "streams_per_step": 1, "seconds_per_stream": SECONDS},
+            "cpu_baseline": {"value": rtf, "unit": "x_realtime", "cores": cores, "kind": kind,
+                             "sample": "1 stream x 10 s x 4 stems per step; reference C sources built -O2 -fopenmp -DCPU_GEMM=1 (naive sgemm)"},
+            "e2e": {"value": rtf, "unit": "x_realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    """Bounded CPU sample for the GPU arm's JSON line: one 10 s stream, 4 stems, all host threads."""
+    from oracle import oracle as O
+    nets = O.four_stem_weights()
+    L, R = O.synth_pcm(0, n=N_SAMPLES)
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    have_ref = O.have_ref()
+    t0 = time.perf_counter()
+    if have_ref:
+        O.ref_exec().separate(nets, L, R, T, F, unaffected=0.1)
+    else:
+        O.separate(nets, L, R, T, F, unaffected=0.1)
+    dt = time.perf_counter() - t0
+    return {"value": SECONDS / dt, "unit": "x_realtime", "cores": cores, "kind": "reference" if have_ref else "port",
+            "sample": f"1 stream x 10 s x 4 stems, {dt:.2f} s wall; reference C sources (oracle/_ref, -O2 -fopenmp -DCPU_GEMM=1 naive sgemm)"
+            if have_ref else f"1 stream x 10 s x 4 stems, {dt:.2f} s wall; oracle port (oracle/srt_oracle.c)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=32, help="10 s stereo streams per GPU per step")
+    ap.add_argument("--max-images", type=int, default=0, help="U-Net tiles per pass (0 = streams)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import spleeterrt_b200 as srt
+    from spleeterrt_b200 import workload as W
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    srt.load_library()
+    nets, wdesc = W.four_stem_nets()
+    S = len(nets)
+    ns = args.streams
+    B = args.max_images or ns
+    stream = torch.cuda.current_stream()
+    sep = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream)
+
+    # ---- inputs: rank-distinct synthetic streams -------------------------------------------
+    pcm = [W.synth_pcm(rank * ns + i, n=N_SAMPLES) for i in range(min(ns, 4))]
+    hin = torch.empty((ns, 2, N_SAMPLES), dtype=torch.float32).pin_memory()
+    for i in range(ns):
+        hin[i, 0] = torch.from_numpy(pcm[i % len(pcm)][0])
+        hin[i, 1] = torch.from_numpy(pcm[i % len(pcm)][1])
+    hout = torch.empty((ns, S, 2, N_SAMPLES), dtype=torch.float32).pin_memory()
+    din = hin.cuda()
+    dout = torch.empty((ns, S, 2, N_SAMPLES), dtype=torch.float32, device="cuda")
+    n_arr = (C.c_size_t * ns)(*([N_SAMPLES] * ns))
+
+    def ptrs(t_in, t_out):
+        pl = (C.c_void_p * ns)(*[t_in[i, 0].data_ptr() for i in range(ns)])
+        pr = (C.c_void_p * ns)(*[t_in[i, 1].data_ptr() for i in range(ns)])
+        po = (C.c_void_p * (ns * S * 2))(*[t_out[i, s, c].data_ptr() for i in range(ns) for s in range(S) for c in range(2)])
+        return pl, pr, po
+    dpl, dpr, dpo = ptrs(din, dout)
+    hpl, hpr, hpo = ptrs(hin, hout)
+
+    def step_device():
+        sep.separate_raw(dpl, dpr, n_arr, ns, None, dpo, device=True)
+
+    def step_e2e():
+        sep.separate_raw(hpl, hpr, n_arr, ns, None, hpo, device=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ----------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sep.set_timing(True)
+    l0 = sep.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    layer_ms = {}
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        for k in W.LAYER_FLOP_PER_PIXEL:      # per-layer CUDA-event durations of the step (sync inside)
+            layer_ms[k] = layer_ms.get(k, 0.0) + sep.timing(k)
+        for k in ("down1", "up6", "up7", "stft", "istft", "ola"):
+            layer_ms[k] = layer_ms.get(k, 0.0) + sep.timing(k)
+    e1.record(stream)
+    barrier()
+    launches = sep.launch_count() - l0
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    sep.set_timing(False)
+
+    # ---- untimed-layer pass for a clean `value` (no per-layer syncs inside) ---------------------
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the host-pointer C ABI --------------------------------------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()                              # synchronous: returns after the D2H of every stem
+    torch.cuda.synchronize()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
+    if rank == 0:
+        pk = peaks()
+        frames = W.padded_frames(N_SAMPLES)
+        tiles = (frames + T - 1) // T
+        audio_s = SECONDS * ns * world
+        P = T * F
+        n_tc_units = ns * tiles * S                               # stem-tiles per step per GPU
+        tc_flop = W.FLOP_PER_PIXEL_TC * P * n_tc_units
+        tc_ms = sum(layer_ms[k] for k in W.LAYER_FLOP_PER_PIXEL) / args.steps
+        tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+        ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        per_layer = {k: {"ms": layer_ms[k] / args.steps,
+                         "tflops": (W.LAYER_FLOP_PER_PIXEL[k] * P * n_tc_units) / (layer_ms[k] / args.steps * 1e-3) / 1e12
+                         if layer_ms[k] > 0 else None} for k in W.LAYER_FLOP_PER_PIXEL}
+        # HBM-bound stages: algorithmic bytes per hop-frame
+        stft_bytes = 2 * 24.4e3 * frames * ns
+        istft_bytes = 96.8e3 * frames * ns
+        other = {k: layer_ms[k] / args.steps for k in ("down1", "up6", "up7", "stft", "istft", "ola")}
+        line = {
+            "metric": "realtime_factor_4stem_44k1_stereo", "value": audio_s / (ms_step * 1e-3), "unit": "x_realtime",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "frames_per_sec": frames * ns * world / (ms_step * 1e-3),
+            "config": {"workload": f"4-stem 44.1 kHz stereo, {ns} x 10 s streams per GPU per step, T=512 F=1024 (1 tile/stream), "
+                                   "STFT + 4 U-Nets + mask + iSTFT/OLA", "streams_per_gpu": ns, "time_step": T, "bin_limit": F,
+                       "stems": S, "weights": wdesc, "l2": "per-step working set (activations) >> 126 MB L2; no explicit flush",
+                       "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+            "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "x_realtime", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(hin.numel() * 4), "d2h_bytes_per_step": int(hout.numel() * 4)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/tconv, 10 layers)", "bound": "tensor",
+                         "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak if tf32_peak else None,
+                         "traffic": None, "peak_source": f"{pk['source']} bf16 sustained {pk['bf16_tflops_sustained']} TF/s / 2 (TF32 operands)",
+                         "ms_per_step": tc_ms, "flop_per_step": tc_flop, "per_layer": per_layer},
+            "stage_ms": other,
+            "hbm_stages": {"stft_gbs": stft_bytes / (other["stft"] * 1e-3) / 1e9 if other["stft"] > 0 else None,
+                           "istft_ola_gbs": istft_bytes / ((other["istft"] + other["ola"]) * 1e-3) / 1e9 if other["istft"] > 0 else None,
+                           "peak_gbs": pk["hbm_gbs"]},
+            "timed_with_layer_events_ms": ms_dev,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample()
+            except Exception as e:  # the checker being unavailable must not hide the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "x_realtime", "cores": os.cpu_count(), "kind": "unavailable",
+                                        "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+    sep.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

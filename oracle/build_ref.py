@@ -37,7 +37,8 @@ WEIGHTS_SHA256 = "b9837a8b6379c71b6442fbf4b0fb3c7eb668c0c76cf2702eda6ce7b7aa93e4
 def decode_weights(force=False):
     import numpy as np
     dst = os.path.join(OUT, "weights_fp16.bin")
-    if os.path.exists(dst) and not force:
+    prod = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights", "model_fp16.bin")
+    if os.path.exists(dst) and os.path.exists(prod) and not force:
         return dst
     raw = open(os.path.join(REF, "Executable", "model.7z"), "rb").read()
     packed = raw[32:32 + 42853703]
@@ -52,6 +53,10 @@ def decode_weights(force=False):
     assert halves.size == 19645450
     assert hashlib.sha256(halves.tobytes()).hexdigest() == WEIGHTS_SHA256
     halves.tofile(dst)
+    # the product's benchmark workload reads the same blob as plain data from its own tree
+    wdir = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights")
+    os.makedirs(wdir, exist_ok=True)
+    halves.tofile(os.path.join(wdir, "model_fp16.bin"))
     return dst
 
 

@@ -1,0 +1,221 @@
+"""ctypes binding of libspleeterrt_b200.so — mirrors the reference's operator interface.
+
+Names follow the reference (james34602/SpleeterRT): ``Separator.process_spleeter`` is
+``processSpleeter`` (Executable/spleeter.c:177), ``stft``/``istft`` are stftFix.c:363/496,
+``separate`` is the CLI's main.c:762-806 flow for a batch of streams and n_stems nets.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+FFTSIZE, HOPSIZE, BINS = 4096, 1024, 2049
+COEFF_FLOATS = 9822725
+
+# every symbol include/*.h declares (checked by the CPU test-suite against the built library)
+HEADER_SYMBOLS = {
+    "srt_b200.h": ["srt_create", "srt_destroy", "srt_last_error", "srt_half_to_float", "srt_unet_host",
+                   "srt_unet_device", "srt_separate_batch", "srt_separate_device", "srt_stft_rows",
+                   "srt_stft_host", "srt_istft_host", "srt_launch_count", "srt_last_timing", "srt_set_timing",
+                   "srt_debug_tensor", "srt_host_alloc", "srt_host_free", "srt_synchronize"],
+    "spleeter.h": ["getCoeffSize", "allocateSpleeterStr", "initSpleeter", "getMaskPtr", "processSpleeter",
+                   "freeSpleeter"],
+    "stftFix.h": ["InitSTFT", "FreeSTFT", "stft", "istft"],
+}
+
+
+class SrtError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("n_stems", C.c_int), ("time_step", C.c_int), ("bin_limit", C.c_int),
+                ("max_images", C.c_int), ("max_batch_images", C.c_int), ("flavour", C.c_int),
+                ("conv_impl", C.c_int), ("cuda_stream", C.c_void_p)]
+
+
+def lib_path():
+    return os.path.join(PKG, "libspleeterrt_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library.  Fails loudly if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SrtError(f"{path} is missing: build it with `python -m spleeterrt_b200.build` "
+                       "(the product has no CPU / PyTorch fallback)")
+    lib = C.CDLL(path)
+    lib.srt_last_error.restype = C.c_char_p
+    lib.srt_create.argtypes = [C.POINTER(_Config), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.srt_destroy.argtypes = [C.c_void_p]
+    lib.srt_unet_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.srt_unet_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.srt_separate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.srt_separate_device.argtypes = lib.srt_separate_batch.argtypes
+    lib.srt_stft_rows.restype = C.c_size_t
+    lib.srt_stft_rows.argtypes = [C.c_size_t]
+    lib.srt_stft_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
+    lib.srt_istft_host.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.srt_launch_count.restype = C.c_longlong
+    lib.srt_launch_count.argtypes = [C.c_void_p]
+    lib.srt_last_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+    lib.srt_set_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.srt_debug_tensor.restype = C.c_longlong
+    lib.srt_debug_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+    lib.srt_host_alloc.restype = C.c_void_p
+    lib.srt_host_alloc.argtypes = [C.c_size_t]
+    lib.srt_host_free.argtypes = [C.c_void_p]
+    lib.srt_synchronize.argtypes = [C.c_void_p]
+    lib.srt_half_to_float.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    """Dynamic symbols of the built library (used by the CPU tests; no GPU needed)."""
+    import subprocess
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib_path()], text=True)
+    return {line.split()[-1] for line in out.splitlines() if line.strip()}
+
+
+def half_to_float(halves):
+    """fp16 model blob -> fp32, denormals as zero (f32Decompress, main.c:423-434)."""
+    h = np.ascontiguousarray(halves, dtype=np.uint16)
+    out = np.empty(h.shape, np.float32)
+    load_library().srt_half_to_float(h.ctypes.data, out.ctypes.data, h.size)
+    return out
+
+
+TIMING_CATEGORIES = {"down2": 0, "down3": 1, "down4": 2, "down5": 3, "down6": 4, "up1": 5, "up2": 6, "up3": 7,
+                     "up4": 8, "up5": 9, "down1": 10, "up6": 11, "up7": 12, "stft": 13, "istft": 14, "ola": 15,
+                     "h2d": 16, "d2h": 17}
+
+
+class Separator:
+    """One context on one B200 for (n_stems nets, T, F).
+
+    nets: list of (coeff float32[9822725], stemMode) — stemMode 0 = LeakyReLU/ReLU, else ELU
+    (initSpleeter, Executable/spleeter.c:130-139).
+    """
+
+    def __init__(self, nets, time_step, bin_limit, max_images=1, max_batch_images=0, device=0, flavour=0,
+                 conv_impl=None, cuda_stream=None):
+        self.lib = load_library()
+        if conv_impl is None:
+            conv_impl = 1 if os.environ.get("SRT_CONV_IMPL", "") == "simt" else 0
+        cfg = _Config(device, len(nets), time_step, bin_limit, max_images, max_batch_images, flavour, conv_impl,
+                      cuda_stream)
+        self.S, self.T, self.F = len(nets), time_step, bin_limit
+        self.max_images = max_images
+        coeffs = [np.ascontiguousarray(c, np.float32) for c, _ in nets]
+        for c in coeffs:
+            if c.size != COEFF_FLOATS:
+                raise SrtError("each net must be one spleeterCoeff blob of 9822725 floats")
+        cp = (C.c_void_p * max(self.S, 1))(*[c.ctypes.data for c in coeffs])
+        modes = (C.c_int * max(self.S, 1))(*[int(m) for _, m in nets])
+        h = C.c_void_p()
+        self._check(self.lib.srt_create(C.byref(cfg), cp if self.S else None, modes if self.S else None, C.byref(h)))
+        self.h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SrtError(f"srt error {rc}: {self.lib.srt_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.srt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- processSpleeter ------------------------------------------------------------------
+    def process_spleeter(self, x):
+        """x: float32[n_img][2][T][F] (or [2][T][F]) magnitudes -> masks float32[S][n_img][2][T][F]."""
+        x = np.ascontiguousarray(x, np.float32)
+        if x.ndim == 3:
+            x = x[None]
+        n = x.shape[0]
+        assert x.shape[1:] == (2, self.T, self.F)
+        y = np.empty((self.S, n, 2, self.T, self.F), np.float32)
+        self._check(self.lib.srt_unet_host(self.h, x.ctypes.data, n, y.ctypes.data))
+        return y
+
+    def unet_device(self, d_mag_ptr, n_img, d_mask_ptr):
+        self._check(self.lib.srt_unet_device(self.h, d_mag_ptr, n_img, d_mask_ptr))
+
+    def debug_tensor(self, name, n_img):
+        level = {"skip": lambda i: i, "up": lambda i: 6 - i}
+        kind = "skip" if name.startswith("skip") else "up"
+        i = int(name[-1])
+        lv = 0 if name == "up6" else level[kind](i)
+        ch = {"skip": [0, 16, 32, 64, 128, 256, 512], "up": [0, 256, 128, 64, 32, 16, 1]}[kind][i]
+        H, W = self.T >> lv, self.F >> lv
+        out = np.empty((self.S, n_img, ch, H, W), np.float32)
+        rc = self.lib.srt_debug_tensor(self.h, name.encode(), out.ctypes.data, out.size)
+        if rc < 0:
+            self._check(int(rc))
+        return out
+
+    # ---- full path ------------------------------------------------------------------------
+    def separate(self, streams, unaffected=None):
+        """streams: list of (L, R) float32 arrays.  Returns list of float32[S][2][n]."""
+        ns = len(streams)
+        Ls = [np.ascontiguousarray(l, np.float32) for l, _ in streams]
+        Rs = [np.ascontiguousarray(r, np.float32) for _, r in streams]
+        n = (C.c_size_t * ns)(*[l.size for l in Ls])
+        pl = (C.c_void_p * ns)(*[l.ctypes.data for l in Ls])
+        pr = (C.c_void_p * ns)(*[r.ctypes.data for r in Rs])
+        outs = [np.empty((self.S, 2, l.size), np.float32) for l in Ls]
+        po = (C.c_void_p * (ns * self.S * 2))(*[o[s, c].ctypes.data for o in outs for s in range(self.S) for c in range(2)])
+        uw = None
+        if unaffected is not None:
+            uw = (C.c_float * self.S)(*[float(u) for u in unaffected])
+        self._check(self.lib.srt_separate_batch(self.h, pl, pr, n, ns, uw, po))
+        return outs
+
+    def separate_raw(self, pl, pr, n, ns, uw, po, device=False):
+        fn = self.lib.srt_separate_device if device else self.lib.srt_separate_batch
+        self._check(fn(self.h, pl, pr, n, ns, uw, po))
+
+    # ---- transforms -----------------------------------------------------------------------
+    def stft(self, L, R):
+        L = np.ascontiguousarray(L, np.float32)
+        R = np.ascontiguousarray(R, np.float32)
+        rows = self.lib.srt_stft_rows(L.size)
+        planes = [np.zeros((rows, FFTSIZE), np.float32) for _ in range(4)]
+        self._check(self.lib.srt_stft_host(self.h, L.ctypes.data, R.ctypes.data, L.size, *[p.ctypes.data for p in planes]))
+        return planes
+
+    def istft(self, reL, imL, reR, imR):
+        planes = [np.ascontiguousarray(a, np.float32) for a in (reL, imL, reR, imR)]
+        frames = planes[0].shape[0]
+        n = frames * HOPSIZE + FFTSIZE - HOPSIZE
+        oL, oR = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._check(self.lib.srt_istft_host(self.h, *[p.ctypes.data for p in planes], frames, oL.ctypes.data, oR.ctypes.data))
+        return oL, oR
+
+    # ---- introspection ----------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.srt_launch_count(self.h))
+
+    def set_timing(self, on=True):
+        self.lib.srt_set_timing(self.h, int(on))
+
+    def timing(self, name):
+        ms = C.c_float()
+        self.lib.srt_last_timing(self.h, TIMING_CATEGORIES[name], C.byref(ms))
+        return ms.value
+
+    def synchronize(self):
+        self._check(self.lib.srt_synchronize(self.h))

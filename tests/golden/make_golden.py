@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures FROM THE REFERENCE'S OWN CODE (oracle/_ref, built by
+oracle/build_ref.py from /root/reference).  Run in the build container:
+
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+
+Fixtures are small on purpose (they are committed): a T=64 x F=64 U-Net call with seeded
+synthetic fp16-representable weights (both activation modes) and a 20-frame STFT/iSTFT."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import oracle as O  # noqa: E402
+
+r = O.ref_exec()
+seed = 4242
+coeff = O.synthetic_weights(seed)
+rng = np.random.default_rng(99)
+x = (np.abs(rng.standard_normal((2, 64, 64))) * 3).astype(np.float32)
+out = {"seed": seed, "x": x}
+for mode in (0, 1):
+    out[f"mask_mode{mode}"] = r.unet(coeff, x, mode)
+np.savez_compressed(os.path.join(HERE, "unet_T64_F64.npz"), **out)
+
+n = 4096 * 3 + 8192 + 300
+L = (rng.standard_normal(n) * 0.3).astype(np.float32)
+R = (rng.standard_normal(n) * 0.3).astype(np.float32)
+planes = r.stft(L, R)
+oL, oR = r.istft(*planes)
+np.savez_compressed(os.path.join(HERE, "stft_small.npz"), L=L, R=R, reL=planes[0][:, :2049], imL=planes[1][:, :2049],
+                    reR=planes[2][:, :2049], imR=planes[3][:, :2049], outL=oL, outR=oR)
+print("golden fixtures written")

@@ -1,0 +1,118 @@
+// host_model.cpp — TEST INFRASTRUCTURE.  A CPU model of what the GPU gather-GEMM kernels do with
+// the product's own k-block tables and packed weights (spleeterrt_b200/csrc/srt_plan.*): TMA box
+// fetches with zero fill outside the tensor, 128B-swizzled weight blocks, tile decomposition,
+// space-to-depth / phase-scatter epilogues.  It lets the CPU test-suite prove the host logic
+// (tables, packing, layouts) against the oracle without a GPU.  It is never part of the product.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../spleeterrt_b200/csrc/srt_plan.h"
+
+using namespace srt;
+
+static float act_apply(int act, float x)
+{
+    switch (act) {
+    case ACT_LEAKY: return x >= 0.f ? x : 0.2f * x;
+    case ACT_RELU: return x >= 0.f ? x : 0.f;
+    case ACT_ELU_CLAMP: return x >= 0.f ? x : (x < -15.f ? -1.f : std::exp(x) - 1.f);
+    case ACT_ELU: return x >= 0.f ? x : std::exp(x) - 1.f;
+    default: return x;
+    }
+}
+
+// src0/src1: planar [C][H][W] fp32 in the *reference's* layout:
+//   encoder: src0 = activated input of the layer at resolution (2*Hs, 2*Ws)
+//   decoder: src0 = skip, src1 = previous decoder output, both at (Hs, Ws); layer up1 has src0 only
+// out: planar [cout][Hout][Wout]; encoder: raw (conv + bias) when want_act == 0, else act(scale*raw+offset)
+//      decoder: scale*act(v + bias) + offset
+extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
+                                    float* out, int want_act)
+{
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1);
+    if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
+    const LayerPlan& L = plans[plan_index];
+    const CoeffLayout cl = coeff_layout();
+    // ---- device layouts of the sources -------------------------------------------------
+    std::vector<std::vector<float>> src(L.nsrc);
+    const int H = L.Hs, W = L.Ws;
+    if (!L.transposed) {
+        const int cin = L.cin, Hi = 2 * H, Wi = 2 * W;
+        src[0].assign((size_t)H * W * 4 * cin, 0.f);
+        for (int c = 0; c < cin; c++)
+            for (int y = 0; y < Hi; y++)
+                for (int x = 0; x < Wi; x++)
+                    src[0][(((size_t)(y / 2) * W + x / 2) * 4 + (y & 1) * 2 + (x & 1)) * cin + c] = src0[((size_t)c * Hi + y) * Wi + x];
+    } else {
+        const float* in[2] = {src0, src1};
+        for (int q = 0; q < L.nsrc; q++) {
+            const int C = L.src[q].C;
+            src[q].assign((size_t)H * W * C, 0.f);
+            for (int c = 0; c < C; c++)
+                for (int y = 0; y < H; y++)
+                    for (int x = 0; x < W; x++) src[q][((size_t)y * W + x) * C + c] = in[q][((size_t)c * H + y) * W + x];
+        }
+    }
+    // ---- weights and epilogue vectors ----------------------------------------------------
+    std::vector<float> wpk(L.w_floats_per_stem);
+    pack_layer(L, coeff, wpk.data());
+    const float* bias = coeff + (L.transposed ? cl.up_b[L.index - 5] : cl.down_b[L.index + 1]);
+    const float* bn = coeff + (L.transposed ? cl.up_bn[L.index - 5] : cl.down_bn[L.index + 1]);
+    const bool has_bn = L.transposed || L.index < 4;
+    const int Hout = L.transposed ? 2 * H : H, Wout = L.transposed ? 2 * W : W;
+    // ---- tiles ------------------------------------------------------------------------------
+    const int tiles_x = (W + L.tw - 1) / L.tw, tiles_y = (H + L.th - 1) / L.th;
+    std::vector<float> acc(L.n_tile);
+    for (int ph = 0; ph < L.phases; ph++) {
+        const size_t nkb = L.kb[ph].size();
+        for (int nt = 0; nt < L.n_tiles; nt++)
+            for (int ty = 0; ty < tiles_y; ty++)
+                for (int tx = 0; tx < tiles_x; tx++)
+                    for (int m = 0; m < kTileM; m++) {
+                        const int x = m % L.tw, y = (m / L.tw) % L.th, nn = m / (L.tw * L.th);
+                        const int X = tx * L.tw + x, Y = ty * L.th + y;
+                        if (X >= W || Y >= H || nn >= 1) continue;   // masked rows of the tile
+                        std::fill(acc.begin(), acc.end(), 0.f);
+                        for (size_t k = 0; k < nkb; k++) {
+                            const KBlock kb = L.kb[ph][k];
+                            const int yy = Y + kb.dy, xx = X + kb.dx;
+                            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;   // TMA zero fill
+                            const int C = L.src[kb.src].C;
+                            if (kb.c_off < 0 || kb.c_off + kKB > C) return -2;      // box must stay inside the channel dim
+                            const float* a = &src[kb.src][((size_t)yy * W + xx) * C + kb.c_off];
+                            const float* wb = &wpk[L.w_phase_off[ph] + ((size_t)nt * nkb + k) * L.n_tile * kKB];
+                            for (int n = 0; n < L.n_tile; n++) {
+                                float s = 0.f;
+                                for (int j = 0; j < kKB; j++) s += a[j] * wb[swz128_index(n, j)];
+                                acc[n] += s;
+                            }
+                        }
+                        for (int n = 0; n < L.n_tile; n++) {
+                            const int o = nt * L.n_tile + n;
+                            float v = acc[n] + bias[o];
+                            if (L.transposed) {
+                                v = bn[L.cout + o] * act_apply(act, v) + bn[o];
+                                const int oy = 2 * Y + (ph >> 1), ox = 2 * X + (ph & 1);
+                                out[((size_t)o * Hout + oy) * Wout + ox] = v;
+                            } else {
+                                if (want_act && has_bn) v = act_apply(act, bn[L.cout + o] * v + bn[o]);
+                                out[((size_t)o * Hout + Y) * Wout + X] = v;
+                            }
+                        }
+                    }
+    }
+    return 0;
+}
+
+extern "C" int srt_host_model_plan_info(int T, int F, int n_img, int plan_index, int* info /* tw,th,nb,n_tile,n_tiles,phases,nkb0..3 */)
+{
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, n_img);
+    if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
+    const LayerPlan& L = plans[plan_index];
+    info[0] = L.tw; info[1] = L.th; info[2] = L.nb; info[3] = L.n_tile; info[4] = L.n_tiles; info[5] = L.phases;
+    for (int p = 0; p < 4; p++) info[6 + p] = p < L.phases ? (int)L.kb[p].size() : 0;
+    return 0;
+}
+
+extern "C" float srt_host_model_round_tf32(float x) { return round_tf32(x); }

@@ -1,0 +1,127 @@
+"""CPU tests of the host logic: k-block tables, weight packing, layouts (via the CPU model of the
+GPU kernels in tests/host_model.cpp) and the C-ABI surface of the built library."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ENC = [2, 16, 32, 64, 128, 256, 512]
+ACT = {"leaky": 1, "relu": 2, "elu_clamp": 3, "elu": 4}
+
+
+def _act(kind, x):
+    if kind == 1:
+        return np.where(x >= 0, x, 0.2 * x)
+    if kind == 2:
+        return np.maximum(x, 0)
+    return np.where(x >= 0, x, np.where(x < -15, -1.0, np.expm1(np.minimum(x, 0)))).astype(np.float32)
+
+
+def _run_layer(hm, T, F, idx, coeff, act, s0, s1, out_shape, want_act=0):
+    out = np.zeros(out_shape, np.float32)
+    s0 = np.ascontiguousarray(s0, np.float32)
+    p1 = None
+    if s1 is not None:
+        s1 = np.ascontiguousarray(s1, np.float32)
+        p1 = s1.ctypes.data
+    rc = hm.srt_host_model_layer(T, F, idx, np.ascontiguousarray(coeff).ctypes.data_as(C.c_void_p), act,
+                                 s0.ctypes.data_as(C.c_void_p), C.c_void_p(p1), out.ctypes.data_as(C.c_void_p), want_act)
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("T,F,mode", [(64, 128, 1), (64, 192, 0), (128, 64, 1)])
+def test_gather_gemm_model_matches_oracle(oracle, host_model, small_nets, T, F, mode):
+    coeff = small_nets[0][0] if mode else small_nets[1][0]
+    rng = np.random.default_rng(T + F)
+    x = (np.abs(rng.standard_normal((2, T, F))) * 3).astype(np.float32)
+    mask, tp = oracle.unet(coeff, x, mode, taps=True)
+    taps = oracle.split_taps(tp, T, F)
+    v = oracle.coeff_views(coeff)
+    a_enc, a_dec = (3, 3) if mode else (1, 2)
+    # encoder down2..down6: input = act(scale*skip+offset) of the previous layer
+    for i in range(1, 6):
+        skip = taps[f"skip{i}"]
+        bn = v[f"down{i}.bn"]
+        act_in = _act(a_enc, bn[1][:, None, None] * skip + bn[0][:, None, None]).astype(np.float32)
+        got = _run_layer(host_model, T, F, i - 1, coeff, a_enc, act_in, None, taps[f"skip{i+1}"].shape)
+        ref = taps[f"skip{i+1}"]
+        err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
+        assert err < 2e-5, f"down{i+1}: rel err {err}"
+    # decoder up1..up5
+    for d in range(5):
+        s0 = taps["skip6"] if d == 0 else taps[f"skip{6-d}"]
+        s1 = None if d == 0 else taps[f"up{d}"]
+        ref = taps[f"up{d+1}"]
+        got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, s0, s1, ref.shape)
+        err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
+        assert err < 2e-5, f"up{d+1}: rel err {err}"
+
+
+def test_plan_shapes(host_model):
+    info = (C.c_int * 10)()
+    # shape A (T=512, F=1024), batch 32: tiles are full and the k-block counts match the design
+    expect_nkb = {0: [15], 1: [25], 2: [50], 3: [100], 4: [200], 5: [64, 96, 96, 144], 9: [8, 12, 12, 18]}
+    for idx, nkb in expect_nkb.items():
+        assert host_model.srt_host_model_plan_info(512, 1024, 32, idx, info) == 0
+        tw, th, nb, n_tile, n_tiles, phases = info[0:6]
+        assert tw * th * nb == 128 and n_tile * n_tiles in (32, 64, 128, 256, 512, 16)
+        assert list(info[6:6 + phases]) == nkb
+    # tiny deep layers batch images into the tile
+    host_model.srt_host_model_plan_info(64, 64, 32, 4, info)
+    assert info[0] * info[1] == 1 and info[2] == 32 or info[0] * info[1] * info[2] == 128
+
+
+def test_round_tf32(host_model):
+    f = host_model.srt_host_model_round_tf32
+    assert f(1.0) == 1.0
+    x = np.float32(1.0 + 2 ** -11)                   # exactly half an ulp of TF32: ties away from zero
+    assert f(float(x)) == np.float32(1.0 + 2 ** -10)
+    h = np.float16(0.333).astype(np.float32)          # fp16 values are exact in TF32
+    assert f(float(h)) == h
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{}]*\)\s*;", txt)
+    return {n for n in names if n not in ("defined",)}
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads (no GPU needed for dlopen) and exports every include/*.h symbol."""
+    import spleeterrt_b200 as srt
+    if not os.path.exists(srt.lib_path()):
+        from spleeterrt_b200.build import build
+        build()
+    lib = C.CDLL(srt.lib_path())
+    exported = srt.exported_symbols()
+    for header, listed in srt.HEADER_SYMBOLS.items():
+        declared = _declared(header)
+        assert declared == set(listed), f"{header}: header and HEADER_SYMBOLS disagree: {declared ^ set(listed)}"
+        for name in listed:
+            assert name in exported, f"{name} (declared in {header}) is not exported"
+            getattr(lib, name)
+    assert lib.getCoeffSize() == 9822725 * 4          # pure host query, no device touched
+
+
+def test_no_cpu_fallback_without_gpu(oracle):
+    """Without a CUDA device the product must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import spleeterrt_b200 as srt
+    with pytest.raises(srt.SrtError):
+        srt.Separator([(oracle.synthetic_weights(1), 1)], 64, 64)
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "spleeterrt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle/", "ORACLE_DOC/") or "import" not in txt.split("oracle")[0][-40:], f
+                assert "from oracle" not in txt and "import oracle" not in txt and "srt_oracle" not in txt, f

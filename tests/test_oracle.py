@@ -1,0 +1,115 @@
+"""CPU tests: the oracle restatement (oracle/srt_oracle.c) is pinned against the reference's own
+C code compiled into oracle/_ref (when present) and against the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _ref(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    return oracle.ref_exec()
+
+
+def test_coeff_layout(oracle):
+    assert oracle.port().srt_oracle_coeff_floats() == 9822725          # sizeof(spleeterCoeff)/4
+    v = oracle.coeff_views(np.zeros(oracle.COEFF_FLOATS, np.float32))
+    assert v["down6.w"].shape == (512, 256, 5, 5) and v["up1.w"].shape == (512, 256, 5, 5)
+    assert "down6.bn" not in v
+
+
+def test_sigmoid_lut_vs_reference(oracle):
+    r = _ref(oracle)
+    xs = np.linspace(-8, 8, 4001).astype(np.float32)
+    a = np.array([r.lib.fastSigmoid(float(x)) for x in xs])
+    b = np.array([oracle.port().srt_oracle_sigmoid_lut(float(x)) for x in xs])
+    assert np.abs(a - b).max() <= 1e-7
+    assert b[0] == 0.0 and b[-1] == 1.0                                  # hard clip outside +-7 (spleeter.c:32-35)
+
+
+def test_weights_sha(oracle):
+    if not oracle.have_real_weights():
+        pytest.skip("model blob not decoded")
+    import hashlib
+    h = oracle.real_weights_fp16()
+    assert hashlib.sha256(h.tobytes()).hexdigest() == "b9837a8b6379c71b6442fbf4b0fb3c7eb668c0c76cf2702eda6ce7b7aa93e459"
+    f = oracle.half_to_float(h)
+    assert np.array_equal(f[np.abs(f) > 0], h.view(np.float16).astype(np.float32)[np.abs(f) > 0])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_unet_port_vs_reference(oracle, small_nets, mode):
+    r = _ref(oracle)
+    rng = np.random.default_rng(3 + mode)
+    x = (np.abs(rng.standard_normal((2, 64, 128))) * 4).astype(np.float32)
+    coeff = small_nets[0][0] if mode else small_nets[1][0]
+    yr = r.unet(coeff, x, mode)
+    yp = oracle.unet(coeff, x, mode)
+    assert np.abs(yr - yp).max() < 2e-6
+    assert yr.std() > 1e-4
+
+
+def test_stft_istft_port_vs_reference(oracle):
+    r = _ref(oracle)
+    rng = np.random.default_rng(5)
+    n = 4096 * 3 + 8192 + 300                      # deliberately not a multiple of the hop
+    L = (rng.standard_normal(n) * 0.3).astype(np.float32)
+    R = (rng.standard_normal(n) * 0.3).astype(np.float32)
+    sr, sp = r.stft(L, R), oracle.stft(L, R)
+    for a, b in zip(sr, sp):
+        assert a.shape == b.shape and np.abs(a - b).max() < 1e-8
+    orr, op = r.istft(*sr), oracle.istft(*sp)
+    for a, b in zip(orr, op):
+        assert np.abs(a - b).max() < 1e-6
+
+
+def test_stft_matches_numpy_fft(oracle):
+    """SURVEY §4 pin: re = Re rfft(x*hann(i+1/2))/4096, im = -Im(...)."""
+    rng = np.random.default_rng(6)
+    n = 4096 * 4
+    L = rng.standard_normal(n).astype(np.float32)
+    R = rng.standard_normal(n).astype(np.float32)
+    re, im, _, _ = oracle.stft(L, R)
+    i = np.arange(4096)
+    hann = 0.5 * (1 - np.cos(2 * np.pi * (i + 0.5) / 4096))
+    for f in range(3):
+        X = np.fft.rfft(L[f * 1024:f * 1024 + 4096].astype(np.float64) * hann) / 4096
+        assert np.abs(re[f, :2049] - X.real).max() < 2e-6
+        assert np.abs(im[f, :2049] + X.imag).max() < 2e-6
+    assert not re[:, 2049:].any()
+
+
+def test_separate_port_vs_reference(oracle, small_nets):
+    r = _ref(oracle)
+    L, R = oracle.synth_pcm(0, n=30000)
+    a = r.separate(small_nets, L, R, 64, 512)
+    b = oracle.separate(small_nets, L, R, 64, 512)
+    assert np.sqrt(((a - b) ** 2).mean()) < 1e-6
+    assert np.abs(a).max() > 1e-3
+
+
+def test_golden_unet(oracle):
+    """Committed fixture generated from the reference build (tests/golden/make_golden.py)."""
+    p = os.path.join(GOLD, "unet_T64_F64.npz")
+    if not os.path.exists(p):
+        pytest.skip("golden not generated")
+    g = np.load(p)
+    coeff = oracle.synthetic_weights(int(g["seed"]))
+    for mode in (0, 1):
+        y = oracle.unet(coeff, g["x"], mode)
+        assert np.abs(y - g[f"mask_mode{mode}"]).max() < 2e-6
+
+
+def test_golden_stft(oracle):
+    p = os.path.join(GOLD, "stft_small.npz")
+    if not os.path.exists(p):
+        pytest.skip("golden not generated")
+    g = np.load(p)
+    planes = oracle.stft(g["L"], g["R"])
+    for q, name in enumerate(("reL", "imL", "reR", "imR")):
+        assert np.abs(planes[q][:, :2049] - g[name]).max() < 1e-8
+    oL, oR = oracle.istft(*planes)
+    assert np.abs(oL - g["outL"]).max() < 1e-6 and np.abs(oR - g["outR"]).max() < 1e-6
