@@ -214,21 +214,18 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # per-kernel CUDA events inside the context (same stream), no host sync between steps
     sep.set_timing(True)
     l0 = sep.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    layer_ms = {}
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
-        for k in W.LAYER_FLOP_PER_PIXEL:      # per-layer CUDA-event durations of the step (sync inside)
-            layer_ms[k] = layer_ms.get(k, 0.0) + sep.timing(k)
-        for k in ("down1", "up6", "up7", "stft", "istft", "ola"):
-            layer_ms[k] = layer_ms.get(k, 0.0) + sep.timing(k)
     e1.record(stream)
     barrier()
     launches = sep.launch_count() - l0
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    layer_ms = {k: sep.timing(k) for k in list(W.LAYER_FLOP_PER_PIXEL) + ["down1", "up6", "up7", "stft", "istft", "ola"]}
     sep.set_timing(False)
 
     # ---- untimed-layer pass for a clean `value` (no per-layer syncs inside) ---------------------

@@ -100,8 +100,10 @@ int srt_istft_host(srt_ctx* ctx, const float* reL, const float* imL, const float
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 long long srt_launch_count(const srt_ctx* ctx);
-/* CUDA events on the context's stream around the most recent call's dominant kernel class:
- * which = 0 tensor-core conv layers, 1 SIMT edge layers, 2 STFT, 3 iSTFT+OLA; returns ms. */
+/* srt_set_timing(ctx, 1) makes every kernel launch of the following calls be bracketed by CUDA
+ * events on the context's stream (spans accumulate over calls; srt_set_timing clears them).
+ * srt_last_timing sums the spans of one category, in ms: 0..9 = tensor-core layers down2..down6,
+ * up1..up5; 10 down1, 11 up6, 12 up7, 13 STFT, 14 mask+iSTFT, 15 OLA, 16 H2D, 17 D2H. */
 int srt_last_timing(const srt_ctx* ctx, int which, float* ms_out);
 int srt_set_timing(srt_ctx* ctx, int enable);
 /* copy an internal activation tensor of the last U-Net pass to the host, converted to the

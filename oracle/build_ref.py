@@ -11,7 +11,7 @@ GPU box with gpurun):
   1. decodes /root/reference/Executable/model.7z (one raw LZMA2 stream at byte 32,
      42 853 703 bytes, dict 128 MiB -> model.c, CRC32 0x80032de0) with the stdlib `lzma`
      and stores the 19 645 450 IEEE-half weights (2 nets, spleeterQuantized layout,
-     Executable/spleeter.h:32-62) as  oracle/_ref/weights_fp16.bin
+     Executable/spleeter.h:32-62) as  spleeterrt_b200/weights/model_fp16.bin (git-ignored data)
   2. compiles the reference's own C sources *where they lie* (never copied) into
         oracle/_ref/libref_exec.so   (Executable flavour: LUT sigmoid, ELU clamp)
         oracle/_ref/libref_vst.so    (VST flavour: exact sigmoid, streaming Spleeter4Stems)
@@ -36,9 +36,12 @@ WEIGHTS_SHA256 = "b9837a8b6379c71b6442fbf4b0fb3c7eb668c0c76cf2702eda6ce7b7aa93e4
 
 def decode_weights(force=False):
     import numpy as np
-    dst = os.path.join(OUT, "weights_fp16.bin")
-    prod = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights", "model_fp16.bin")
-    if os.path.exists(dst) and os.path.exists(prod) and not force:
+    # one copy only (it travels with every gpurun push): the decoded blob lives in the product's
+    # git-ignored data directory and the oracle reads the same file
+    wdir = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights")
+    os.makedirs(wdir, exist_ok=True)
+    dst = os.path.join(wdir, "model_fp16.bin")
+    if os.path.exists(dst) and not force:
         return dst
     raw = open(os.path.join(REF, "Executable", "model.7z"), "rb").read()
     packed = raw[32:32 + 42853703]
@@ -53,10 +56,6 @@ def decode_weights(force=False):
     assert halves.size == 19645450
     assert hashlib.sha256(halves.tobytes()).hexdigest() == WEIGHTS_SHA256
     halves.tofile(dst)
-    # the product's benchmark workload reads the same blob as plain data from its own tree
-    wdir = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights")
-    os.makedirs(wdir, exist_ok=True)
-    halves.tofile(os.path.join(wdir, "model_fp16.bin"))
     return dst
 
 

@@ -63,14 +63,17 @@ def port():
 
 
 # ----------------------------------------------------------------------------- weights
+WEIGHTS_BLOB = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights", "model_fp16.bin")
+
+
 def have_real_weights():
-    return os.path.exists(os.path.join(REF_DIR, "weights_fp16.bin"))
+    return os.path.exists(WEIGHTS_BLOB)
 
 
 def real_weights_fp16():
     """uint16[2][9822725]: net 0 = ELU 'drum' net, net 1 = LeakyReLU/ReLU 'vocal' net
     (Executable/main.c:759-760)."""
-    h = np.fromfile(os.path.join(REF_DIR, "weights_fp16.bin"), dtype=np.uint16)
+    h = np.fromfile(WEIGHTS_BLOB, dtype=np.uint16)
     return h.reshape(2, COEFF_FLOATS)
 
 

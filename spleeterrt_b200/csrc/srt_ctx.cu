@@ -447,8 +447,11 @@ static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, in
     return 0;
 }
 
+// Spans accumulate over calls while timing is on (so a caller can time K back-to-back steps
+// without a host sync in between) and are cleared by srt_set_timing().
 static void reset_spans(srt_ctx* c)
 {
+    if (c->timing) return;
     c->spans.clear();
     c->ev_used = 0;
 }
@@ -786,6 +789,9 @@ extern "C" long long srt_launch_count(const srt_ctx* c) { return c ? c->launches
 extern "C" int srt_set_timing(srt_ctx* c, int enable)
 {
     if (!c) return SRT_ERR_STATE;
+    cudaStreamSynchronize(c->stream);
+    c->timing = false;
+    reset_spans(c);
     c->timing = enable != 0;
     return 0;
 }
