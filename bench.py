@@ -166,7 +166,8 @@ def main():
     S = len(nets)
     ns = args.streams
     B = args.max_images or ns
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # a real (non-default) stream shared by torch events and the context
+    torch.cuda.set_stream(stream)
     sep = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream)
 
     # ---- inputs: rank-distinct synthetic streams -------------------------------------------

@@ -112,8 +112,12 @@ struct srt_ctx {
     float* d_mask = nullptr;      // [S][NB][T][F][2]
     float2* d_frames = nullptr;   // [max(S,1)][B][T][4096]
     // per-call metadata (device + pinned host mirror)
-    uint8_t *d_meta = nullptr, *h_meta = nullptr;
-    size_t meta_cap = 0;
+    // a ring of 4 slots so back-to-back calls never wait on the host for the previous call
+    uint8_t *d_meta_base = nullptr, *h_meta_base = nullptr;
+    uint8_t *d_meta = nullptr, *h_meta = nullptr;   // current slot
+    size_t meta_cap = 0;                            // bytes per slot
+    cudaEvent_t meta_ev[4]{};
+    int meta_slot = 0;
     // staging for the host-pointer API
     float *d_pcm = nullptr, *d_out = nullptr;
     size_t pcm_cap = 0, out_cap = 0;
@@ -198,8 +202,10 @@ extern "C" void srt_destroy(srt_ctx* c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
-    if (c->d_meta) cudaFree(c->d_meta);
-    if (c->h_meta) cudaFreeHost(c->h_meta);
+    if (c->d_meta_base) cudaFree(c->d_meta_base);
+    if (c->h_meta_base) cudaFreeHost(c->h_meta_base);
+    for (int i = 0; i < 4; i++)
+        if (c->meta_ev[i]) cudaEventDestroy(c->meta_ev[i]);
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_out) cudaFree(c->d_out);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -506,14 +512,30 @@ struct BatchMeta {
 
 static size_t padded_len(size_t n) { return (size_t)kFFT * ((n + kFFT - 1) / kFFT) + 2 * kFFT; }   // main.c:762-763
 
+// Picks the next metadata slot (device block + pinned host mirror).  Waits only if that slot's
+// previous upload, four calls ago, has not been consumed yet.
 static int ensure_meta(srt_ctx* c, size_t bytes)
 {
-    if (bytes <= c->meta_cap) return 0;
-    if (c->d_meta) cudaFree(c->d_meta);
-    if (c->h_meta) cudaFreeHost(c->h_meta);
-    c->meta_cap = bytes * 2 + 4096;
-    CK(cudaMalloc((void**)&c->d_meta, c->meta_cap));
-    CK(cudaMallocHost((void**)&c->h_meta, c->meta_cap));
+    if (bytes > c->meta_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->d_meta_base) cudaFree(c->d_meta_base);
+        if (c->h_meta_base) cudaFreeHost(c->h_meta_base);
+        c->meta_cap = (bytes * 2 + 4095) & ~(size_t)4095;
+        CK(cudaMalloc((void**)&c->d_meta_base, c->meta_cap * 4));
+        CK(cudaMallocHost((void**)&c->h_meta_base, c->meta_cap * 4));
+        for (int i = 0; i < 4; i++)
+            if (!c->meta_ev[i]) CK(cudaEventCreateWithFlags(&c->meta_ev[i], cudaEventDisableTiming));
+    }
+    c->meta_slot = (c->meta_slot + 1) & 3;
+    CK(cudaEventSynchronize(c->meta_ev[c->meta_slot]));
+    c->d_meta = c->d_meta_base + (size_t)c->meta_slot * c->meta_cap;
+    c->h_meta = c->h_meta_base + (size_t)c->meta_slot * c->meta_cap;
+    return 0;
+}
+static int commit_meta(srt_ctx* c, size_t bytes)
+{
+    CK(cudaMemcpyAsync(c->d_meta, c->h_meta, bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->meta_ev[c->meta_slot], c->stream));
     return 0;
 }
 
@@ -541,7 +563,6 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     const size_t o_img = (o_i0 + 4 * (size_t)n_streams + 7) & ~(size_t)7, total_b = o_img + sizeof(ImgDesc) * m.imgs.size();
     int r = ensure_meta(c, total_b);
     if (r) return r;
-    CK(cudaStreamSynchronize(c->stream));   // the pinned mirror may still be in flight from the previous call
     std::memcpy(c->h_meta + o_pl, d_pcmL, 8 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_pr, d_pcmR, 8 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_out, d_out, 8 * (size_t)n_streams * S * 2);
@@ -549,7 +570,7 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     std::memcpy(c->h_meta + o_nfr, m.nfr.data(), 4 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_i0, m.img0.data(), 4 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_img, m.imgs.data(), sizeof(ImgDesc) * m.imgs.size());
-    CK(cudaMemcpyAsync(c->d_meta, c->h_meta, total_b, cudaMemcpyHostToDevice, c->stream));
+    if ((r = commit_meta(c, total_b))) return r;
     const ImgDesc* d_imgs = (const ImgDesc*)(c->d_meta + o_img);
     const int* d_n = (const int*)(c->d_meta + o_n);
     const int* d_nfr = (const int*)(c->d_meta + o_nfr);
@@ -701,7 +722,6 @@ extern "C" int srt_stft_host(srt_ctx* c, const float* L, const float* R, size_t 
         const size_t o_pl = 0, o_pr = 8, o_n = 16, o_nfr = 20, o_img = 24, total_b = o_img + sizeof(ImgDesc) * nr;
         int rr = ensure_meta(c, total_b);
         if (rr) return rr;
-        CK(cudaStreamSynchronize(c->stream));
         const float* pl = c->d_pcm;
         const float* pr = c->d_pcm + np;
         const int ni = (int)n, nf = computed;
@@ -711,7 +731,7 @@ extern "C" int srt_stft_host(srt_ctx* c, const float* L, const float* R, size_t 
         std::memcpy(c->h_meta + o_nfr, &nf, 4);
         ImgDesc* im = (ImgDesc*)(c->h_meta + o_img);
         for (int i = 0; i < nr; i++) im[i] = ImgDesc{0, (int)r0 + i};
-        CK(cudaMemcpyAsync(c->d_meta, c->h_meta, total_b, cudaMemcpyHostToDevice, c->stream));
+        if ((rr = commit_meta(c, total_b))) return rr;
         StftParams p{};
         p.pcmL = (const float* const*)(c->d_meta + o_pl);
         p.pcmR = (const float* const*)(c->d_meta + o_pr);
@@ -754,7 +774,6 @@ extern "C" int srt_istft_host(srt_ctx* c, const float* reL, const float* imL, co
     const size_t o_out = 0, o_n = 16, o_nfr = 20, o_i0 = 24, o_img = 32, total_b = o_img + sizeof(ImgDesc) * frames;
     int r = ensure_meta(c, total_b);
     if (r) return r;
-    CK(cudaStreamSynchronize(c->stream));
     float* po[2] = {c->d_out, c->d_out + out_n};
     const int ni = (int)out_n, nf = (int)frames, i0 = 0;
     std::memcpy(c->h_meta + o_out, po, 16);
@@ -763,7 +782,7 @@ extern "C" int srt_istft_host(srt_ctx* c, const float* reL, const float* imL, co
     std::memcpy(c->h_meta + o_i0, &i0, 4);
     ImgDesc* im = (ImgDesc*)(c->h_meta + o_img);
     for (size_t i = 0; i < frames; i++) im[i] = ImgDesc{0, (int)i};
-    CK(cudaMemcpyAsync(c->d_meta, c->h_meta, total_b, cudaMemcpyHostToDevice, c->stream));
+    if ((r = commit_meta(c, total_b))) return r;
     CK(cudaMemcpyAsync(c->d_spec, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
     IstftParams p{};
     p.spec = c->d_spec; p.mask = nullptr; p.imgs = (const ImgDesc*)(c->d_meta + o_img); p.n_frames = (const int*)(c->d_meta + o_nfr);
