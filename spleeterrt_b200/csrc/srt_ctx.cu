@@ -63,6 +63,7 @@ static PFN_encodeTiled get_encode()
 // activation tensor [n][H][W][C] fp32 -> 4-D map, box {32, tw, th, nb}, 128B swizzle, zero OOB fill
 static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int N, int tw, int th, int nb)
 {
+    // box = {32 channels, tw pixels, th rows, nb images}; may overhang the tensor (zero fill)
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -102,6 +103,8 @@ struct srt_ctx {
     float *d_w7 = nullptr, *d_b7 = nullptr;                                            // up7
     std::vector<LayerPlan> plans;
     std::vector<ConvParams> conv;   // 10 tensor-core layers
+    RowConvParams rp[10];           // row-patch form of the small-N layers (down2, down3, up4, up5)
+    bool use_rp[10]{};
     // activations
     float* E[7]{};    // E[1..6] raw skips (NHWC)
     float* A[6]{};    // A[1..5] activated, space-to-depth
@@ -232,12 +235,23 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         if ((r = upload(c, &c->d_postwin, post))) return r;
         if ((r = upload(c, &c->d_twiddle, tw))) return r;
         if (c->cfg.flavour == 0) {
-            std::vector<float> lut(1026);   // fastSigmoid's table regenerated: sigma(-7 + i*14/1024) to 8 decimals
+            // fastSigmoid's table regenerated (sigma(-7 + i*14/1024) printed to 8 decimals, spleeter.c:29) and
+            // its per-interval slope / origin, evaluated with the reference's float expression (spleeter.c:38-40)
+            std::vector<float> t(1026);
             for (int i = 0; i <= 1024; i++) {
-                const double s = 1.0 / (1.0 + exp(-(-7.0 + i * (14.0 / 1024.0))));
-                lut[i] = (float)(floor(s * 1e8 + 0.5) / 1e8);
+                const double sg = 1.0 / (1.0 + exp(-(-7.0 + i * (14.0 / 1024.0))));
+                t[i] = (float)(floor(sg * 1e8 + 0.5) / 1e8);
             }
-            lut[1025] = 1.0f;
+            t[1025] = 1.0f;
+            std::vector<float> lut(1025 * 4);
+            const volatile float step = 0.01367188f;
+            for (int i = 0; i < 1025; i++) {
+                volatile float m1 = step * (float)i, m2 = step * (float)(i + 1);
+                volatile float x1 = -7.0f + m1, x2 = -7.0f + m2;
+                volatile float den = x2 - x1, num = t[i + 1] - t[i];
+                volatile float slope = num / den;
+                lut[4 * i + 0] = t[i]; lut[4 * i + 1] = slope; lut[4 * i + 2] = x1; lut[4 * i + 3] = 0.0f;
+            }
             if ((r = upload(c, &c->d_lut, lut))) return r;
         }
     }
@@ -361,6 +375,38 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         }
         if (L.nsrc == 1) p.tmap[1] = p.tmap[0];
     }
+    // ---- row-patch variants of the small-N layers ------------------------------------------
+    // SRT_CONV_RP: "0" = never, "1" = whenever supported, unset = when the tile row is wide enough to pay
+    const char* rpe = getenv("SRT_CONV_RP");
+    const char* boe = getenv("SRT_RP_BO");
+    for (size_t li = 0; li < c->plans.size(); li++) {
+        if (!row_plan_supported((int)li) || c->cfg.conv_impl == 1) continue;
+        const RowPlan rpl = build_row_plan(NetGeom{T, F}, (int)li);
+        const bool want = rpe ? atoi(rpe) != 0 : rpl.Ws >= 96;
+        if (!want) continue;
+        RowConvParams& q = c->rp[li];
+        std::memset(&q, 0, sizeof q);
+        std::vector<float> wpk((size_t)S * rpl.w_floats_per_stem);
+        for (int s = 0; s < S; s++) pack_row_layer(rpl, coeffs[s], &wpk[(size_t)s * rpl.w_floats_per_stem]);
+        float* dw;
+        RowChunk* dch;
+        KBlock* dkb;
+        if ((r = upload(c, &dw, wpk)) || (r = upload(c, &dch, rpl.chunks)) || (r = upload(c, &dkb, rpl.kb))) return r;
+        q.chunks = dch; q.n_chunks = (int)rpl.chunks.size();
+        q.kb = dkb; q.nkb = (int)rpl.kb.size();
+        q.w = dw; q.w_stem_stride = rpl.w_floats_per_stem;
+        q.N = rpl.N; q.R = rpl.R;
+        q.tiles_x = (rpl.Ws + kTileM - 1) / kTileM;
+        q.tiles_y = (rpl.Hs + rpl.R - 1) / rpl.R;
+        q.bo_mode = boe ? atoi(boe) : 1;
+        q.ep = c->conv[li];
+        bool ok = true;
+        for (int k = 0; k < rpl.nsrc; k++)
+            if (make_tmap(&q.tmap[k], c->conv[li].src_ptr[k], rpl.src[k].C, rpl.src[k].W, rpl.src[k].H, S * c->B, kPatchW, rpl.R + 2, 1)) ok = false;
+        if (rpl.nsrc == 1) q.tmap[1] = q.tmap[0];
+        if (!ok) { fprintf(stderr, "[spleeterrt_b200] row-patch tensor map rejected for layer %zu (%s); using the generic kernel\n", li, g_err.c_str()); continue; }
+        c->use_rp[li] = true;
+    }
     return 0;
 }
 
@@ -426,6 +472,7 @@ static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, in
         p.Bv = Bv;
         p.tiles_n = (Bv + p.nb - 1) / p.nb;
         if (c->cfg.conv_impl == 1) launch_conv_simt(p, c->stream);
+        else if (c->use_rp[li]) { c->rp[li].ep.Bv = Bv; launch_conv_rp(c->rp[li], c->stream); }
         else launch_conv_tc(p, c->stream);
         c->launches++;
     }

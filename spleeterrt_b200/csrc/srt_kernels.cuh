@@ -41,6 +41,22 @@ struct alignas(64) ConvParams {
     int round_raw, round_act;     // round stored values to TF32 (consumer is a tensor-core layer)
 };
 
+// Row-patch tensor-core kernel (srt_conv_rp.cu): small-N layers, see srt_plan.h RowPlan.
+struct alignas(64) RowConvParams {
+    CUtensorMap tmap[2];          // dims {C, W, H, S*B}, box {32, kPatchW, R+2, 1}, SW128
+    const RowChunk* chunks;
+    int n_chunks;
+    const KBlock* kb;
+    int nkb;
+    const float* w;               // packed weights [stem][k-block][N][32]
+    size_t w_stem_stride;
+    int N, R;
+    int tiles_x, tiles_y;
+    int bo_mode;                  // descriptor base-offset convention for row-shifted operand windows
+    ConvParams ep;                // geometry + epilogue (tmap / k-block fields unused)
+};
+void launch_conv_rp(const RowConvParams& p, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------
 // SIMT edge layers
 // ---------------------------------------------------------------------------------------
@@ -72,7 +88,7 @@ struct Up7Params {                // 4x4 dilation-2 conv 1->2 + bias + sigmoid, 
     const float* in;              // [S*B][T][F]
     const float* w;               // [S][2][16]
     const float* bias;            // [S][2]
-    const float* lut;             // 1026-entry sigmoid table (Executable flavour) or nullptr (exact)
+    const float* lut;             // sigmoid table, 1025 x {t0, slope, x1, 0} (Executable flavour) or nullptr (exact)
     float* mask;                  // [S][mask_stem_stride images][T][F][2], first image of this launch = mask_img0
     int T, F, B, Bv, S;
     int mask_stem_stride, mask_img0;

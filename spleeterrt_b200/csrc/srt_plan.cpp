@@ -193,4 +193,116 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// row-patch plans
+// ------------------------------------------------------------------------------------------
+bool row_plan_supported(int layer_index) { return layer_index == 0 || layer_index == 1 || layer_index == 8 || layer_index == 9; }
+
+// transposed conv: which kernel row serves output parity `par` at input offset d (o = 2h + kh - 1); -1 = none
+static int dec_kh(int par, int d)
+{
+    if (par == 0) return d == 0 ? 1 : (d == -1 ? 3 : -1);
+    return d == 1 ? 0 : (d == 0 ? 2 : 4);
+}
+
+RowPlan build_row_plan(NetGeom g, int layer_index)
+{
+    RowPlan L{};
+    L.index = layer_index;
+    if (layer_index < 5) {
+        const int i = layer_index + 1;          // down{i+1}: cin = kEnc[i]
+        L.transposed = false;
+        L.cin = kEnc[i];
+        L.cout = kEnc[i + 1];
+        L.Hs = g.T >> (i + 1);
+        L.Ws = g.F >> (i + 1);
+        L.N = L.cout;
+        L.phases = 1;
+        L.nsrc = 1;
+        L.src[0] = SrcDesc{4 * L.cin, L.Ws, L.Hs};
+        // chunks = 32-channel slabs of the S2D pixel [py][px][cin]
+        for (int c_off = 0; c_off < 4 * L.cin; c_off += kKB) {
+            RowChunk ch{0, c_off, (int32_t)L.kb.size(), 0};
+            // which (kh, kw) land in this slab, and at which S2D offset
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    std::vector<KElemP> el(kKB);
+                    bool any = false;
+                    for (int j = 0; j < kKB; j++) {
+                        const int c = c_off + j, pp = c / L.cin, cin = c % L.cin, py = pp >> 1, px = pp & 1;
+                        KElemP e{-1, {-1, -1, -1, -1}, {-1, -1, -1, -1}};
+                        for (int kh = 0; kh < 5; kh++)
+                            for (int kw = 0; kw < 5; kw++) {
+                                int d1, p1, d2, p2;
+                                enc_tap(kh, d1, p1);
+                                enc_tap(kw, d2, p2);
+                                if (d1 == dy && p1 == py && d2 == dx && p2 == px) { e.cin = cin; e.kh[0] = (int8_t)kh; e.kw[0] = (int8_t)kw; any = true; }
+                            }
+                        el[j] = e;
+                    }
+                    if (!any) continue;
+                    L.kb.push_back(KBlock{0, (int8_t)dy, (int8_t)dx, 0, c_off});
+                    L.kelem.insert(L.kelem.end(), el.begin(), el.end());
+                    ch.nkb++;
+                }
+            L.chunks.push_back(ch);
+        }
+    } else {
+        const int d = layer_index - 5;          // up{d+1}
+        L.transposed = true;
+        L.cin = kDecIn[d];
+        L.cout = kDecOut[d];
+        L.Hs = g.T >> (6 - d);
+        L.Ws = g.F >> (6 - d);
+        L.N = 4 * L.cout;
+        L.phases = 4;
+        L.nsrc = d == 0 ? 1 : 2;
+        L.src[0] = SrcDesc{d == 0 ? 512 : L.cin / 2, L.Ws, L.Hs};
+        L.src[1] = L.src[0];
+        for (int sidx = 0; sidx < L.nsrc; sidx++)
+            for (int c_off = 0; c_off < L.src[sidx].C; c_off += kKB) {
+                RowChunk ch{(int8_t)sidx, c_off, (int32_t)L.kb.size(), 0};
+                for (int dy = -1; dy <= 1; dy++)
+                    for (int dx = -1; dx <= 1; dx++) {
+                        L.kb.push_back(KBlock{(int8_t)sidx, (int8_t)dy, (int8_t)dx, 0, c_off});
+                        for (int j = 0; j < kKB; j++) {
+                            KElemP e{(sidx ? L.src[0].C : 0) + c_off + j, {-1, -1, -1, -1}, {-1, -1, -1, -1}};
+                            for (int ph = 0; ph < 4; ph++) {
+                                const int kh = dec_kh(ph >> 1, dy), kw = dec_kh(ph & 1, dx);
+                                if (kh >= 0 && kw >= 0) { e.kh[ph] = (int8_t)kh; e.kw[ph] = (int8_t)kw; }
+                            }
+                            L.kelem.push_back(e);
+                        }
+                        ch.nkb++;
+                    }
+                L.chunks.push_back(ch);
+            }
+    }
+    L.R = row_plan_R(L.N);
+    L.w_floats_per_stem = L.kb.size() * (size_t)L.N * kKB;
+    return L;
+}
+
+void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
+{
+    const CoeffLayout cl = coeff_layout();
+    const float* w = coeff + (L.transposed ? cl.up_w[L.index - 5] : cl.down_w[L.index + 1]);
+    for (size_t kb = 0; kb < L.kb.size(); kb++) {
+        float* blk = out + kb * (size_t)L.N * kKB;
+        for (int n = 0; n < L.N; n++) {
+            const int ph = L.transposed ? n / L.cout : 0, o = L.transposed ? n % L.cout : n;
+            for (int j = 0; j < kKB; j++) {
+                const KElemP& e = L.kelem[kb * kKB + j];
+                float v = 0.0f;
+                if (e.cin >= 0 && e.kh[ph] >= 0) {
+                    const size_t idx = L.transposed ? (((size_t)e.cin * L.cout + o) * 5 + e.kh[ph]) * 5 + e.kw[ph]
+                                                    : (((size_t)o * L.cin + e.cin) * 5 + e.kh[ph]) * 5 + e.kw[ph];
+                    v = round_tf32(w[idx]);
+                }
+                blk[swz128_index(n, j)] = v;
+            }
+        }
+    }
+}
+
 }  // namespace srt

@@ -94,6 +94,45 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out);
 
 float round_tf32(float x);
 
+// ---------------------------------------------------------------------------------------
+// "Row-patch" form of the small-N layers (down2, down3, up4, up5).  A CTA owns R output rows x
+// 128 columns of one image.  For every 32-channel slab ("chunk") of a source it loads ONE
+// (R+2)-row x 136-pixel patch and issues the MMAs of all taps from shifted windows of that patch
+// (A-operand descriptor start = patch + (r+dy+1)*row_pitch + (dx+1)*128 B), so every input pixel
+// crosses L2->SM (R+2)/R times instead of once per tap.  Decoder layers fuse the 4 output
+// parities into N = 4*cout (a tap that a parity does not use gets zero weights).
+// ---------------------------------------------------------------------------------------
+constexpr int kPatchW = 136;            // pixels per patch row (130 used; 136 keeps rows 1024B-aligned)
+
+struct KElemP {
+    int32_t cin;                        // -1 = zero slab element
+    int8_t kh[4], kw[4];                // per fused phase; kh < 0: this phase does not use the tap
+};
+struct RowChunk {
+    int8_t src;
+    int32_t c_off;
+    int32_t kb0, nkb;                   // its taps = k-blocks [kb0, kb0+nkb)
+};
+struct RowPlan {
+    int index;                          // same numbering as LayerPlan::index
+    bool transposed;
+    int cin, cout, Hs, Ws;
+    int N;                              // MMA N: cout (encoder) or 4*cout (decoder, phases fused)
+    int R;                              // output rows per CTA
+    int phases;                         // 1 or 4 (fused into N)
+    int nsrc;
+    SrcDesc src[2];
+    std::vector<RowChunk> chunks;
+    std::vector<KBlock> kb;             // dy, dx per k-block (src / c_off copied from the chunk)
+    std::vector<KElemP> kelem;          // 32 per k-block
+    size_t w_floats_per_stem;           // kb.size() * N * 32
+};
+// rows per CTA for a given N (fixed by the shared-memory / TMEM budget, see srt_conv_rp.cu)
+inline int row_plan_R(int N) { return N <= 64 ? 3 : 2; }
+bool row_plan_supported(int layer_index);                 // down2, down3, up4, up5
+RowPlan build_row_plan(NetGeom g, int layer_index);
+void pack_row_layer(const RowPlan& L, const float* coeff, float* out);
+
 // index of (row n, k-element j) inside a swizzled [rows][32] fp32 block
 SRT_HD inline int swz128_index(int row, int j) { return row * 32 + ((((j >> 2) ^ (row & 7)) << 2) | (j & 3)); }
 

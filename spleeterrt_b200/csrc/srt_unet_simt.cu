@@ -56,11 +56,14 @@ void launch_conv_simt(const ConvParams& p, cudaStream_t st)
 // Input row 2*oh + kh - 1, col 2*ow + kw - 1 (im2col_dilated.c:19-27).  Writes the raw skip
 // (conv + bias, fp32) and the activated feature in space-to-depth form, TF32-rounded, which is
 // what down2's tensor-core kernel reads.
+// Each thread produces a 2x2 block of output pixels x 16 channels (64 accumulators), so every
+// broadcast weight load feeds 4 pixels and the kernel is FMA-bound rather than LDS-bound.
 // =========================================================================================
-constexpr int D1_TW = 32, D1_TH = 8;
+constexpr int D1_BX = 16, D1_BY = 8;                    // threads
+constexpr int D1_TW = 2 * D1_BX, D1_TH = 2 * D1_BY;     // output pixels per block: 32 x 16
 constexpr int D1_PW = 2 * D1_TW + 3, D1_PH = 2 * D1_TH + 3;
 
-__global__ void __launch_bounds__(D1_TW* D1_TH) down1_kernel(const Down1Params p)
+__global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p)
 {
     __shared__ float2 patch[D1_PH][D1_PW + 1];
     __shared__ __align__(16) float wsm[25 * 2 * 16];   // [tap][cin][cout]
@@ -81,123 +84,176 @@ __global__ void __launch_bounds__(D1_TW* D1_TH) down1_kernel(const Down1Params p
         patch[r][c] = v;
     }
     __syncthreads();
-    const int tx = tid % D1_TW, ty = tid / D1_TW;
-    const int ow = ow0 + tx, oh = oh0 + ty;
-    float acc[16];
+    const int tx = tid % D1_BX, ty = tid / D1_BX;
+    float acc[2][2][16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+    for (int a = 0; a < 2; a++)
 #pragma unroll
-    for (int kh = 0; kh < 5; kh++)
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[a][c][i] = 0.0f;
+#pragma unroll
+    for (int kh = 0; kh < 5; kh++) {
+        // the two output rows of this thread read patch rows 4ty + kh and 4ty + 2 + kh
+        float2 rowv[2][7];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int c = 0; c < 7; c++) rowv[a][c] = patch[4 * ty + 2 * a + kh][4 * tx + c];
 #pragma unroll
         for (int kw = 0; kw < 5; kw++) {
-            const float2 v = patch[2 * ty + kh][2 * tx + kw];
             const float4* wl = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 0) * 16]);
             const float4* wr = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 1) * 16]);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const float4 a = wl[q], c = wr[q];
-                acc[4 * q + 0] = fmaf(a.x, v.x, fmaf(c.x, v.y, acc[4 * q + 0]));
-                acc[4 * q + 1] = fmaf(a.y, v.x, fmaf(c.y, v.y, acc[4 * q + 1]));
-                acc[4 * q + 2] = fmaf(a.z, v.x, fmaf(c.z, v.y, acc[4 * q + 2]));
-                acc[4 * q + 3] = fmaf(a.w, v.x, fmaf(c.w, v.y, acc[4 * q + 3]));
+                const float4 wa = wl[q], wb = wr[q];
+#pragma unroll
+                for (int a = 0; a < 2; a++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        const float2 v = rowv[a][2 * c + kw];
+                        float* ac = &acc[a][c][4 * q];
+                        ac[0] = fmaf(wa.x, v.x, fmaf(wb.x, v.y, ac[0]));
+                        ac[1] = fmaf(wa.y, v.x, fmaf(wb.y, v.y, ac[1]));
+                        ac[2] = fmaf(wa.z, v.x, fmaf(wb.z, v.y, ac[2]));
+                        ac[3] = fmaf(wa.w, v.x, fmaf(wb.w, v.y, ac[3]));
+                    }
             }
         }
+    }
+    // the 2x2 output block of this thread is exactly one space-to-depth pixel of the activated tensor
+    const int ow = ow0 + 2 * tx, oh = oh0 + 2 * ty;
     if (ow >= Wo || oh >= Ho) return;
-    float raw[16], av[16];
+    float bias[16], sc[16], of[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const float t = acc[i] + p.bias[s * 16 + i];
-        raw[i] = t;
-        av[i] = ptx::rna_tf32(apply_act(p.act[s], p.bn_scale[s * 16 + i] * t + p.bn_offset[s * 16 + i]));
+        bias[i] = p.bias[s * 16 + i];
+        sc[i] = p.bn_scale[s * 16 + i];
+        of[i] = p.bn_offset[s * 16 + i];
     }
-    float4* d0 = reinterpret_cast<float4*>(p.out_raw + (((size_t)n * Ho + oh) * Wo + ow) * 16);
-    float4* d1 = reinterpret_cast<float4*>(
-        p.out_act + ((((size_t)n * (Ho / 2) + oh / 2) * (Wo / 2) + ow / 2) * 4 + (oh & 1) * 2 + (ow & 1)) * 16);
+    float4* d1 = reinterpret_cast<float4*>(p.out_act + (((size_t)n * (Ho / 2) + oh / 2) * (Wo / 2) + ow / 2) * 64);
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        d0[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
-        d1[q] = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
-    }
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            float raw[16], av[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float t = acc[a][c][i] + bias[i];
+                raw[i] = t;
+                av[i] = ptx::rna_tf32(apply_act(p.act[s], sc[i] * t + of[i]));
+            }
+            float4* d0 = reinterpret_cast<float4*>(p.out_raw + (((size_t)n * Ho + oh + a) * Wo + ow + c) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                d0[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
+                d1[(a * 2 + c) * 4 + q] = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
+            }
+        }
 }
 
 void launch_down1(const Down1Params& p, cudaStream_t st)
 {
     dim3 grid((p.F / 2 + D1_TW - 1) / D1_TW, (p.T / 2 + D1_TH - 1) / D1_TH, p.S * p.Bv);
-    down1_kernel<<<grid, D1_TW * D1_TH, 0, st>>>(p);
+    down1_kernel<<<grid, D1_BX * D1_BY, 0, st>>>(p);
 }
 
 // =========================================================================================
 // up6: 5x5 stride-2 transposed conv, [skip1 | up5] (32 ch) -> 1 ch, then act, then BN
 // (spleeter.c:289-294).  Output (2h+kh-1, 2w+kw-1) (im2col_dilated.c:57-58, 37-40).
-// One thread per input-resolution pixel produces its 2x2 output block.
+// One thread handles two horizontally adjacent input-resolution pixels (a 2x4 output block), 16
+// channels at a time (skip half, then up5 half), weights read as broadcast float4.
 // =========================================================================================
-constexpr int U6_TW = 32, U6_TH = 8;
-constexpr int U6_PW = U6_TW + 2, U6_PH = U6_TH + 2, U6_PS = U6_PW + 1;
+constexpr int U6_BX = 32, U6_BY = 8;                  // threads
+constexpr int U6_TW = 2 * U6_BX, U6_TH = U6_BY;       // input pixels per block: 64 x 8
+constexpr int U6_PW = U6_TW + 2, U6_PH = U6_TH + 2, U6_PS = U6_PW + 2;   // row stride 68 floats (even)
 
-__global__ void __launch_bounds__(U6_TW* U6_TH) up6_kernel(const Up6Params p)
+__global__ void __launch_bounds__(U6_BX* U6_BY) up6_kernel(const Up6Params p)
 {
-    extern __shared__ float u6_smem[];
-    float* patch = u6_smem;                          // [32][U6_PH][U6_PS]
-    float* wsm = u6_smem + 32 * U6_PH * U6_PS;       // [32][25] (+pad)
+    __shared__ __align__(16) float patch[16 * U6_PH * U6_PS];   // [16 ch][10][68]
+    __shared__ __align__(16) float wsm[32 * 28];                // [32 ch][25 (+3 pad)]
     const int s = blockIdx.z / p.Bv, n = s * p.B + blockIdx.z % p.Bv;
     const int H = p.T / 2, W = p.F / 2;
     const int x0 = blockIdx.x * U6_TW, y0 = blockIdx.y * U6_TH;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 32 * 25; i += blockDim.x) wsm[i] = p.w[(size_t)s * 800 + i];
-    // fill the patch: 16 channels from the skip, 16 from up5; one float4 per (pixel, quarter)
-    for (int i = tid; i < U6_PH * U6_PW * 8; i += blockDim.x) {
-        const int q = i & 7, pix = i >> 3;
-        const int r = pix / U6_PW, c = pix % U6_PW;
-        const int yy = y0 - 1 + r, xx = x0 - 1 + c;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-            const float* src = (q < 4 ? p.skip : p.up) + (((size_t)n * H + yy) * W + xx) * 16 + (q & 3) * 4;
-            v = *reinterpret_cast<const float4*>(src);
+    for (int i = tid; i < 32 * 28; i += blockDim.x) {
+        const int c = i / 28, t = i % 28;
+        wsm[i] = t < 25 ? p.w[(size_t)s * 800 + c * 25 + t] : 0.0f;
+    }
+    const int tx = tid % U6_BX, ty = tid / U6_BX;
+    float o[2][4];   // [output row parity][output col 0..3] for input pixels (2tx, 2tx+1)
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) o[a][b] = 0.0f;
+    for (int half = 0; half < 2; half++) {
+        __syncthreads();   // previous half fully consumed (and weights visible)
+        const float* src = half ? p.up : p.skip;
+        for (int i = tid; i < U6_PH * U6_PW * 4; i += blockDim.x) {
+            const int q = i & 3, pix = i >> 2;
+            const int r = pix / U6_PW, c = pix % U6_PW;
+            const int yy = y0 - 1 + r, xx = x0 - 1 + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *reinterpret_cast<const float4*>(src + (((size_t)n * H + yy) * W + xx) * 16 + q * 4);
+            float* d = patch + ((q * 4) * U6_PH + r) * U6_PS + c;
+            d[0] = v.x;
+            d[U6_PH * U6_PS] = v.y;
+            d[2 * U6_PH * U6_PS] = v.z;
+            d[3 * U6_PH * U6_PS] = v.w;
         }
-        const int ch = q * 4;
-        patch[((ch + 0) * U6_PH + r) * U6_PS + c] = v.x;
-        patch[((ch + 1) * U6_PH + r) * U6_PS + c] = v.y;
-        patch[((ch + 2) * U6_PH + r) * U6_PS + c] = v.z;
-        patch[((ch + 3) * U6_PH + r) * U6_PS + c] = v.w;
-    }
-    __syncthreads();
-    const int tx = tid % U6_TW, ty = tid / U6_TW;
-    float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
-    for (int c = 0; c < 32; c++) {
-        float nb[3][3];
+        __syncthreads();
+#pragma unroll 2
+        for (int c = 0; c < 16; c++) {
+            // neighbourhood: rows ty..ty+2 (dy = -1..1), cols 2tx..2tx+3 (input x-1 .. x+2)
+            float nb[3][4];
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+            for (int a = 0; a < 3; a++) {
+                const float2* rp = reinterpret_cast<const float2*>(patch + (c * U6_PH + ty + a) * U6_PS + 2 * tx);
+                const float2 u = rp[0], v = rp[1];
+                nb[a][0] = u.x; nb[a][1] = u.y; nb[a][2] = v.x; nb[a][3] = v.y;
+            }
+            float w[28];
+            const float4* wp = reinterpret_cast<const float4*>(wsm + (half * 16 + c) * 28);
 #pragma unroll
-            for (int b = 0; b < 3; b++) nb[a][b] = patch[(c * U6_PH + ty + a) * U6_PS + tx + b];   // (dy,dx) = (a-1,b-1)
-        const float* w = wsm + c * 25;
-        // output row parity 0: kh=1 (dy=0), kh=3 (dy=-1); parity 1: kh=0 (dy=+1), kh=2 (dy=0), kh=4 (dy=-1)
-        // same for columns.  w index = kh*5 + kw.
-#define TAP(kh, kw, dy, dx) (w[(kh) * 5 + (kw)] * nb[(dy) + 1][(dx) + 1])
-        o00 += TAP(1, 1, 0, 0) + TAP(1, 3, 0, -1) + TAP(3, 1, -1, 0) + TAP(3, 3, -1, -1);
-        o01 += TAP(1, 0, 0, 1) + TAP(1, 2, 0, 0) + TAP(1, 4, 0, -1) + TAP(3, 0, -1, 1) + TAP(3, 2, -1, 0) + TAP(3, 4, -1, -1);
-        o10 += TAP(0, 1, 1, 0) + TAP(0, 3, 1, -1) + TAP(2, 1, 0, 0) + TAP(2, 3, 0, -1) + TAP(4, 1, -1, 0) + TAP(4, 3, -1, -1);
-        o11 += TAP(0, 0, 1, 1) + TAP(0, 2, 1, 0) + TAP(0, 4, 1, -1) + TAP(2, 0, 0, 1) + TAP(2, 2, 0, 0) + TAP(2, 4, 0, -1) +
-               TAP(4, 0, -1, 1) + TAP(4, 2, -1, 0) + TAP(4, 4, -1, -1);
+            for (int q = 0; q < 7; q++) {
+                const float4 t = wp[q];
+                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+            }
+            // output row parity 0: kh=1 (dy=0), kh=3 (dy=-1); parity 1: kh=0 (dy=+1), kh=2 (dy=0), kh=4 (dy=-1)
+            // output col parity likewise.  j = 0/1 selects the input pixel; its neighbourhood column for dx is j+1+dx.
+#define TAP(kh, kw, dy, dx) (w[(kh) * 5 + (kw)] * nb[(dy) + 1][j + 1 + (dx)])
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                o[0][2 * j + 0] += TAP(1, 1, 0, 0) + TAP(1, 3, 0, -1) + TAP(3, 1, -1, 0) + TAP(3, 3, -1, -1);
+                o[0][2 * j + 1] += TAP(1, 0, 0, 1) + TAP(1, 2, 0, 0) + TAP(1, 4, 0, -1) + TAP(3, 0, -1, 1) + TAP(3, 2, -1, 0) + TAP(3, 4, -1, -1);
+                o[1][2 * j + 0] += TAP(0, 1, 1, 0) + TAP(0, 3, 1, -1) + TAP(2, 1, 0, 0) + TAP(2, 3, 0, -1) + TAP(4, 1, -1, 0) + TAP(4, 3, -1, -1);
+                o[1][2 * j + 1] += TAP(0, 0, 1, 1) + TAP(0, 2, 1, 0) + TAP(0, 4, 1, -1) + TAP(2, 0, 0, 1) + TAP(2, 2, 0, 0) + TAP(2, 4, 0, -1) +
+                                   TAP(4, 0, -1, 1) + TAP(4, 2, -1, 0) + TAP(4, 4, -1, -1);
+            }
 #undef TAP
+        }
     }
-    const int X = x0 + tx, Y = y0 + ty;
+    const int X = x0 + 2 * tx, Y = y0 + ty;
     if (X >= W || Y >= H) return;
     const float bias = p.bias[s], sc = p.bn_scale[s], of = p.bn_offset[s];
-    float2 r0, r1;
-    r0.x = sc * apply_act(p.act[s], o00 + bias) + of;
-    r0.y = sc * apply_act(p.act[s], o01 + bias) + of;
-    r1.x = sc * apply_act(p.act[s], o10 + bias) + of;
-    r1.y = sc * apply_act(p.act[s], o11 + bias) + of;
+    float4 r0, r1;
+    r0.x = sc * apply_act(p.act[s], o[0][0] + bias) + of;
+    r0.y = sc * apply_act(p.act[s], o[0][1] + bias) + of;
+    r0.z = sc * apply_act(p.act[s], o[0][2] + bias) + of;
+    r0.w = sc * apply_act(p.act[s], o[0][3] + bias) + of;
+    r1.x = sc * apply_act(p.act[s], o[1][0] + bias) + of;
+    r1.y = sc * apply_act(p.act[s], o[1][1] + bias) + of;
+    r1.z = sc * apply_act(p.act[s], o[1][2] + bias) + of;
+    r1.w = sc * apply_act(p.act[s], o[1][3] + bias) + of;
     float* dst = p.out + ((size_t)n * p.T + 2 * Y) * p.F + 2 * X;
-    *reinterpret_cast<float2*>(dst) = r0;
-    *reinterpret_cast<float2*>(dst + p.F) = r1;
+    *reinterpret_cast<float4*>(dst) = r0;            // W is even and X is even: 16-byte aligned
+    *reinterpret_cast<float4*>(dst + p.F) = r1;
 }
 
 void launch_up6(const Up6Params& p, cudaStream_t st)
 {
     dim3 grid((p.F / 2 + U6_TW - 1) / U6_TW, (p.T / 2 + U6_TH - 1) / U6_TH, p.S * p.Bv);
-    const size_t smem = (32 * U6_PH * U6_PS + 32 * 25) * sizeof(float);
-    up6_kernel<<<grid, U6_TW * U6_TH, smem, st>>>(p);
+    up6_kernel<<<grid, U6_BX * U6_BY, 0, st>>>(p);
 }
 
 // =========================================================================================
@@ -206,17 +262,17 @@ void launch_up6(const Up6Params& p, cudaStream_t st)
 // =========================================================================================
 constexpr int U7_TW = 64, U7_TH = 8;
 
-__device__ __forceinline__ float sigmoid_lut(const float* __restrict__ tbl, float x)
+// fastSigmoid (spleeter.c:30-42) with the per-interval constants precomputed on the host with the
+// same float operations: entry = {tbl[i], (tbl[i+1]-tbl[i]) / ((-7+step*(i+1)) - (-7+step*i)), -7+step*i}.
+// Only the index division remains; results are bit-identical to evaluating the original expression.
+__device__ __forceinline__ float sigmoid_lut(const float4* __restrict__ tbl, float x)
 {
-    // Same float operations, in the same order, as fastSigmoid (spleeter.c:30-42).
     const float step = 0.01367188f;
     if (x > 7.0f) return 1.0f;
     if (x < -7.0f) return 0.0f;
     const int idx = (int)(short)__fdiv_rn(__fadd_rn(x, 7.0f), step);
-    const float x1 = __fadd_rn(-7.0f, __fmul_rn(step, (float)idx));
-    const float t0 = __ldg(tbl + idx), t1 = __ldg(tbl + idx + 1);
-    const float den = __fsub_rn(__fadd_rn(-7.0f, __fmul_rn(step, (float)(idx + 1))), x1);
-    return __fadd_rn(t0, __fmul_rn(__fdiv_rn(__fsub_rn(t1, t0), den), __fsub_rn(x, x1)));
+    const float4 e = __ldg(tbl + idx);
+    return __fadd_rn(e.x, __fmul_rn(e.y, __fsub_rn(x, e.z)));
 }
 
 __global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const Up7Params p)
@@ -251,8 +307,9 @@ __global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const Up7Params p)
     a1 += wsm[33];
     float2 m;
     if (p.lut) {
-        m.x = sigmoid_lut(p.lut, a0);
-        m.y = sigmoid_lut(p.lut, a1);
+        const float4* lut = reinterpret_cast<const float4*>(p.lut);
+        m.x = sigmoid_lut(lut, a0);
+        m.y = sigmoid_lut(lut, a1);
     } else {
         m.x = a0 >= 0.f ? 1.0f / (1.0f + expf(-a0)) : expf(a0) / (1.0f + expf(a0));
         m.y = a1 >= 0.f ? 1.0f / (1.0f + expf(-a1)) : expf(a1) / (1.0f + expf(a1));

@@ -116,3 +116,76 @@ extern "C" int srt_host_model_plan_info(int T, int F, int n_img, int plan_index,
 }
 
 extern "C" float srt_host_model_round_tf32(float x) { return round_tf32(x); }
+
+// ---- row-patch ("v2") form of down2 / down3 / up4 / up5 --------------------------------------
+extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
+                                        float* out, int want_act)
+{
+    if (!row_plan_supported(plan_index)) return -1;
+    const RowPlan L = build_row_plan(NetGeom{T, F}, plan_index);
+    const CoeffLayout cl = coeff_layout();
+    const int H = L.Hs, W = L.Ws;
+    std::vector<std::vector<float>> src(L.nsrc);
+    if (!L.transposed) {
+        const int cin = L.cin, Hi = 2 * H, Wi = 2 * W;
+        src[0].assign((size_t)H * W * 4 * cin, 0.f);
+        for (int c = 0; c < cin; c++)
+            for (int y = 0; y < Hi; y++)
+                for (int x = 0; x < Wi; x++)
+                    src[0][(((size_t)(y / 2) * W + x / 2) * 4 + (y & 1) * 2 + (x & 1)) * cin + c] = src0[((size_t)c * Hi + y) * Wi + x];
+    } else {
+        const float* in[2] = {src0, src1};
+        for (int q = 0; q < L.nsrc; q++) {
+            const int C = L.src[q].C;
+            src[q].assign((size_t)H * W * C, 0.f);
+            for (int c = 0; c < C; c++)
+                for (int y = 0; y < H; y++)
+                    for (int x = 0; x < W; x++) src[q][((size_t)y * W + x) * C + c] = in[q][((size_t)c * H + y) * W + x];
+        }
+    }
+    std::vector<float> wpk(L.w_floats_per_stem);
+    pack_row_layer(L, coeff, wpk.data());
+    const float* bias = coeff + (L.transposed ? cl.up_b[L.index - 5] : cl.down_b[L.index + 1]);
+    const float* bn = coeff + (L.transposed ? cl.up_bn[L.index - 5] : cl.down_bn[L.index + 1]);
+    const int Hout = L.transposed ? 2 * H : H, Wout = L.transposed ? 2 * W : W;
+    std::vector<float> acc(L.N);
+    // CTA tiles: R rows x 128 columns; the patch is rows y0-1 .. y0+R, columns x0-1 .. x0+134
+    for (int y0 = 0; y0 < H; y0 += L.R)
+        for (int x0 = 0; x0 < W; x0 += kTileM)
+            for (int r = 0; r < L.R; r++)
+                for (int m = 0; m < kTileM; m++) {
+                    const int Y = y0 + r, X = x0 + m;
+                    if (Y >= H || X >= W) continue;
+                    std::fill(acc.begin(), acc.end(), 0.f);
+                    for (const RowChunk& ch : L.chunks)
+                        for (int k = ch.kb0; k < ch.kb0 + ch.nkb; k++) {
+                            const KBlock kb = L.kb[k];
+                            if (kb.src != ch.src || kb.c_off != ch.c_off) return -3;
+                            // window position inside the patch must exist: rows r+dy+1 in [0, R+2), cols m+dx+1 in [0, 136)
+                            if (r + kb.dy + 1 < 0 || r + kb.dy + 1 >= L.R + 2 || m + kb.dx + 1 < 0 || m + kb.dx + 1 >= kPatchW) return -4;
+                            const int yy = Y + kb.dy, xx = X + kb.dx;
+                            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                            const int C = L.src[kb.src].C;
+                            if (kb.c_off + kKB > C) return -2;
+                            const float* a = &src[kb.src][((size_t)yy * W + xx) * C + kb.c_off];
+                            const float* wb = &wpk[(size_t)k * L.N * kKB];
+                            for (int n = 0; n < L.N; n++) {
+                                float s = 0.f;
+                                for (int j = 0; j < kKB; j++) s += a[j] * wb[swz128_index(n, j)];
+                                acc[n] += s;
+                            }
+                        }
+                    for (int n = 0; n < L.N; n++) {
+                        const int ph = L.transposed ? n / L.cout : 0, o = L.transposed ? n % L.cout : n;
+                        float v = acc[n] + bias[o];
+                        if (L.transposed) {
+                            v = bn[L.cout + o] * act_apply(act, v) + bn[o];
+                            out[((size_t)o * Hout + 2 * Y + (ph >> 1)) * Wout + 2 * X + (ph & 1)] = v;
+                        } else {
+                            if (want_act) v = act_apply(act, bn[L.cout + o] * v + bn[o]);
+                            out[((size_t)o * Hout + Y) * Wout + X] = v;
+                        }
+                    }
+                }
+    return 0;
+}

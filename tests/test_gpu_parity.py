@@ -124,6 +124,16 @@ def test_unet_layers_tcgen05_path(srt, oracle, small_nets, T, F):
     assert w["mask_rms"] < 5e-4 and w["mask_max"] < 3e-2, w
 
 
+@pytest.mark.parametrize("T,F", [(64, 1152), (128, 1024)])
+def test_unet_layers_rowpatch_kernel(srt, oracle, small_nets, T, F, monkeypatch):
+    """Row-patch tensor-core kernel forced on for down2/down3/up4/up5 (multi-tile rows, halos, partial tiles)."""
+    monkeypatch.setenv("SRT_CONV_RP", "1")
+    w = _layer_check(srt, oracle, small_nets[:1], T, F, impl=0, n_img=2)
+    bad = {k: v for k, v in w.items() if not k.startswith("mask") and v > 5e-3}
+    assert not bad, f"layer mismatch {bad} (all: {w})"
+    assert w["mask_rms"] < 5e-4 and w["mask_max"] < 3e-2, w
+
+
 def test_unet_golden(srt, oracle):
     g = np.load(os.path.join(GOLD, "unet_T64_F64.npz"))
     coeff = oracle.synthetic_weights(int(g["seed"]))

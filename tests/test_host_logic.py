@@ -20,14 +20,15 @@ def _act(kind, x):
     return np.where(x >= 0, x, np.where(x < -15, -1.0, np.expm1(np.minimum(x, 0)))).astype(np.float32)
 
 
-def _run_layer(hm, T, F, idx, coeff, act, s0, s1, out_shape, want_act=0):
+def _run_layer(hm, T, F, idx, coeff, act, s0, s1, out_shape, want_act=0, row=False):
     out = np.zeros(out_shape, np.float32)
     s0 = np.ascontiguousarray(s0, np.float32)
     p1 = None
     if s1 is not None:
         s1 = np.ascontiguousarray(s1, np.float32)
         p1 = s1.ctypes.data
-    rc = hm.srt_host_model_layer(T, F, idx, np.ascontiguousarray(coeff).ctypes.data_as(C.c_void_p), act,
+    fn = hm.srt_host_model_row_layer if row else hm.srt_host_model_layer
+    rc = fn(T, F, idx, np.ascontiguousarray(coeff).ctypes.data_as(C.c_void_p), act,
                                  s0.ctypes.data_as(C.c_void_p), C.c_void_p(p1), out.ctypes.data_as(C.c_void_p), want_act)
     assert rc == 0
     return out
@@ -47,18 +48,20 @@ def test_gather_gemm_model_matches_oracle(oracle, host_model, small_nets, T, F, 
         skip = taps[f"skip{i}"]
         bn = v[f"down{i}.bn"]
         act_in = _act(a_enc, bn[1][:, None, None] * skip + bn[0][:, None, None]).astype(np.float32)
-        got = _run_layer(host_model, T, F, i - 1, coeff, a_enc, act_in, None, taps[f"skip{i+1}"].shape)
         ref = taps[f"skip{i+1}"]
-        err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
-        assert err < 2e-5, f"down{i+1}: rel err {err}"
+        for row in ([False, True] if i - 1 in (0, 1) else [False]):
+            got = _run_layer(host_model, T, F, i - 1, coeff, a_enc, act_in, None, ref.shape, row=row)
+            err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
+            assert err < 2e-5, f"down{i+1} (row-patch={row}): rel err {err}"
     # decoder up1..up5
     for d in range(5):
         s0 = taps["skip6"] if d == 0 else taps[f"skip{6-d}"]
         s1 = None if d == 0 else taps[f"up{d}"]
         ref = taps[f"up{d+1}"]
-        got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, s0, s1, ref.shape)
-        err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
-        assert err < 2e-5, f"up{d+1}: rel err {err}"
+        for row in ([False, True] if 5 + d in (8, 9) else [False]):
+            got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, s0, s1, ref.shape, row=row)
+            err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
+            assert err < 2e-5, f"up{d+1} (row-patch={row}): rel err {err}"
 
 
 def test_plan_shapes(host_model):
