@@ -7,8 +7,9 @@
 // descriptors point at shifted windows of that patch:
 //        start = patch + (r + dy + 1) * row_pitch + (dx + 1) * 128 B (+ 32 B per K step)
 // Rows of the patch are 136 pixels * 128 B = 17 KB apart (a multiple of the 1 KB swizzle atom);
-// the +-1 pixel column shift moves the start by 128 B inside the atom, which the descriptor's
-// base-offset field accounts for.  Decoder layers fuse the four output parities into N = 4*cout.
+// the +-1 pixel column shift moves the start by 128 B inside the atom.  Measured on B200
+// (tools/rp_probe.py): the 128B swizzle is a function of the absolute shared-memory address, so the
+// descriptor's base-offset field stays 0 for such windows (setting it to (addr>>7)&7 is wrong).  Decoder layers fuse the four output parities into N = 4*cout.
 // Weights stream through a small ring of pre-swizzled [N][32] blocks, one per (slab, tap).
 // Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (shared with the generic kernel).
 #include "srt_epilogue.cuh"

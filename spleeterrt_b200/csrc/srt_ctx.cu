@@ -398,7 +398,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         q.N = rpl.N; q.R = rpl.R;
         q.tiles_x = (rpl.Ws + kTileM - 1) / kTileM;
         q.tiles_y = (rpl.Hs + rpl.R - 1) / rpl.R;
-        q.bo_mode = boe ? atoi(boe) : 1;
+        q.bo_mode = boe ? atoi(boe) : 0;   // measured on B200: the swizzle is a function of the absolute smem address, base offset stays 0
         q.ep = c->conv[li];
         bool ok = true;
         for (int k = 0; k < rpl.nsrc; k++)

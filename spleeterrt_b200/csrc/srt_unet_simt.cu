@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
     }
     __syncthreads();
     const int tx = tid % D1_BX, ty = tid / D1_BX;
+    // this thread's 2x2 outputs are (ty + 8a, tx + 16c): interleaved so that neighbouring lanes read
+    // neighbouring patch columns (no shared-memory bank conflicts)
     float acc[2][2][16];
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -94,14 +96,13 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
             for (int i = 0; i < 16; i++) acc[a][c][i] = 0.0f;
 #pragma unroll
     for (int kh = 0; kh < 5; kh++) {
-        // the two output rows of this thread read patch rows 4ty + kh and 4ty + 2 + kh
-        float2 rowv[2][7];
-#pragma unroll
-        for (int a = 0; a < 2; a++)
-#pragma unroll
-            for (int c = 0; c < 7; c++) rowv[a][c] = patch[4 * ty + 2 * a + kh][4 * tx + c];
 #pragma unroll
         for (int kw = 0; kw < 5; kw++) {
+            float2 v[2][2];
+#pragma unroll
+            for (int a = 0; a < 2; a++)
+#pragma unroll
+                for (int c = 0; c < 2; c++) v[a][c] = patch[2 * (ty + D1_BY * a) + kh][2 * (tx + D1_BX * c) + kw];
             const float4* wl = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 0) * 16]);
             const float4* wr = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 1) * 16]);
 #pragma unroll
@@ -111,19 +112,15 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
                 for (int a = 0; a < 2; a++)
 #pragma unroll
                     for (int c = 0; c < 2; c++) {
-                        const float2 v = rowv[a][2 * c + kw];
                         float* ac = &acc[a][c][4 * q];
-                        ac[0] = fmaf(wa.x, v.x, fmaf(wb.x, v.y, ac[0]));
-                        ac[1] = fmaf(wa.y, v.x, fmaf(wb.y, v.y, ac[1]));
-                        ac[2] = fmaf(wa.z, v.x, fmaf(wb.z, v.y, ac[2]));
-                        ac[3] = fmaf(wa.w, v.x, fmaf(wb.w, v.y, ac[3]));
+                        ac[0] = fmaf(wa.x, v[a][c].x, fmaf(wb.x, v[a][c].y, ac[0]));
+                        ac[1] = fmaf(wa.y, v[a][c].x, fmaf(wb.y, v[a][c].y, ac[1]));
+                        ac[2] = fmaf(wa.z, v[a][c].x, fmaf(wb.z, v[a][c].y, ac[2]));
+                        ac[3] = fmaf(wa.w, v[a][c].x, fmaf(wb.w, v[a][c].y, ac[3]));
                     }
             }
         }
     }
-    // the 2x2 output block of this thread is exactly one space-to-depth pixel of the activated tensor
-    const int ow = ow0 + 2 * tx, oh = oh0 + 2 * ty;
-    if (ow >= Wo || oh >= Ho) return;
     float bias[16], sc[16], of[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -131,11 +128,12 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
         sc[i] = p.bn_scale[s * 16 + i];
         of[i] = p.bn_offset[s * 16 + i];
     }
-    float4* d1 = reinterpret_cast<float4*>(p.out_act + (((size_t)n * (Ho / 2) + oh / 2) * (Wo / 2) + ow / 2) * 64);
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int c = 0; c < 2; c++) {
+            const int oh = oh0 + ty + D1_BY * a, ow = ow0 + tx + D1_BX * c;
+            if (ow >= Wo || oh >= Ho) continue;
             float raw[16], av[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
@@ -143,11 +141,13 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
                 raw[i] = t;
                 av[i] = ptx::rna_tf32(apply_act(p.act[s], sc[i] * t + of[i]));
             }
-            float4* d0 = reinterpret_cast<float4*>(p.out_raw + (((size_t)n * Ho + oh + a) * Wo + ow + c) * 16);
+            float4* d0 = reinterpret_cast<float4*>(p.out_raw + (((size_t)n * Ho + oh) * Wo + ow) * 16);
+            float4* d1 = reinterpret_cast<float4*>(
+                p.out_act + ((((size_t)n * (Ho / 2) + oh / 2) * (Wo / 2) + ow / 2) * 4 + (oh & 1) * 2 + (ow & 1)) * 16);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 d0[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
-                d1[(a * 2 + c) * 4 + q] = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
+                d1[q] = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
             }
         }
 }
