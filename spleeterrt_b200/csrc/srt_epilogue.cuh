@@ -12,6 +12,16 @@
 
 namespace srt {
 
+__device__ __forceinline__ void load16(const float* __restrict__ src, float* v)
+{
+    const float4* q = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float4 t = __ldg(q + i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+
 __device__ __forceinline__ void store16(float* dst, const float* v)
 {
     float4* d = reinterpret_cast<float4*>(dst);
@@ -22,10 +32,12 @@ __device__ __forceinline__ void store16(float* dst, const float* v)
 // v[16]: accumulators for channels [c0, c0+16) of pixel (n, Y, X) in tile space.
 __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, int Y, int X, int phase, int c0, float* v)
 {
-    const float* bias = p.bias + s * p.cout + c0;
+    float bias[16];
+    load16(p.bias + s * p.cout + c0, bias);
     if (p.mode == 2) {
-        const float* sc = p.bn_scale + s * p.cout + c0;
-        const float* of = p.bn_offset + s * p.cout + c0;
+        float sc[16], of[16];
+        load16(p.bn_scale + s * p.cout + c0, sc);
+        load16(p.bn_offset + s * p.cout + c0, of);
         float o[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -40,8 +52,9 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
 #pragma unroll
     for (int i = 0; i < 16; i++) raw[i] = v[i] + bias[i];
     if (p.mode == 0) {
-        const float* sc = p.bn_scale + s * p.cout + c0;
-        const float* of = p.bn_offset + s * p.cout + c0;
+        float sc[16], of[16];
+        load16(p.bn_scale + s * p.cout + c0, sc);
+        load16(p.bn_offset + s * p.cout + c0, of);
         float a[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) {
