@@ -147,19 +147,20 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 for (int ci = 0; ci < p.n_chunks; ci++) {
                     const RowChunk ch = hdr->chunks[ci];
                     ptx::mbar_wait(&hdr->patch_full[ps], pph);
-                    const uint32_t pbase = patch_base + (uint32_t)ps * kPatchBytes;
+                    const uint32_t p_lo = ptx::umma_desc_lo(patch_base + (uint32_t)ps * kPatchBytes);
                     for (int k = ch.kb0; k < ch.kb0 + ch.nkb; k++) {
                         const KBlock kb = hdr->kb[k];
+                        // descriptor low word of the tap's window for row r = 0, K step 0 (16-byte units)
+                        const uint32_t a_lo = p_lo + (uint32_t)((kb.dy + 1) * (kRowPitch >> 4) + (kb.dx + 1) * (128 >> 4));
+                        const uint32_t b_lo = ptx::umma_desc_lo(wring_base + (uint32_t)ws * kWBytes);
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
-                        const uint32_t b_addr = wring_base + (uint32_t)ws * kWBytes;
 #pragma unroll
                         for (int r = 0; r < R; r++) {
-                            const uint32_t a_addr = pbase + (uint32_t)(r + kb.dy + 1) * kRowPitch + (uint32_t)(kb.dx + 1) * 128u;
 #pragma unroll
                             for (int kk = 0; kk < kKB / 8; kk++)
-                                ptx::mma_tf32_ss(acc + (uint32_t)(r * N), ptx::umma_desc_sw128(a_addr + kk * 32),
-                                                 ptx::umma_desc_sw128(b_addr + kk * 32), idesc, (!first || kk != 0) ? 1u : 0u);
+                                ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2),
+                                                    idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
                         }
                         first = false;
                         ptx::mma_commit(&hdr->w_empty[ws]);

@@ -106,14 +106,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
             for (int k = 0; k < nkb; k++) {
                 ptx::mbar_wait(&hdr->full[stage], ph);
                 ptx::tc_fence_after();
-                const uint32_t a_addr = tiles_base + (uint32_t)stage * kStageBytes;
-                const uint32_t b_addr = a_addr + kABytes;
+                const uint32_t a_lo = ptx::umma_desc_lo(tiles_base + (uint32_t)stage * kStageBytes);
+                const uint32_t b_lo = a_lo + (kABytes >> 4);
 #pragma unroll
-                for (int kk = 0; kk < kKB / 8; kk++) {
-                    const uint64_t adesc = ptx::umma_desc_sw128(a_addr + kk * 32);
-                    const uint64_t bdesc = ptx::umma_desc_sw128(b_addr + kk * 32);
-                    ptx::mma_tf32_ss(tmem_d, adesc, bdesc, idesc, (k | kk) != 0);
-                }
+                for (int kk = 0; kk < kKB / 8; kk++)
+                    ptx::mma_tf32_ss_lo(tmem_d, a_lo + kk * 2, b_lo + kk * 2, idesc, (kk != 0) ? 1u : (k != 0 ? 1u : 0u));
                 ptx::mma_commit(&hdr->empty[stage]);   // frees the stage once these MMAs retire
                 if (++stage == stages) { stage = 0; ph ^= 1; }
             }
