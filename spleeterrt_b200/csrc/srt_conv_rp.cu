@@ -17,7 +17,7 @@
 //   warp 0  patch producer   : TMA boxes into a 2-deep patch ring            (patch_full/empty)
 //   warp 1  weight producer  : pre-swizzled [N][32] blocks into a deep ring   (w_full/empty)
 //   warp 2  MMA issuer       : tcgen05.mma.kind::tf32 into one of 2 TMEM accumulator sets
-//   warps 3-6 epilogue       : tcgen05.ld -> bias/BN/act -> global, overlapped with the next tile's MMAs
+//   warps 3-10 epilogue      : tcgen05.ld -> bias/BN/act -> global, overlapped with the next tile's MMAs
 // The first non-persistent version of this kernel was latency-bound (refill chains of ~3 us per
 // weight block / patch, profiles/r1c_*); deep prefetch across tile boundaries removes those bubbles.
 #include "srt_epilogue.cuh"
@@ -26,7 +26,7 @@
 
 namespace srt {
 
-constexpr int kRpThreads = 224;
+constexpr int kRpThreads = 352;   // 3 control warps + 8 epilogue warps
 constexpr int kRowPitch = kPatchW * 128;
 constexpr int kRpMaxChunks = 8, kRpMaxKB = 80, kRpMaxWStages = 12;
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
             ptx::mbar_init(&hdr->patch_full[i], 1);
             ptx::mbar_init(&hdr->patch_empty[i], 1);
             ptx::mbar_init(&hdr->acc_full[i], 1);
-            ptx::mbar_init(&hdr->acc_empty[i], 4);   // one arrival per epilogue warp
+            ptx::mbar_init(&hdr->acc_empty[i], 8);   // one arrival per epilogue warp
         }
         for (int i = 0; i < WS; i++) {
             ptx::mbar_init(&hdr->w_full[i], 1);
@@ -111,8 +111,11 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 for (int ci = 0; ci < p.n_chunks; ci++) {
                     const RowChunk ch = hdr->chunks[ci];
                     ptx::mbar_wait(&hdr->patch_empty[ps], pph ^ 1);
+                    if (p.dbg & 4) { ptx::mbar_arrive(&hdr->patch_full[ps]); }
+                    else {
                     ptx::mbar_arrive_expect_tx(&hdr->patch_full[ps], kPatchBytes);
                     ptx::tma_load_4d(patch + (size_t)ps * kPatchBytes, &p.tmap[ch.src], &hdr->patch_full[ps], ch.c_off, tl.x0 - 1, tl.y0 - 1, tl.n);
+                    }
                     if (++ps == 2) { ps = 0; pph ^= 1; }
                 }
             }
@@ -127,8 +130,11 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 const float* wsrc = p.w + (size_t)s * p.w_stem_stride;
                 for (int k = 0; k < p.nkb; k++) {
                     ptx::mbar_wait(&hdr->w_empty[ws], wph ^ 1);
+                    if (p.dbg & 8) { ptx::mbar_arrive(&hdr->w_full[ws]); }
+                    else {
                     ptx::mbar_arrive_expect_tx(&hdr->w_full[ws], kWBytes);
                     ptx::bulk_load_1d(wring + (size_t)ws * kWBytes, wsrc + (size_t)k * N * kKB, kWBytes, &hdr->w_full[ws]);
+                    }
                     if (++ws == WS) { ws = 0; wph ^= 1; }
                 }
             }
@@ -155,10 +161,13 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                         const uint32_t b_lo = ptx::umma_desc_lo(wring_base + (uint32_t)ws * kWBytes);
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
+                        if (!(p.dbg & 2))
+                        // K step outer, row inner: consecutive MMAs hit different accumulators (dependent MMAs on one
+                        // accumulator cost ~100 cycles each, independent ones ~60: tools/mma_probe.cu)
 #pragma unroll
-                        for (int r = 0; r < R; r++) {
+                        for (int kk = 0; kk < kKB / 8; kk++) {
 #pragma unroll
-                            for (int kk = 0; kk < kKB / 8; kk++)
+                            for (int r = 0; r < R; r++)
                                 ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2),
                                                     idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
                         }
@@ -174,8 +183,8 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
             }
         }
     } else {
-        // ===== epilogue (warps 3..6 -> TMEM lane quarters 3,0,1,2) =================================
-        const int q = warp & 3;
+        // ===== epilogue: warps 3..10; warp%4 selects the TMEM lane quarter, (warp-3)/4 the column half =====
+        const int q = warp & 3, half = (warp - 3) >> 2;
         const int m = q * 32 + lane;
         int as = 0;
         uint32_t aph = 0;
@@ -190,10 +199,10 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 const int Y = tl.y0 + r;
                 const bool valid = X < p.ep.Ws && Y < p.ep.Hs;
 #pragma unroll 1
-                for (int c0 = 0; c0 < N; c0 += 16) {
+                for (int c0 = half * 16; c0 < N; c0 += 32) {
                     float v[16];
                     ptx::tmem_ld16(acc + (uint32_t)(r * N + c0), v);
-                    if (valid) {
+                    if (valid && !(p.dbg & 1)) {
                         if (p.ep.mode == 2) epilogue16(p.ep, tl.s, tl.n, Y, X, c0 / p.ep.cout, c0 % p.ep.cout, v);
                         else epilogue16(p.ep, tl.s, tl.n, Y, X, 0, c0, v);
                     }

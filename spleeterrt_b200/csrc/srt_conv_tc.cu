@@ -9,7 +9,7 @@
 //     zero-filled by the TMA unit (= the reference's zero padding).  128B-swizzled, K-major.
 //   * W_kb is a pre-packed, pre-swizzled [N][32] block streamed with a 1-D bulk copy.
 //   * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (accumulator lives in TMEM),
-//     warps 2..5 = epilogue (tcgen05.ld -> bias / BN / activation -> global, see srt_epilogue.cuh).
+//     warps 2..9 = epilogue (tcgen05.ld -> bias / BN / activation -> global, see srt_epilogue.cuh).
 //   * ring of mbarrier-guarded stages; one output tile per CTA.
 #include "srt_epilogue.cuh"
 #include "srt_kernels.cuh"
@@ -17,7 +17,7 @@
 
 namespace srt {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;   // producer, MMA issuer, 8 epilogue warps
 constexpr int kABytes = kTileM * kKB * 4;   // 16 KiB per stage
 constexpr int kMaxKB = 512;
 
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
     } else {
         // ===== epilogue: TMEM -> registers -> bias/BN/act -> global ======================
-        const int q = warp & 3;                         // TMEM lane quarter this warp may read
+        const int q = warp & 3, half = (warp - 2) >> 2;   // TMEM lane quarter this warp may read; column half
         const int m = q * 32 + lane;
         const int x = m % p.tw, y = (m / p.tw) % p.th, nn = m / (p.tw * p.th);
         const int X = tx * p.tw + x, Y = ty * p.th + y, b = tz * p.nb + nn;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         ptx::mbar_wait(&hdr->tmem_full, 0);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 16) {
+        for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
             float v[16];
             ptx::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (valid) epilogue16(p, s, n, Y, X, phase, nt * N_TILE + c0, v);

@@ -400,6 +400,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         q.tiles_y = (rpl.Hs + rpl.R - 1) / rpl.R;
         q.bo_mode = boe ? atoi(boe) : 0;   // measured on B200: the swizzle is a function of the absolute smem address, base offset stays 0
         q.ep = c->conv[li];
+        q.dbg = getenv("SRT_RP_DBG") ? atoi(getenv("SRT_RP_DBG")) : 0;
         bool ok = true;
         for (int k = 0; k < rpl.nsrc; k++)
             if (make_tmap(&q.tmap[k], c->conv[li].src_ptr[k], rpl.src[k].C, rpl.src[k].W, rpl.src[k].H, S * c->B, kPatchW, rpl.R + 2, 1)) ok = false;

@@ -29,21 +29,52 @@ __device__ __forceinline__ void store16(float* dst, const float* v)
     for (int q = 0; q < 4; q++) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+// Branch-free activations for the tensor-core epilogues.  The epilogue warps are instruction-latency
+// bound (ncu / tools/rp_dbg_sweep.sh: the epilogue, not the MMAs, dominated the small-N layers), so the
+// activation kind is resolved once per 16-channel chunk and ELU uses ex2.approx (__expf): its absolute
+// error (~1e-7) is far below the TF32 rounding applied to the stored value right after.
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x)
+{
+    if (ACT == ACT_LEAKY) return x >= 0.0f ? x : 0.2f * x;
+    if (ACT == ACT_RELU) return fmaxf(x, 0.0f);
+    if (ACT == ACT_ELU_CLAMP) { const float e = x < -15.0f ? -1.0f : __expf(x) - 1.0f; return x >= 0.0f ? x : e; }
+    if (ACT == ACT_ELU) { const float e = __expf(x) - 1.0f; return x >= 0.0f ? x : e; }
+    return x;
+}
+
+template <int ACT>
+__device__ __forceinline__ void dec16(const float* v, const float* bias, const float* sc, const float* of, bool round, float* o)
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float t = fmaf(sc[i], act_fast<ACT>(v[i] + bias[i]), of[i]);
+        o[i] = round ? ptx::rna_tf32(t) : t;
+    }
+}
+template <int ACT>
+__device__ __forceinline__ void enc16(const float* raw, const float* sc, const float* of, bool round, float* a)
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float t = act_fast<ACT>(fmaf(sc[i], raw[i], of[i]));
+        a[i] = round ? ptx::rna_tf32(t) : t;
+    }
+}
+
 // v[16]: accumulators for channels [c0, c0+16) of pixel (n, Y, X) in tile space.
 __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, int Y, int X, int phase, int c0, float* v)
 {
+    const int act = p.act[s];
     float bias[16];
     load16(p.bias + s * p.cout + c0, bias);
     if (p.mode == 2) {
-        float sc[16], of[16];
+        float sc[16], of[16], o[16];
         load16(p.bn_scale + s * p.cout + c0, sc);
         load16(p.bn_offset + s * p.cout + c0, of);
-        float o[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            float t = sc[i] * apply_act(p.act[s], v[i] + bias[i]) + of[i];
-            o[i] = p.round_act ? ptx::rna_tf32(t) : t;
-        }
+        if (act == ACT_ELU_CLAMP) dec16<ACT_ELU_CLAMP>(v, bias, sc, of, p.round_act, o);
+        else if (act == ACT_RELU) dec16<ACT_RELU>(v, bias, sc, of, p.round_act, o);
+        else dec16<ACT_ELU>(v, bias, sc, of, p.round_act, o);
         const int oy = 2 * Y + (phase >> 1), ox = 2 * X + (phase & 1);
         store16(p.out_dec + (((size_t)n * (2 * p.Hs) + oy) * (2 * p.Ws) + ox) * p.cout + c0, o);
         return;
@@ -52,15 +83,12 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
 #pragma unroll
     for (int i = 0; i < 16; i++) raw[i] = v[i] + bias[i];
     if (p.mode == 0) {
-        float sc[16], of[16];
+        float sc[16], of[16], a[16];
         load16(p.bn_scale + s * p.cout + c0, sc);
         load16(p.bn_offset + s * p.cout + c0, of);
-        float a[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            float t = apply_act(p.act[s], sc[i] * raw[i] + of[i]);
-            a[i] = p.round_act ? ptx::rna_tf32(t) : t;
-        }
+        if (act == ACT_ELU_CLAMP) enc16<ACT_ELU_CLAMP>(raw, sc, of, p.round_act, a);
+        else if (act == ACT_LEAKY) enc16<ACT_LEAKY>(raw, sc, of, p.round_act, a);
+        else enc16<ACT_ELU>(raw, sc, of, p.round_act, a);
         store16(p.out_act + ((((size_t)n * (p.Hs / 2) + Y / 2) * (p.Ws / 2) + X / 2) * 4 + (Y & 1) * 2 + (X & 1)) * p.cout + c0, a);
     }
     if (p.round_raw) {

@@ -52,7 +52,8 @@ struct alignas(64) RowConvParams {
     size_t w_stem_stride;
     int N, R;
     int tiles_x, tiles_y;
-    int bo_mode;                  // descriptor base-offset convention for row-shifted operand windows
+    int bo_mode;                  // (diagnostic) descriptor base-offset convention, 0 = product setting
+    int dbg;                      // (diagnostic, SRT_RP_DBG) 1: skip epilogue math+stores, 2: skip MMAs, 4: skip patch loads, 8: skip weight loads
     ConvParams ep;                // geometry + epilogue (tmap / k-block fields unused)
 };
 void launch_conv_rp(const RowConvParams& p, cudaStream_t st);
