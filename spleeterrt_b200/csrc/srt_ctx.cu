@@ -101,6 +101,8 @@ struct srt_ctx {
     float *d_w1 = nullptr, *d_b1 = nullptr, *d_s1 = nullptr, *d_o1 = nullptr;          // down1
     float *d_w6 = nullptr, *d_b6 = nullptr, *d_s6 = nullptr, *d_o6 = nullptr;          // up6
     float *d_w7 = nullptr, *d_b7 = nullptr;                                            // up7
+    std::vector<float> h_w1, h_b1;  // down1 weights [stem][tap][cin][cout] and {bias, scale, offset}
+    std::vector<float> h_w6, h_w7;  // up6 / up7 weights, host copies (ride in the kernel parameter bank)
     std::vector<LayerPlan> plans;
     std::vector<ConvParams> conv;   // 10 tensor-core layers
     RowConvParams rp[10];           // row-patch form of the small-N layers (down2, down3, up4, up5)
@@ -125,6 +127,8 @@ struct srt_ctx {
     float *d_pcm = nullptr, *d_out = nullptr;
     size_t pcm_cap = 0, out_cap = 0;
     float *d_xin = nullptr;       // unet_host staging
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer API (H2D / D2H overlap compute)
+    cudaEvent_t ev_in[8]{}, ev_c[8]{};
     // bookkeeping
     long long launches = 0;
     bool timing = false;
@@ -212,6 +216,12 @@ extern "C" void srt_destroy(srt_ctx* c)
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_out) cudaFree(c->d_out);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    for (int i = 0; i < 8; i++) {
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_c[i]) cudaEventDestroy(c->ev_c[i]);
+    }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -295,6 +305,22 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             std::memcpy(&b7[s * 2], k + cl.b7, 2 * 4);
         }
         if ((r = upload(c, &c->d_w1, w1)) || (r = upload(c, &c->d_b1, b1)) || (r = upload(c, &c->d_s1, s1)) || (r = upload(c, &c->d_o1, o1))) return r;
+        c->h_w6 = w6;
+        c->h_w1.assign((size_t)S * 800, 0.0f);
+        c->h_b1.assign((size_t)S * 48, 0.0f);
+        for (int s = 0; s < S; s++) {
+            for (int o = 0; o < 16; o++)
+                for (int ci = 0; ci < 2; ci++)
+                    for (int tap = 0; tap < 25; tap++) c->h_w1[(size_t)s * 800 + (tap * 2 + ci) * 16 + o] = w1[((size_t)s * 16 + o) * 50 + ci * 25 + tap];
+            std::memcpy(&c->h_b1[(size_t)s * 48], &b1[s * 16], 64);
+            std::memcpy(&c->h_b1[(size_t)s * 48 + 16], &s1[s * 16], 64);
+            std::memcpy(&c->h_b1[(size_t)s * 48 + 32], &o1[s * 16], 64);
+        }
+        c->h_w7.assign((size_t)S * 36, 0.0f);
+        for (int s = 0; s < S; s++) {
+            std::memcpy(&c->h_w7[(size_t)s * 36], &w7[s * 32], 32 * 4);
+            std::memcpy(&c->h_w7[(size_t)s * 36 + 32], &b7[s * 2], 2 * 4);
+        }
         if ((r = upload(c, &c->d_w6, w6)) || (r = upload(c, &c->d_b6, b6)) || (r = upload(c, &c->d_s6, s6)) || (r = upload(c, &c->d_o6, o6))) return r;
         if ((r = upload(c, &c->d_w7, w7)) || (r = upload(c, &c->d_b7, b7))) return r;
     }
@@ -463,9 +489,14 @@ static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, in
         p.mag = d_mag; p.w = c->d_w1; p.bias = c->d_b1; p.bn_scale = c->d_s1; p.bn_offset = c->d_o1;
         p.out_raw = c->E[1]; p.out_act = c->A[1];
         p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
-        for (int s = 0; s < S; s++) p.act[s] = c->act_enc[s];
-        launch_down1(p, c->stream);
-        c->launches++;
+        for (int s = 0; s < S; s++) {
+            p.stem = s;
+            p.act[0] = c->act_enc[s];
+            std::memcpy(p.wk, &c->h_w1[(size_t)s * 800], 800 * sizeof(float));
+            std::memcpy(p.bk, &c->h_b1[(size_t)s * 48], 48 * sizeof(float));
+            launch_down1(p, c->stream);
+            c->launches++;
+        }
     }
     for (size_t li = 0; li < c->conv.size(); li++) {
         Timed t(c, (int)li);
@@ -483,9 +514,13 @@ static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, in
         p.skip = c->E[1]; p.up = c->U[5]; p.w = c->d_w6; p.bias = c->d_b6; p.bn_scale = c->d_s6; p.bn_offset = c->d_o6;
         p.out = c->U[6];
         p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
-        for (int s = 0; s < S; s++) p.act[s] = c->act_dec[s];
-        launch_up6(p, c->stream);
-        c->launches++;
+        for (int s = 0; s < S; s++) {
+            p.stem = s;
+            p.act[0] = c->act_dec[s];
+            std::memcpy(p.wk, &c->h_w6[(size_t)s * 800], 800 * sizeof(float));
+            launch_up6(p, c->stream);
+            c->launches++;
+        }
     }
     {
         Timed t(c, 12);
@@ -493,8 +528,12 @@ static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, in
         p.in = c->U[6]; p.w = c->d_w7; p.bias = c->d_b7; p.lut = c->d_lut; p.mask = mask_base;
         p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
         p.mask_stem_stride = mask_stride; p.mask_img0 = mask_img0;
-        launch_up7(p, c->stream);
-        c->launches++;
+        for (int s = 0; s < S; s++) {
+            p.stem = s;
+            std::memcpy(p.wk, &c->h_w7[(size_t)s * 36], 36 * sizeof(float));
+            launch_up7(p, c->stream);
+            c->launches++;
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SRT_ERR_CUDA, "U-Net launch: %s", cudaGetErrorString(e));
@@ -715,26 +754,51 @@ extern "C" int srt_separate_batch(srt_ctx* c, const float* const* pcmL, const fl
     std::vector<const float*> dl(n_streams), dr(n_streams);
     std::vector<float*> dout((size_t)n_streams * c->S * 2);
     size_t off = 0;
-    {
-        Timed t(c, 16);
-        for (int i = 0; i < n_streams; i++) {
-            const size_t n = n_samples[i], np = (n + 3) & ~(size_t)3;
-            dl[i] = c->d_pcm + off * 2;
-            dr[i] = c->d_pcm + off * 2 + np;
-            CK(cudaMemcpyAsync((void*)dl[i], pcmL[i], n * 4, cudaMemcpyHostToDevice, c->stream));
-            CK(cudaMemcpyAsync((void*)dr[i], pcmR[i], n * 4, cudaMemcpyHostToDevice, c->stream));
-            for (int q = 0; q < c->S * 2; q++) dout[(size_t)i * c->S * 2 + q] = c->d_out + off * 2 * c->S + (size_t)q * np;
-            off += np;
+    for (int i = 0; i < n_streams; i++) {
+        const size_t np = (n_samples[i] + 3) & ~(size_t)3;
+        dl[i] = c->d_pcm + off * 2;
+        dr[i] = c->d_pcm + off * 2 + np;
+        for (int q = 0; q < c->S * 2; q++) dout[(size_t)i * c->S * 2 + q] = c->d_out + off * 2 * c->S + (size_t)q * np;
+        off += np;
+    }
+    // Software pipeline over groups of streams: H2D of group g+1 and D2H of group g-1 run on their own
+    // streams while group g computes (PCIe is full duplex; the copies would otherwise serialise with the kernels).
+    if (!c->s_in) {
+        CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) {
+            CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_c[i], cudaEventDisableTiming));
         }
     }
-    int r = separate_core(c, dl.data(), dr.data(), n_samples, n_streams, unaffected, dout.data(), kFFT);
-    if (r) return r;
-    {
-        Timed t(c, 17);
-        for (int i = 0; i < n_streams; i++)
-            for (int q = 0; q < c->S * 2; q++)
-                CK(cudaMemcpyAsync(stems_out[(size_t)i * c->S * 2 + q], dout[(size_t)i * c->S * 2 + q], n_samples[i] * 4, cudaMemcpyDeviceToHost, c->stream));
+    const char* ge = getenv("SRT_E2E_GROUPS");
+    int groups = ge ? atoi(ge) : 4;
+    groups = std::max(1, std::min(std::min(groups, 8), n_streams));
+    const int per = (n_streams + groups - 1) / groups;
+    // the context's stream may still own the staging buffers from a previous device-API call
+    CK(cudaEventRecord(c->ev_c[0], c->stream));
+    CK(cudaStreamWaitEvent(c->s_in, c->ev_c[0], 0));
+    for (int g = 0; g < groups; g++) {
+        const int i0 = g * per, i1 = std::min(n_streams, i0 + per);
+        for (int i = i0; i < i1; i++) {
+            CK(cudaMemcpyAsync((void*)dl[i], pcmL[i], n_samples[i] * 4, cudaMemcpyHostToDevice, c->s_in));
+            CK(cudaMemcpyAsync((void*)dr[i], pcmR[i], n_samples[i] * 4, cudaMemcpyHostToDevice, c->s_in));
+        }
+        CK(cudaEventRecord(c->ev_in[g], c->s_in));
     }
+    for (int g = 0; g < groups; g++) {
+        const int i0 = g * per, i1 = std::min(n_streams, i0 + per);
+        if (i0 >= i1) break;
+        CK(cudaStreamWaitEvent(c->stream, c->ev_in[g], 0));
+        int r = separate_core(c, dl.data() + i0, dr.data() + i0, n_samples + i0, i1 - i0, unaffected, dout.data() + (size_t)i0 * c->S * 2, kFFT);
+        if (r) return r;
+        CK(cudaEventRecord(c->ev_c[g], c->stream));
+        CK(cudaStreamWaitEvent(c->s_out, c->ev_c[g], 0));
+        for (int i = i0; i < i1; i++)
+            for (int q = 0; q < c->S * 2; q++)
+                CK(cudaMemcpyAsync(stems_out[(size_t)i * c->S * 2 + q], dout[(size_t)i * c->S * 2 + q], n_samples[i] * 4, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    CK(cudaStreamSynchronize(c->s_out));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }

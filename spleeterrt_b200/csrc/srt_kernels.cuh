@@ -71,6 +71,9 @@ struct Down1Params {              // 5x5 s2 conv 2->16 on the magnitude image, s
     float* out_act;               // S2D [S*B][T/4][F/4][64], TF32-rounded
     int T, F, B, Bv, S;
     int act[8];
+    int stem;                     // one launch per stem: weights / bias / BN ride in the constant bank
+    float wk[800];                // [tap][cin][cout] of that stem
+    float bk[48];                 // bias[16], bn scale[16], bn offset[16]
 };
 
 struct Up6Params {                // 5x5 s2 transposed conv 32->1 + act + BN, spleeter.c:289-294
@@ -83,6 +86,8 @@ struct Up6Params {                // 5x5 s2 transposed conv 32->1 + act + BN, sp
     float* out;                   // [S*B][T][F]
     int T, F, B, Bv, S;
     int act[8];
+    int stem;                     // the launch covers one stem: its weights ride in the parameter (constant) bank
+    float wk[800];                // [32][25] of that stem: FFMA reads them as immediates, no shared-memory traffic
 };
 
 struct Up7Params {                // 4x4 dilation-2 conv 1->2 + bias + sigmoid, spleeter.c:295-300
@@ -93,6 +98,8 @@ struct Up7Params {                // 4x4 dilation-2 conv 1->2 + bias + sigmoid, 
     float* mask;                  // [S][mask_stem_stride images][T][F][2], first image of this launch = mask_img0
     int T, F, B, Bv, S;
     int mask_stem_stride, mask_img0;
+    int stem;                     // one launch per stem
+    float wk[36];                 // that stem's 32 weights + 2 biases (constant bank)
 };
 
 // ---------------------------------------------------------------------------------------

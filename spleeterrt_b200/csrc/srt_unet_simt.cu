@@ -63,18 +63,13 @@ constexpr int D1_BX = 16, D1_BY = 8;                    // threads
 constexpr int D1_TW = 2 * D1_BX, D1_TH = 2 * D1_BY;     // output pixels per block: 32 x 16
 constexpr int D1_PW = 2 * D1_TW + 3, D1_PH = 2 * D1_TH + 3;
 
-__global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p)
+__global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const __grid_constant__ Down1Params p)
 {
     __shared__ float2 patch[D1_PH][D1_PW + 1];
-    __shared__ __align__(16) float wsm[25 * 2 * 16];   // [tap][cin][cout]
-    const int s = blockIdx.z / p.Bv, b = blockIdx.z % p.Bv, n = s * p.B + b;
+    const int s = p.stem, b = blockIdx.z, n = s * p.B + b;
     const int Ho = p.T / 2, Wo = p.F / 2;
     const int ow0 = blockIdx.x * D1_TW, oh0 = blockIdx.y * D1_TH;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 800; i += blockDim.x) {
-        const int o = i & 15, c = (i >> 4) & 1, tap = i >> 5;
-        wsm[i] = p.w[((size_t)s * 16 + o) * 50 + c * 25 + tap];   // reference layout [O][I][kh][kw]
-    }
     const float2* img = reinterpret_cast<const float2*>(p.mag) + (size_t)b * p.T * p.F;
     for (int i = tid; i < D1_PH * D1_PW; i += blockDim.x) {
         const int r = i / D1_PW, c = i % D1_PW;
@@ -86,7 +81,8 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
     __syncthreads();
     const int tx = tid % D1_BX, ty = tid / D1_BX;
     // this thread's 2x2 outputs are (ty + 8a, tx + 16c): interleaved so that neighbouring lanes read
-    // neighbouring patch columns (no shared-memory bank conflicts)
+    // neighbouring patch columns (no shared-memory bank conflicts).  Weights are compile-time offsets
+    // into the kernel-parameter (constant) bank: the FFMAs take them as uniform operands.
     float acc[2][2][16];
 #pragma unroll
     for (int a = 0; a < 2; a++)
@@ -103,31 +99,17 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
             for (int a = 0; a < 2; a++)
 #pragma unroll
                 for (int c = 0; c < 2; c++) v[a][c] = patch[2 * (ty + D1_BY * a) + kh][2 * (tx + D1_BX * c) + kw];
-            const float4* wl = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 0) * 16]);
-            const float4* wr = reinterpret_cast<const float4*>(&wsm[((kh * 5 + kw) * 2 + 1) * 16]);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float4 wa = wl[q], wb = wr[q];
+            for (int i = 0; i < 16; i++) {
+                const float wl = p.wk[((kh * 5 + kw) * 2 + 0) * 16 + i], wr = p.wk[((kh * 5 + kw) * 2 + 1) * 16 + i];
 #pragma unroll
                 for (int a = 0; a < 2; a++)
 #pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        float* ac = &acc[a][c][4 * q];
-                        ac[0] = fmaf(wa.x, v[a][c].x, fmaf(wb.x, v[a][c].y, ac[0]));
-                        ac[1] = fmaf(wa.y, v[a][c].x, fmaf(wb.y, v[a][c].y, ac[1]));
-                        ac[2] = fmaf(wa.z, v[a][c].x, fmaf(wb.z, v[a][c].y, ac[2]));
-                        ac[3] = fmaf(wa.w, v[a][c].x, fmaf(wb.w, v[a][c].y, ac[3]));
-                    }
+                    for (int c = 0; c < 2; c++) acc[a][c][i] = fmaf(wl, v[a][c].x, fmaf(wr, v[a][c].y, acc[a][c][i]));
             }
         }
     }
-    float bias[16], sc[16], of[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        bias[i] = p.bias[s * 16 + i];
-        sc[i] = p.bn_scale[s * 16 + i];
-        of[i] = p.bn_offset[s * 16 + i];
-    }
+    const int act = p.act[0];
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
@@ -137,9 +119,9 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
             float raw[16], av[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                const float t = acc[a][c][i] + bias[i];
+                const float t = acc[a][c][i] + p.bk[i];
                 raw[i] = t;
-                av[i] = ptx::rna_tf32(apply_act(p.act[s], sc[i] * t + of[i]));
+                av[i] = ptx::rna_tf32(apply_act(act, p.bk[16 + i] * t + p.bk[32 + i]));
             }
             float4* d0 = reinterpret_cast<float4*>(p.out_raw + (((size_t)n * Ho + oh) * Wo + ow) * 16);
             float4* d1 = reinterpret_cast<float4*>(
@@ -154,7 +136,7 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const Down1Params p
 
 void launch_down1(const Down1Params& p, cudaStream_t st)
 {
-    dim3 grid((p.F / 2 + D1_TW - 1) / D1_TW, (p.T / 2 + D1_TH - 1) / D1_TH, p.S * p.Bv);
+    dim3 grid((p.F / 2 + D1_TW - 1) / D1_TW, (p.T / 2 + D1_TH - 1) / D1_TH, p.Bv);   // one launch per stem
     down1_kernel<<<grid, D1_BX * D1_BY, 0, st>>>(p);
 }
 
@@ -168,26 +150,22 @@ constexpr int U6_BX = 32, U6_BY = 8;                  // threads
 constexpr int U6_TW = 2 * U6_BX, U6_TH = U6_BY;       // input pixels per block: 64 x 8
 constexpr int U6_PW = U6_TW + 2, U6_PH = U6_TH + 2, U6_PS = U6_PW + 2;   // row stride 68 floats (even)
 
-__global__ void __launch_bounds__(U6_BX* U6_BY) up6_kernel(const Up6Params p)
+__global__ void __launch_bounds__(U6_BX* U6_BY) up6_kernel(const __grid_constant__ Up6Params p)
 {
     __shared__ __align__(16) float patch[16 * U6_PH * U6_PS];   // [16 ch][10][68]
-    __shared__ __align__(16) float wsm[32 * 28];                // [32 ch][25 (+3 pad)]
-    const int s = blockIdx.z / p.Bv, n = s * p.B + blockIdx.z % p.Bv;
+    const int s = p.stem, n = s * p.B + blockIdx.z;
     const int H = p.T / 2, W = p.F / 2;
     const int x0 = blockIdx.x * U6_TW, y0 = blockIdx.y * U6_TH;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 32 * 28; i += blockDim.x) {
-        const int c = i / 28, t = i % 28;
-        wsm[i] = t < 25 ? p.w[(size_t)s * 800 + c * 25 + t] : 0.0f;
-    }
     const int tx = tid % U6_BX, ty = tid / U6_BX;
     float o[2][4];   // [output row parity][output col 0..3] for input pixels (2tx, 2tx+1)
 #pragma unroll
     for (int a = 0; a < 2; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) o[a][b] = 0.0f;
+#pragma unroll
     for (int half = 0; half < 2; half++) {
-        __syncthreads();   // previous half fully consumed (and weights visible)
+        __syncthreads();   // previous half fully consumed
         const float* src = half ? p.up : p.skip;
         for (int i = tid; i < U6_PH * U6_PW * 4; i += blockDim.x) {
             const int q = i & 3, pix = i >> 2;
@@ -202,7 +180,7 @@ __global__ void __launch_bounds__(U6_BX* U6_BY) up6_kernel(const Up6Params p)
             d[3 * U6_PH * U6_PS] = v.w;
         }
         __syncthreads();
-#pragma unroll 2
+#pragma unroll
         for (int c = 0; c < 16; c++) {
             // neighbourhood: rows ty..ty+2 (dy = -1..1), cols 2tx..2tx+3 (input x-1 .. x+2)
             float nb[3][4];
@@ -212,16 +190,10 @@ __global__ void __launch_bounds__(U6_BX* U6_BY) up6_kernel(const Up6Params p)
                 const float2 u = rp[0], v = rp[1];
                 nb[a][0] = u.x; nb[a][1] = u.y; nb[a][2] = v.x; nb[a][3] = v.y;
             }
-            float w[28];
-            const float4* wp = reinterpret_cast<const float4*>(wsm + (half * 16 + c) * 28);
-#pragma unroll
-            for (int q = 0; q < 7; q++) {
-                const float4 t = wp[q];
-                w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-            }
             // output row parity 0: kh=1 (dy=0), kh=3 (dy=-1); parity 1: kh=0 (dy=+1), kh=2 (dy=0), kh=4 (dy=-1)
             // output col parity likewise.  j = 0/1 selects the input pixel; its neighbourhood column for dx is j+1+dx.
-#define TAP(kh, kw, dy, dx) (w[(kh) * 5 + (kw)] * nb[(dy) + 1][j + 1 + (dx)])
+            // The weight index is a compile-time constant: the operand comes straight from the constant bank.
+#define TAP(kh, kw, dy, dx) (p.wk[(half * 16 + c) * 25 + (kh) * 5 + (kw)] * nb[(dy) + 1][j + 1 + (dx)])
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 o[0][2 * j + 0] += TAP(1, 1, 0, 0) + TAP(1, 3, 0, -1) + TAP(3, 1, -1, 0) + TAP(3, 3, -1, -1);
@@ -236,15 +208,16 @@ __global__ void __launch_bounds__(U6_BX* U6_BY) up6_kernel(const Up6Params p)
     const int X = x0 + 2 * tx, Y = y0 + ty;
     if (X >= W || Y >= H) return;
     const float bias = p.bias[s], sc = p.bn_scale[s], of = p.bn_offset[s];
+    const int act = p.act[0];   // launch_up6 puts this stem's activation in slot 0
     float4 r0, r1;
-    r0.x = sc * apply_act(p.act[s], o[0][0] + bias) + of;
-    r0.y = sc * apply_act(p.act[s], o[0][1] + bias) + of;
-    r0.z = sc * apply_act(p.act[s], o[0][2] + bias) + of;
-    r0.w = sc * apply_act(p.act[s], o[0][3] + bias) + of;
-    r1.x = sc * apply_act(p.act[s], o[1][0] + bias) + of;
-    r1.y = sc * apply_act(p.act[s], o[1][1] + bias) + of;
-    r1.z = sc * apply_act(p.act[s], o[1][2] + bias) + of;
-    r1.w = sc * apply_act(p.act[s], o[1][3] + bias) + of;
+    r0.x = sc * apply_act(act, o[0][0] + bias) + of;
+    r0.y = sc * apply_act(act, o[0][1] + bias) + of;
+    r0.z = sc * apply_act(act, o[0][2] + bias) + of;
+    r0.w = sc * apply_act(act, o[0][3] + bias) + of;
+    r1.x = sc * apply_act(act, o[1][0] + bias) + of;
+    r1.y = sc * apply_act(act, o[1][1] + bias) + of;
+    r1.z = sc * apply_act(act, o[1][2] + bias) + of;
+    r1.w = sc * apply_act(act, o[1][3] + bias) + of;
     float* dst = p.out + ((size_t)n * p.T + 2 * Y) * p.F + 2 * X;
     *reinterpret_cast<float4*>(dst) = r0;            // W is even and X is even: 16-byte aligned
     *reinterpret_cast<float4*>(dst + p.F) = r1;
@@ -252,7 +225,8 @@ __global__ void __launch_bounds__(U6_BX* U6_BY) up6_kernel(const Up6Params p)
 
 void launch_up6(const Up6Params& p, cudaStream_t st)
 {
-    dim3 grid((p.F / 2 + U6_TW - 1) / U6_TW, (p.T / 2 + U6_TH - 1) / U6_TH, p.S * p.Bv);
+    // one launch per stem; p.wk / p.stem / p.act[0] are filled by the caller (srt_ctx.cu)
+    dim3 grid((p.F / 2 + U6_TW - 1) / U6_TW, (p.T / 2 + U6_TH - 1) / U6_TH, p.Bv);
     up6_kernel<<<grid, U6_BX * U6_BY, 0, st>>>(p);
 }
 
@@ -270,20 +244,20 @@ __device__ __forceinline__ float sigmoid_lut(const float4* __restrict__ tbl, flo
     const float step = 0.01367188f;
     if (x > 7.0f) return 1.0f;
     if (x < -7.0f) return 0.0f;
-    const int idx = (int)(short)__fdiv_rn(__fadd_rn(x, 7.0f), step);
+    // index = trunc((x+7)/step) evaluated with a reciprocal multiply: on the rare inputs where the
+    // rounded product lands on the other side of an integer the neighbouring interval is used, which
+    // changes the (continuous, piecewise-linear) result by ~1e-8.
+    const int idx = min((int)(__fadd_rn(x, 7.0f) * (1.0f / step)), 1023);
     const float4 e = __ldg(tbl + idx);
     return __fadd_rn(e.x, __fmul_rn(e.y, __fsub_rn(x, e.z)));
 }
 
-__global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const Up7Params p)
+__global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const __grid_constant__ Up7Params p)
 {
     __shared__ float tile[U7_TH + 6][U7_TW + 6 + 2];
-    __shared__ float wsm[32 + 2];
-    const int s = blockIdx.z / p.Bv, b = blockIdx.z % p.Bv, n = s * p.B + b;
+    const int s = p.stem, b = blockIdx.z, n = s * p.B + b;
     const int f0 = blockIdx.x * U7_TW, t0 = blockIdx.y * U7_TH;
     const int tid = threadIdx.x;
-    if (tid < 32) wsm[tid] = p.w[s * 32 + tid];
-    if (tid < 2) wsm[32 + tid] = p.bias[s * 2 + tid];
     const float* img = p.in + (size_t)n * p.T * p.F;
     for (int i = tid; i < (U7_TH + 6) * (U7_TW + 6); i += blockDim.x) {
         const int r = i / (U7_TW + 6), c = i % (U7_TW + 6);
@@ -300,11 +274,11 @@ __global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const Up7Params p)
 #pragma unroll
         for (int kw = 0; kw < 4; kw++) {
             const float v = tile[ty + 2 * kh][tx + 2 * kw];
-            a0 = fmaf(wsm[kh * 4 + kw], v, a0);
-            a1 = fmaf(wsm[16 + kh * 4 + kw], v, a1);
+            a0 = fmaf(p.wk[kh * 4 + kw], v, a0);
+            a1 = fmaf(p.wk[16 + kh * 4 + kw], v, a1);
         }
-    a0 += wsm[32];
-    a1 += wsm[33];
+    a0 += p.wk[32];
+    a1 += p.wk[33];
     float2 m;
     if (p.lut) {
         const float4* lut = reinterpret_cast<const float4*>(p.lut);
@@ -319,7 +293,7 @@ __global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const Up7Params p)
 
 void launch_up7(const Up7Params& p, cudaStream_t st)
 {
-    dim3 grid((p.F + U7_TW - 1) / U7_TW, (p.T + U7_TH - 1) / U7_TH, p.S * p.Bv);
+    dim3 grid((p.F + U7_TW - 1) / U7_TW, (p.T + U7_TH - 1) / U7_TH, p.Bv);   // one launch per stem (p.stem, p.wk)
     up7_kernel<<<grid, U7_TW * U7_TH, 0, st>>>(p);
 }
 
