@@ -170,8 +170,11 @@ def main():
     torch.cuda.set_stream(stream)
     sep = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream)
 
-    # ---- inputs: rank-distinct synthetic streams -------------------------------------------
-    pcm = [W.synth_pcm(rank * ns + i, n=N_SAMPLES) for i in range(min(ns, 4))]
+    # ---- inputs: stream i of the global batch lives on rank i mod world (dispatch.py) -----------
+    from spleeterrt_b200 import dispatch as D
+    my_streams = D.stream_ids_for_rank(ns * world, world, rank)
+    assert len(my_streams) == ns
+    pcm = [W.synth_pcm(sid, n=N_SAMPLES) for sid in my_streams[:4]]
     hin = torch.empty((ns, 2, N_SAMPLES), dtype=torch.float32).pin_memory()
     for i in range(ns):
         hin[i, 0] = torch.from_numpy(pcm[i % len(pcm)][0])
@@ -197,16 +200,11 @@ def main():
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(x, device="cuda")
 
     # ---- device-resident throughput ----------------------------------------------------------
     for _ in range(args.warmup):
