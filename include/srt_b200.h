@@ -97,6 +97,22 @@ int srt_stft_host(srt_ctx* ctx, const float* L, const float* R, size_t n,
 int srt_istft_host(srt_ctx* ctx, const float* reL, const float* imL, const float* reR, const float* imR,
                    size_t frames, float* outL, float* outR);
 
+/* ---- real-time streaming flavour (VST/Source/Spleeter4Stems.c) ------------------------------
+ * One stereo stream, n_stems nets (the VST uses 4, all ELU).  Every 1024 new samples ("hop") the
+ * newest 4096-sample frame is analysed (asymmetric window, Spleeter4Stems.c:383-416) and the frame
+ * recorded two T-frame tiles earlier is synthesised with that tile's masks (:257-320); every T hops
+ * the nets run on the finished tile in the background (:351-371).  Latency 2*T*1024 + 1024 samples.
+ * srt_stream_process mirrors Spleeter4StemsProcessSamples (:512-582): `components` = 2*n_stems
+ * planar outputs (stem-major, L then R), written only when output is available.
+ * cfg: n_stems, time_step, bin_limit, device are used (flavour is forced to 1 = VST: exact sigmoid,
+ * unclamped ELU); unaffected[s] = weight of the bins >= F (NULL = 0.25, 0.0, 0.25, 0.25 as
+ * Spleeter4Stems.c:73,281). */
+typedef struct srt_stream srt_stream;
+int srt_stream_create(const srt_config* cfg, const float* const* coeffs, const float* unaffected, srt_stream** out);
+int srt_stream_process(srt_stream* st, const float* inL, const float* inR, int n, float* const* components);
+void srt_stream_destroy(srt_stream* st);
+long long srt_stream_launch_count(const srt_stream* st);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 long long srt_launch_count(const srt_ctx* ctx);

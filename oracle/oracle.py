@@ -357,6 +357,39 @@ class RefExec:
         return out
 
 
+class RefVst:
+    """The reference's real-time streamer (VST/Source/Spleeter4Stems.c) compiled as is into
+    oracle/_ref/libref_vst.so (naive CPU_GEMM backend).  One instance = one Spleeter4Stems object."""
+
+    def __init__(self, nets, T, F):
+        path = os.path.join(REF_DIR, "libref_vst.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.Spleeter4StemsInit.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self.lib.Spleeter4StemsProcessSamples.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, C.c_void_p]
+        self.lib.Spleeter4StemsFree.argtypes = [C.c_void_p]
+        assert len(nets) == 4
+        self.coeffs = [np.ascontiguousarray(c, np.float32) for c, _ in nets]
+        self.cp = (C.c_void_p * 4)(*[c.ctypes.data for c in self.coeffs])
+        self.obj = C.create_string_buffer(4 << 20)          # >= sizeof(Spleeter4Stems) (~0.4 MB)
+        self.lib.Spleeter4StemsInit(self.obj, F, T, self.cp)
+
+    def process(self, L, R):
+        """feed one block (<= 1024 samples); returns float32[8][n] with NaN where nothing was written"""
+        L = np.ascontiguousarray(L, np.float32)
+        R = np.ascontiguousarray(R, np.float32)
+        out = np.full((8, L.size), np.nan, np.float32)
+        ptrs = (C.c_void_p * 8)(*[out[j].ctypes.data for j in range(8)])
+        self.lib.Spleeter4StemsProcessSamples(self.obj, L, R, L.size, ptrs)
+        return out
+
+    def close(self):
+        if self.obj is not None:
+            self.lib.Spleeter4StemsFree(self.obj)
+            self.obj = None
+
+
 _ref_exec = None
 
 

@@ -18,10 +18,12 @@ HEADER_SYMBOLS = {
     "srt_b200.h": ["srt_create", "srt_destroy", "srt_last_error", "srt_half_to_float", "srt_unet_host",
                    "srt_unet_device", "srt_separate_batch", "srt_separate_device", "srt_stft_rows",
                    "srt_stft_host", "srt_istft_host", "srt_launch_count", "srt_last_timing", "srt_set_timing",
-                   "srt_debug_tensor", "srt_host_alloc", "srt_host_free", "srt_synchronize"],
+                   "srt_debug_tensor", "srt_host_alloc", "srt_host_free", "srt_synchronize",
+                   "srt_stream_create", "srt_stream_process", "srt_stream_destroy", "srt_stream_launch_count"],
     "spleeter.h": ["getCoeffSize", "allocateSpleeterStr", "initSpleeter", "getMaskPtr", "processSpleeter",
                    "freeSpleeter"],
     "stftFix.h": ["InitSTFT", "FreeSTFT", "stft", "istft"],
+    "Spleeter4Stems.h": ["Spleeter4StemsInit", "Spleeter4StemsFree", "Spleeter4StemsProcessSamples"],
 }
 
 
@@ -74,6 +76,11 @@ def load_library():
     lib.srt_host_free.argtypes = [C.c_void_p]
     lib.srt_synchronize.argtypes = [C.c_void_p]
     lib.srt_half_to_float.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.srt_stream_create.argtypes = [C.POINTER(_Config), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.srt_stream_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.srt_stream_destroy.argtypes = [C.c_void_p]
+    lib.srt_stream_launch_count.restype = C.c_longlong
+    lib.srt_stream_launch_count.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -219,3 +226,48 @@ class Separator:
 
     def synchronize(self):
         self._check(self.lib.srt_synchronize(self.h))
+
+
+class Streamer:
+    """Real-time streaming flavour: mirrors Spleeter4StemsInit / ProcessSamples / Free
+    (VST/Source/Spleeter4Stems.h:67-69).  nets: list of coeff arrays (all ELU, as the VST does)."""
+
+    def __init__(self, coeffs, time_step, bin_limit, device=0, unaffected=None):
+        self.lib = load_library()
+        self.S = len(coeffs)
+        self._coeffs = [np.ascontiguousarray(c, np.float32) for c in coeffs]
+        cfg = _Config(device, self.S, time_step, bin_limit, 1, 1, 1, 0, None)
+        cp = (C.c_void_p * self.S)(*[c.ctypes.data for c in self._coeffs])
+        uw = None
+        if unaffected is not None:
+            uw = (C.c_float * self.S)(*[float(u) for u in unaffected])
+        h = C.c_void_p()
+        rc = self.lib.srt_stream_create(C.byref(cfg), cp, uw, C.byref(h))
+        if rc != 0:
+            raise SrtError(f"srt error {rc}: {self.lib.srt_last_error().decode()}")
+        self.h = h
+
+    def process(self, L, R):
+        """feed one block; returns float32[2S][n] (NaN where the call wrote nothing, as the reference leaves it untouched)"""
+        L = np.ascontiguousarray(L, np.float32)
+        R = np.ascontiguousarray(R, np.float32)
+        out = np.full((2 * self.S, L.size), np.nan, np.float32)
+        ptrs = (C.c_void_p * (2 * self.S))(*[out[j].ctypes.data for j in range(2 * self.S)])
+        rc = self.lib.srt_stream_process(self.h, L.ctypes.data, R.ctypes.data, L.size, ptrs)
+        if rc != 0:
+            raise SrtError(f"srt error {rc}: {self.lib.srt_last_error().decode()}")
+        return out
+
+    def launch_count(self):
+        return int(self.lib.srt_stream_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.srt_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/srt_b200.h"
+#include "srt_internal.h"
 #include "srt_kernels.cuh"
 #include "srt_plan.h"
 
@@ -542,6 +543,19 @@ static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, in
 
 // Spans accumulate over calls while timing is on (so a caller can time K back-to-back steps
 // without a host sync in between) and are cleared by srt_set_timing().
+namespace srt {
+namespace internal {
+int ctx_run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, int mask_stride, int mask_img0)
+{
+    return run_unet(c, d_mag, Bv, mask_base, mask_stride, mask_img0);
+}
+cudaStream_t ctx_stream(srt_ctx* c) { return c->stream; }
+const float2* ctx_twiddle(srt_ctx* c) { return c->d_twiddle; }
+void ctx_count_launch(srt_ctx* c, int n) { c->launches += n; }
+int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+}  // namespace internal
+}  // namespace srt
+
 static void reset_spans(srt_ctx* c)
 {
     if (c->timing) return;

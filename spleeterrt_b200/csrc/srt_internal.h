@@ -1,0 +1,16 @@
+// srt_internal.h — the few context internals the streaming flavour (srt_stream.cu) needs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/srt_b200.h"
+
+namespace srt {
+namespace internal {
+// U-Net on Bv images (layout [Bv][T][F][2]) of `ctx`, masks to mask_base[s][mask_img0 + b]; enqueued on ctx's stream
+int ctx_run_unet(srt_ctx* ctx, const float* d_mag, int Bv, float* mask_base, int mask_stride, int mask_img0);
+cudaStream_t ctx_stream(srt_ctx* ctx);
+const float2* ctx_twiddle(srt_ctx* ctx);
+void ctx_count_launch(srt_ctx* ctx, int n);
+int set_error(int code, const char* msg);
+}  // namespace internal
+}  // namespace srt

@@ -215,3 +215,46 @@ def test_capacity_errors_are_loud(srt, oracle):
     sep.close()
     with pytest.raises(srt.SrtError):
         srt.Separator([(coeff, 1)], 60, 64)       # T must be a multiple of 64
+
+
+# ----------------------------------------------------------------------------- streaming (VST) flavour
+def test_unet_vst_flavour(srt, oracle, small_nets):
+    """exact sigmoid + unclamped ELU (VST/Source/spleeter.c:56-77)"""
+    T, F = 64, 128
+    coeff = small_nets[0][0]
+    x = (np.abs(np.random.default_rng(2).standard_normal((2, T, F))) * 3).astype(np.float32)
+    sep = srt.Separator([(coeff, 1)], T, F, max_images=1, flavour=1)
+    y = sep.process_spleeter(x)[0, 0]
+    sep.close()
+    ref = oracle.unet(coeff, x, 1, flavour=1)
+    assert rms(y - ref) < 5e-4 and np.abs(y - ref).max() < 3e-2
+
+
+@pytest.mark.parametrize("block", [1024, 512, 300])
+def test_streamer_vs_reference_vst(srt, oracle, block):
+    """Spleeter4Stems flavour against the reference's own streamer (oracle/_ref/libref_vst.so): same
+    delayed output (2*T*1024 + 1024 samples), same untouched-output pattern, 1e-4 RMS per component."""
+    if not os.path.exists(os.path.join(oracle.REF_DIR, "libref_vst.so")):
+        pytest.skip("reference VST build absent")
+    T, F = 64, 512
+    nets = [(oracle.synthetic_weights(40 + k), 1) for k in range(4)]
+    n_total = (2 * T + 6) * 1024
+    L, R = oracle.synth_pcm(7, n=n_total)
+    ref = oracle.RefVst(nets, T, F)
+    got = srt.Streamer([c for c, _ in nets], T, F)
+    outs_r, outs_g = [], []
+    for o in range(0, n_total, block):
+        l, r = L[o:o + block], R[o:o + block]
+        outs_r.append(ref.process(l, r))
+        outs_g.append(got.process(l, r))
+    launches = got.launch_count()
+    ref.close()
+    got.close()
+    a, b = np.concatenate(outs_r, axis=1), np.concatenate(outs_g, axis=1)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "output availability pattern differs"
+    ok = ~np.isnan(a[0])
+    tail = slice(2 * T * 1024 + 1024, None)                   # where real (non-zero) output starts
+    assert rms(a[:, tail][:, ok[tail]]) > 1e-3
+    for j in range(8):
+        assert rms(a[j][ok] - b[j][ok]) < 1e-4, f"component {j}: {rms(a[j][ok] - b[j][ok])}"
+    assert launches >= n_total // 1024
