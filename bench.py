@@ -247,6 +247,35 @@ def main():
     torch.cuda.synchronize()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
 
+    # ---- single stream (BASELINE.json configs[1]): one 10 s stereo stream, 4 stems, latency --------------
+    single = None
+    if rank == 0:
+        sep1 = srt.Separator(nets, T, F, max_images=1, max_batch_images=1, device=local_rank, cuda_stream=stream.cuda_stream)
+        n1 = (C.c_size_t * 1)(N_SAMPLES)
+        d1l, d1r = (C.c_void_p * 1)(din[0, 0].data_ptr()), (C.c_void_p * 1)(din[0, 1].data_ptr())
+        d1o = (C.c_void_p * (S * 2))(*[dout[0, s, c].data_ptr() for s in range(S) for c in range(2)])
+        h1l, h1r = (C.c_void_p * 1)(hin[0, 0].data_ptr()), (C.c_void_p * 1)(hin[0, 1].data_ptr())
+        h1o = (C.c_void_p * (S * 2))(*[hout[0, s, c].data_ptr() for s in range(S) for c in range(2)])
+        for _ in range(3):
+            sep1.separate_raw(d1l, d1r, n1, 1, None, d1o, device=True)
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record(stream)
+        for _ in range(reps):
+            sep1.separate_raw(d1l, d1r, n1, 1, None, d1o, device=True)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / reps
+        for _ in range(2):
+            sep1.separate_raw(h1l, h1r, n1, 1, None, h1o, device=False)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sep1.separate_raw(h1l, h1r, n1, 1, None, h1o, device=False)
+        ms1e = (time.perf_counter() - t0) * 1e3 / reps
+        single = {"ms_device": ms1, "x_realtime_device": SECONDS / (ms1 * 1e-3), "ms_e2e": ms1e,
+                  "x_realtime_e2e": SECONDS / (ms1e * 1e-3), "note": "one 10 s stereo stream, 4 stems, batch of 1 tile"}
+        sep1.close()
+
     if rank == 0:
         pk = peaks()
         frames = W.padded_frames(N_SAMPLES)
@@ -287,6 +316,7 @@ def main():
                            "istft_ola_gbs": istft_bytes / ((other["istft"] + other["ola"]) * 1e-3) / 1e9 if other["istft"] > 0 else None,
                            "peak_gbs": pk["hbm_gbs"]},
             "timed_with_layer_events_ms": ms_dev,
+            "single_stream": single,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -199,7 +199,10 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 const int Y = tl.y0 + r;
                 const bool valid = X < p.ep.Ws && Y < p.ep.Hs;
 #pragma unroll 1
-                for (int c0 = half * 16; c0 < N; c0 += 32) {
+                // the two epilogue warps of a lane quarter split the columns in two contiguous halves, so each
+                // thread writes whole 128-byte lines (for the fused decoder layers: both column parities of one
+                // output row; for the encoder: half of the pixel's channels)
+                for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(acc + (uint32_t)(r * N + c0), v);
                     if (valid && !(p.dbg & 1)) {

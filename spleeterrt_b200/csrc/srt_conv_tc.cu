@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         ptx::mbar_wait(&hdr->tmem_full, 0);
         ptx::tc_fence_after();
 #pragma unroll 1
-        for (int c0 = half * 16; c0 < N_TILE; c0 += 32) {
+        constexpr int kHalfCols = N_TILE >= 32 ? N_TILE / 2 : N_TILE;   // contiguous column halves per warp pair
+        for (int c0 = half * kHalfCols; c0 < (half + 1) * kHalfCols && c0 < N_TILE; c0 += 16) {
             float v[16];
             ptx::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (valid) epilogue16(p, s, n, Y, X, phase, nt * N_TILE + c0, v);
