@@ -357,6 +357,35 @@ class RefExec:
         return out
 
 
+class PortVst:
+    """oracle/srt_oracle.c restatement of the streamer (srt_oracle_vst_*)."""
+
+    def __init__(self, nets, T, F, unaffected=None):
+        lib = port()
+        lib.srt_oracle_vst_create.restype = C.c_void_p
+        lib.srt_oracle_vst_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib.srt_oracle_vst_process.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, C.c_void_p]
+        lib.srt_oracle_vst_destroy.argtypes = [C.c_void_p]
+        self.lib, self.S = lib, len(nets)
+        self.coeffs = [np.ascontiguousarray(c, np.float32) for c, _ in nets]
+        cp = (C.c_void_p * self.S)(*[c.ctypes.data for c in self.coeffs])
+        uw = (C.c_float * self.S)(*unaffected) if unaffected is not None else None
+        self.h = lib.srt_oracle_vst_create(cp, self.S, T, F, uw)
+
+    def process(self, L, R):
+        L = np.ascontiguousarray(L, np.float32)
+        R = np.ascontiguousarray(R, np.float32)
+        out = np.full((2 * self.S, L.size), np.nan, np.float32)
+        ptrs = (C.c_void_p * (2 * self.S))(*[out[j].ctypes.data for j in range(2 * self.S)])
+        self.lib.srt_oracle_vst_process(self.h, L, R, L.size, ptrs)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.srt_oracle_vst_destroy(self.h)
+            self.h = None
+
+
 class RefVst:
     """The reference's real-time streamer (VST/Source/Spleeter4Stems.c) compiled as is into
     oracle/_ref/libref_vst.so (naive CPU_GEMM backend).  One instance = one Spleeter4Stems object."""

@@ -516,3 +516,169 @@ void srt_oracle_half_to_float(const uint16_t *in, float *out, size_t n)
         memcpy(&out[i], &bits, 4);
     }
 }
+
+/* ====================================================================================
+ * Real-time streaming flavour: restatement of VST/Source/Spleeter4Stems.c.
+ * Same state machine, written single-threaded: the reference's NN threads are joined before
+ * their masks are used (Spleeter4Stems.c:357-360), so running the nets synchronously at the tile
+ * boundary gives identical output.  VST flavour of the net (exact sigmoid, unclamped ELU).
+ * ================================================================================== */
+typedef struct {
+    int S, T, F;
+    const float **coeff;
+    float uw[8];
+    float awin[SRT_FFT], swin[SRT_FFT];
+    float in[2][SRT_FFT];
+    int in_pos, need, cursor, ofp;
+    float *spec[2][4];              /* [buffer][reL, imL, reR, imR][T][2049]   (:423-438) */
+    float *mag;                     /* [2][T][F]                                (:419-420) */
+    float *mask[2][8];              /* [buffer][stem][2][T][F], start at 1.0    (:447-466) */
+    float *overlap;                 /* [2S][1024]  mOverlapStage2dash */
+    float *ready;                   /* finished hop blocks, interleaved like mOutputBuffer: [1024][2S] */
+    int n_ready, read_off;          /* number of queued blocks (each 1024 * 2S floats), read offset in the first */
+    int cap_ready;
+} orc_vst;
+
+/* getAsymmetricWindow(k = 4096, m = 1024, freq_temporal = 1) + analysis scaling (Spleeter4Stems.c:383-416) */
+static void vst_windows(float *an, float *sy)
+{
+    const int k = SRT_FFT, m = 1024;
+    memset(sy, 0, sizeof(float) * k);
+    int n = ((k - m) << 1) + 2;
+    for (int i = 0; i < k - m; ++i) an[i] = (float)pow(0.5 * (1.0 - cos(2.0 * M_PI * (i + 1.0) / (double)n)), 1.0);
+    n = (m << 1) + 2;
+    for (int i = k - m; i < k; ++i) an[i] = (float)pow(sqrt(0.5 * (1.0 - cos(2.0 * M_PI * ((m + i - (k - m)) + 1.0) / (double)n))), 1.0);
+    n = m << 1;
+    for (int i = k - (m << 1); i < k; ++i) sy[i] = (float)(0.5 * (1.0 - cos(2.0 * M_PI * (double)(i - (k - (m << 1))) / (double)n))) / an[i];
+    for (int i = 0; i < k - 2048; i++) sy[i] = sy[i + 2048];          /* pre-shift by SAMPLESHIFT (:399-400) */
+    for (int i = 0; i < k; i++) an[i] *= (1.0 / SRT_FFT) * 0.5f;      /* :415-416 */
+}
+
+void *srt_oracle_vst_create(const float *const *coeffs, int nStems, int T, int F, const float *unaffected)
+{
+    tables_init();
+    orc_vst *v = (orc_vst *)calloc(1, sizeof(orc_vst));
+    v->S = nStems; v->T = T; v->F = F;
+    v->coeff = (const float **)malloc(sizeof(float *) * nStems);
+    static const float kUw[4] = {0.25f, 0.0f, 0.25f, 0.25f};          /* :73, :281 */
+    for (int s = 0; s < nStems; s++) { v->coeff[s] = coeffs[s]; v->uw[s] = unaffected ? unaffected[s] : (s < 4 ? kUw[s] : 0.25f); }
+    vst_windows(v->awin, v->swin);
+    v->need = SRT_HOP;
+    for (int b = 0; b < 2; b++) {
+        for (int q = 0; q < 4; q++) v->spec[b][q] = (float *)calloc((size_t)T * SRT_BINS, sizeof(float));
+        for (int s = 0; s < nStems; s++) {
+            v->mask[b][s] = (float *)malloc(sizeof(float) * 2 * T * F);
+            for (size_t i = 0; i < (size_t)2 * T * F; i++) v->mask[b][s][i] = 1.0f;
+        }
+    }
+    v->mag = (float *)calloc((size_t)2 * T * F, sizeof(float));
+    v->overlap = (float *)calloc((size_t)2 * nStems * 1024, sizeof(float));
+    v->cap_ready = 4;
+    v->ready = (float *)malloc(sizeof(float) * v->cap_ready * 1024 * 2 * nStems);
+    return v;
+}
+
+void srt_oracle_vst_destroy(void *h)
+{
+    orc_vst *v = (orc_vst *)h;
+    for (int b = 0; b < 2; b++) {
+        for (int q = 0; q < 4; q++) free(v->spec[b][q]);
+        for (int s = 0; s < v->S; s++) free(v->mask[b][s]);
+    }
+    free(v->mag); free(v->overlap); free(v->ready); free((void *)v->coeff); free(v);
+}
+
+/* LLPAMSProcessNPR (Spleeter4Stems.c:257-379) */
+static void vst_hop(orc_vst *v)
+{
+    const int S = v->S, T = v->T, F = v->F, C = 2 * S;
+    float fl[SRT_FFT], fr[SRT_FFT];
+    float *td = (float *)malloc(sizeof(float) * C * SRT_FFT);
+    for (int i = 0; i < SRT_FFT; i++) {                                /* :261-267 */
+        const int k = (i + v->in_pos) & (SRT_FFT - 1);
+        fl[g_rev[i]] = v->in[0][k] * v->awin[i];
+        fr[g_rev[i]] = v->in[1][k] * v->awin[i];
+    }
+    float **sp = v->spec[v->ofp];
+    const size_t row = (size_t)SRT_BINS * v->cursor;
+    for (int s = 0; s < S; s++) {                                      /* :270-297 and task_type1 :64-89 */
+        const float *mk = v->mask[v->ofp][s];
+        for (int c = 0; c < 2; c++) {
+            float *h = td + (size_t)(2 * s + c) * SRT_FFT;
+            const float *re = sp[2 * c] + row, *im = sp[2 * c + 1] + row;
+            const float *m = mk + (size_t)c * T * F + (size_t)F * v->cursor;
+            h[0] = re[0] * m[0];
+            for (int i = 1; i < SRT_BINS; i++) {
+                const float w = i < F ? m[i] : v->uw[s];
+                h[g_rev[i]] = (re[i] + im[i]) * w;
+                h[g_rev[SRT_FFT - i]] = (re[i] - im[i]) * w;
+            }
+            dht4096(h);
+            for (int i = 0; i < SRT_FFT - 2048; i++) h[i] = h[i + 2048] * v->swin[i];   /* :303-309 */
+        }
+    }
+    dht4096(fl);
+    dht4096(fr);
+    if (v->n_ready == v->cap_ready) {
+        v->cap_ready *= 2;
+        v->ready = (float *)realloc(v->ready, sizeof(float) * v->cap_ready * 1024 * C);
+    }
+    float *ob = v->ready + (size_t)v->n_ready * 1024 * C;              /* :311-320 */
+    v->n_ready++;
+    for (int i = 0; i < 1024; i++)
+        for (int j = 0; j < C; j++) {
+            ob[(size_t)i * C + j] = v->overlap[(size_t)j * 1024 + i] + td[(size_t)j * SRT_FFT + i];
+            v->overlap[(size_t)j * 1024 + i] = td[(size_t)j * SRT_FFT + 1024 + i];
+        }
+    /* spectral analysis of the new frame (:322-349) */
+    const float *hb[2] = {fl, fr};
+    for (int c = 0; c < 2; c++) {
+        float *re = sp[2 * c] + row, *im = sp[2 * c + 1] + row;
+        float *mg = v->mag + (size_t)c * T * F + (size_t)F * v->cursor;
+        re[0] = hb[c][0] * 2.0f;
+        mg[0] = fabsf(re[0]) * (float)SRT_FFT;
+        for (int i = 1; i < SRT_BINS; i++) {
+            re[i] = hb[c][i] + hb[c][SRT_FFT - i];
+            im[i] = hb[c][i] - hb[c][SRT_FFT - i];
+            if (i < F) mg[i] = hypotf(re[i], im[i]) * (float)SRT_FFT;
+        }
+    }
+    if (++v->cursor >= T) {                                            /* :351-371 */
+        v->ofp = !v->ofp;
+        for (int s = 0; s < S; s++) srt_oracle_unet(v->coeff[s], F, T, 1, 1, v->mag, v->mask[!v->ofp][s], NULL);
+        v->cursor = 0;
+    }
+    v->need = SRT_HOP;
+    free(td);
+}
+
+/* Spleeter4StemsProcessSamples (Spleeter4Stems.c:512-582); components: 2S planar pointers */
+void srt_oracle_vst_process(void *h, const float *inL, const float *inR, int n, float *const *components)
+{
+    orc_vst *v = (orc_vst *)h;
+    const int C = 2 * v->S, want = n;
+    while (n > 0) {
+        const int c = v->need < n ? v->need : n;
+        for (int i = 0; i < c; i++) {
+            v->in[0][(v->in_pos + i) & (SRT_FFT - 1)] = inL[i];
+            v->in[1][(v->in_pos + i) & (SRT_FFT - 1)] = inR[i];
+        }
+        inL += c; inR += c; n -= c;
+        v->in_pos = (v->in_pos + c) & (SRT_FFT - 1);
+        v->need -= c;
+        if (v->need == 0) vst_hop(v);
+    }
+    int done = 0;
+    while (v->n_ready > 0 && done < want) {
+        const int c = (1024 - v->read_off) < (want - done) ? (1024 - v->read_off) : (want - done);
+        for (int i = 0; i < c; i++)
+            for (int j = 0; j < C; j++) components[j][done + i] = v->ready[(size_t)(v->read_off + i) * C + j];
+        done += c;
+        v->read_off += c;
+        if (v->read_off == 1024) {
+            v->read_off = 0;
+            v->n_ready--;
+            memmove(v->ready, v->ready + (size_t)1024 * C, sizeof(float) * (size_t)v->n_ready * 1024 * C);
+        }
+    }
+}

@@ -234,13 +234,12 @@ def test_unet_vst_flavour(srt, oracle, small_nets):
 def test_streamer_vs_reference_vst(srt, oracle, block):
     """Spleeter4Stems flavour against the reference's own streamer (oracle/_ref/libref_vst.so): same
     delayed output (2*T*1024 + 1024 samples), same untouched-output pattern, 1e-4 RMS per component."""
-    if not os.path.exists(os.path.join(oracle.REF_DIR, "libref_vst.so")):
-        pytest.skip("reference VST build absent")
     T, F = 64, 512
     nets = [(oracle.synthetic_weights(40 + k), 1) for k in range(4)]
     n_total = (2 * T + 6) * 1024
     L, R = oracle.synth_pcm(7, n=n_total)
-    ref = oracle.RefVst(nets, T, F)
+    have_ref = os.path.exists(os.path.join(oracle.REF_DIR, "libref_vst.so"))
+    ref = oracle.RefVst(nets, T, F) if have_ref else oracle.PortVst(nets, T, F)   # the port is pinned to the reference on CPU
     got = srt.Streamer([c for c, _ in nets], T, F)
     outs_r, outs_g = [], []
     for o in range(0, n_total, block):
@@ -258,3 +257,18 @@ def test_streamer_vs_reference_vst(srt, oracle, block):
     for j in range(8):
         assert rms(a[j][ok] - b[j][ok]) < 1e-4, f"component {j}: {rms(a[j][ok] - b[j][ok])}"
     assert launches >= n_total // 1024
+
+
+def test_five_stem_batch(srt, oracle, small_nets):
+    """BASELINE.json configs[3] shape in small: 5 nets per stream (n_stems is a context parameter)."""
+    T, F = 64, 256
+    nets = [(small_nets[0][0], 1), (small_nets[1][0], 0)] + [(oracle.synthetic_weights(60 + k), 1) for k in range(3)]
+    streams = [tuple(x[:n] for x in oracle.synth_pcm(20 + i, n=40000)) for i, n in enumerate((40000, 25000))]
+    sep = srt.Separator(nets, T, F, max_images=2, max_batch_images=2)
+    got = sep.separate(streams)
+    sep.close()
+    for (L, R), g in zip(streams, got):
+        ref = oracle.separate(nets, L, R, T, F)
+        assert g.shape == (5, 2, L.size)
+        for s in range(5):
+            assert rms(g[s] - ref[s]) < 1e-4

@@ -113,3 +113,25 @@ def test_golden_stft(oracle):
         assert np.abs(planes[q][:, :2049] - g[name]).max() < 1e-8
     oL, oR = oracle.istft(*planes)
     assert np.abs(oL - g["outL"]).max() < 1e-6 and np.abs(oR - g["outR"]).max() < 1e-6
+
+
+def test_vst_streamer_port_vs_reference(oracle):
+    """oracle port of the real-time streamer vs the reference's own Spleeter4Stems.c build."""
+    if not os.path.exists(os.path.join(oracle.REF_DIR, "libref_vst.so")):
+        pytest.skip("reference VST build absent")
+    T, F = 64, 512
+    nets = [(oracle.synthetic_weights(40 + k), 1) for k in range(4)]
+    n_total = (2 * T + 4) * 1024
+    L, R = oracle.synth_pcm(7, n=n_total)
+    ref, prt = oracle.RefVst(nets, T, F), oracle.PortVst(nets, T, F)
+    a, b = [], []
+    for o in range(0, n_total, 700):                      # ragged host blocks
+        a.append(ref.process(L[o:o + 700], R[o:o + 700]))
+        b.append(prt.process(L[o:o + 700], R[o:o + 700]))
+    ref.close()
+    prt.close()
+    a, b = np.concatenate(a, axis=1), np.concatenate(b, axis=1)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a[0])
+    assert np.sqrt(np.mean(a[:, ok] ** 2)) > 1e-3
+    assert np.abs(a[:, ok] - b[:, ok]).max() < 5e-6
