@@ -27,7 +27,6 @@
 namespace srt {
 
 constexpr int kRpThreads = 352;   // 3 control warps + 8 epilogue warps
-constexpr int kRowPitch = kPatchW * 128;
 constexpr int kRpMaxChunks = 8, kRpMaxKB = 80, kRpMaxWStages = 12;
 
 struct RpHeader {
@@ -39,8 +38,8 @@ struct RpHeader {
     KBlock kb[kRpMaxKB];
 };
 
-template <int N, int R, int WS>
-constexpr size_t rp_smem_bytes() { return sizeof(RpHeader) + 1024 + (size_t)2 * (R + 2) * kRowPitch + (size_t)WS * N * 128; }
+template <int N, int R, int WS, int KB>
+constexpr size_t rp_smem_bytes() { return sizeof(RpHeader) + 1024 + (size_t)2 * (R + 2) * kPatchW * KB * 4 + (size_t)WS * N * KB * 4; }
 
 struct RpTile {
     int s, n, x0, y0;
@@ -60,15 +59,18 @@ __device__ __forceinline__ RpTile rp_tile(const RowConvParams& p, int t, int R)
     return o;
 }
 
-template <int N, int R, int WS>
+template <int N, int R, int WS, int KB>
 __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_constant__ RowConvParams p)
 {
     extern __shared__ uint8_t smem_raw[];
     RpHeader* hdr = reinterpret_cast<RpHeader*>(smem_raw);
     const uint32_t patch_base = (ptx::smem_u32(smem_raw) + (uint32_t)sizeof(RpHeader) + 1023u) & ~1023u;
     uint8_t* patch = smem_raw + (patch_base - ptx::smem_u32(smem_raw));
+    constexpr int kRowBytes = KB * 4;                 // 128 (SWIZZLE_128B) or 32 (SWIZZLE_32B)
+    constexpr int kRowPitch = kPatchW * kRowBytes;    // multiple of the 8-row swizzle atom
     constexpr int kPatchBytes = (R + 2) * kRowPitch;
-    constexpr int kWBytes = N * 128;
+    constexpr int kWBytes = N * kRowBytes;
+    constexpr uint32_t kDescHi = KB == 32 ? ptx::kDescHiSw128 : ptx::kDescHiSw32;
     constexpr int kAccCols = R * N;
     constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128 : 2 * kAccCols <= 256 ? 256 : 512;
     static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                     if (p.dbg & 4) { ptx::mbar_arrive(&hdr->patch_full[ps]); }
                     else {
                     ptx::mbar_arrive_expect_tx(&hdr->patch_full[ps], kPatchBytes);
-                    ptx::tma_load_4d(patch + (size_t)ps * kPatchBytes, &p.tmap[ch.src], &hdr->patch_full[ps], ch.c_off, tl.x0 - 1, tl.y0 - 1, tl.n);
+                    ptx::tma_load_4d(patch + (size_t)ps * kPatchBytes, &p.tmap[ch.src], &hdr->patch_full[ps], ch.c_off, tl.x0 - 1, tl.y0 - 1, p.src_img0 + tl.n);
                     }
                     if (++ps == 2) { ps = 0; pph ^= 1; }
                 }
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                     if (p.dbg & 8) { ptx::mbar_arrive(&hdr->w_full[ws]); }
                     else {
                     ptx::mbar_arrive_expect_tx(&hdr->w_full[ws], kWBytes);
-                    ptx::bulk_load_1d(wring + (size_t)ws * kWBytes, wsrc + (size_t)k * N * kKB, kWBytes, &hdr->w_full[ws]);
+                    ptx::bulk_load_1d(wring + (size_t)ws * kWBytes, wsrc + (size_t)k * N * KB, kWBytes, &hdr->w_full[ws]);
                     }
                     if (++ws == WS) { ws = 0; wph ^= 1; }
                 }
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                     for (int k = ch.kb0; k < ch.kb0 + ch.nkb; k++) {
                         const KBlock kb = hdr->kb[k];
                         // descriptor low word of the tap's window for row r = 0, K step 0 (16-byte units)
-                        const uint32_t a_lo = p_lo + (uint32_t)((kb.dy + 1) * (kRowPitch >> 4) + (kb.dx + 1) * (128 >> 4));
+                        const uint32_t a_lo = p_lo + (uint32_t)((kb.dy + 1) * (kRowPitch >> 4) + (kb.dx + 1) * (kRowBytes >> 4));
                         const uint32_t b_lo = ptx::umma_desc_lo(wring_base + (uint32_t)ws * kWBytes);
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
@@ -165,11 +167,11 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                         // K step outer, row inner: consecutive MMAs hit different accumulators (dependent MMAs on one
                         // accumulator cost ~100 cycles each, independent ones ~60: tools/mma_probe.cu)
 #pragma unroll
-                        for (int kk = 0; kk < kKB / 8; kk++) {
+                        for (int kk = 0; kk < KB / 8; kk++) {
 #pragma unroll
                             for (int r = 0; r < R; r++)
                                 ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2),
-                                                    idesc, (kk != 0) ? 1u : (first ? 0u : 1u));
+                                                    idesc, (kk != 0) ? 1u : (first ? 0u : 1u), kDescHi);
                         }
                         first = false;
                         ptx::mma_commit(&hdr->w_empty[ws]);
@@ -202,11 +204,15 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 // the two epilogue warps of a lane quarter split the columns in two contiguous halves, so each
                 // thread writes whole 128-byte lines (for the fused decoder layers: both column parities of one
                 // output row; for the encoder: half of the pixel's channels)
-                for (int c0 = half * (N / 2); c0 < (half + 1) * (N / 2); c0 += 16) {
+                constexpr int kHalfCols = N >= 32 ? N / 2 : N;
+                for (int c0 = half * kHalfCols; c0 < (half + 1) * kHalfCols && c0 < N; c0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(acc + (uint32_t)(r * N + c0), v);
                     if (valid && !(p.dbg & 1)) {
-                        if (p.ep.mode == 2) epilogue16(p.ep, tl.s, tl.n, Y, X, c0 / p.ep.cout, c0 % p.ep.cout, v);
+                        if (p.stems_per_tile > 1 || p.stem0 > 0) {   // down1: the column selects the stem (its own output image)
+                            const int se = p.stem0 + c0 / p.ep.cout;
+                            epilogue16(p.ep, se, se * p.ep.B + tl.n, Y, X, 0, c0 % p.ep.cout, v);
+                        } else if (p.ep.mode == 2) epilogue16(p.ep, tl.s, tl.n, Y, X, c0 / p.ep.cout, c0 % p.ep.cout, v);
                         else epilogue16(p.ep, tl.s, tl.n, Y, X, 0, c0, v);
                     }
                 }
@@ -225,28 +231,32 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
     }
 }
 
-template <int N, int R, int WS>
+template <int N, int R, int WS, int KB>
 static void launch_rp(const RowConvParams& p, cudaStream_t st)
 {
-    constexpr size_t smem = rp_smem_bytes<N, R, WS>();
+    constexpr size_t smem = rp_smem_bytes<N, R, WS, KB>();
     static_assert(smem <= 232448, "must fit the 227 KB per-CTA limit");
     static int sms = 0;
     if (!sms) {
-        cudaFuncSetAttribute(conv_rp_kernel<N, R, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_rp_kernel<N, R, WS, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int n_tiles = p.tiles_x * p.tiles_y * p.ep.Bv * p.ep.S;
     dim3 grid(n_tiles < sms ? n_tiles : sms, 1, 1);
-    conv_rp_kernel<N, R, WS><<<grid, kRpThreads, smem, st>>>(p);
+    conv_rp_kernel<N, R, WS, KB><<<grid, kRpThreads, smem, st>>>(p);
 }
 
 void launch_conv_rp(const RowConvParams& p, cudaStream_t st)
 {
-    if (p.N == 32 && p.R == 3) launch_rp<32, 3, 12>(p, st);
-    else if (p.N == 64 && p.R == 3) launch_rp<64, 3, 6>(p, st);
-    else if (p.N == 128 && p.R == 2) launch_rp<128, 2, 5>(p, st);
+    if (p.kb_width == 8) {   // down1: 8-channel k-blocks, up to 4 stems fused into N
+        if (p.N == 64 && p.R == 4) launch_rp<64, 4, 9, 8>(p, st);
+        else if (p.N == 32 && p.R == 4) launch_rp<32, 4, 9, 8>(p, st);
+        else if (p.N == 16 && p.R == 4) launch_rp<16, 4, 9, 8>(p, st);
+    } else if (p.N == 32 && p.R == 3) launch_rp<32, 3, 12, 32>(p, st);
+    else if (p.N == 64 && p.R == 3) launch_rp<64, 3, 6, 32>(p, st);
+    else if (p.N == 128 && p.R == 2) launch_rp<128, 2, 5, 32>(p, st);
 }
 
 }  // namespace srt

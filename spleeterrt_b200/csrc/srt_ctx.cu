@@ -62,17 +62,18 @@ static PFN_encodeTiled get_encode()
 }
 
 // activation tensor [n][H][W][C] fp32 -> 4-D map, box {32, tw, th, nb}, 128B swizzle, zero OOB fill
-static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int N, int tw, int th, int nb)
+static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int N, int tw, int th, int nb, int kbw = kKB)
 {
-    // box = {32 channels, tw pixels, th rows, nb images}; may overhang the tensor (zero fill)
+    // box = {kbw channels (32 -> SWIZZLE_128B, 8 -> SWIZZLE_32B), tw pixels, th rows, nb images}; may overhang the tensor (zero fill)
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kKB, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+    cuuint32_t box[4] = {(cuuint32_t)kbw, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     kbw == kKB ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d N=%d box=%d,%d,%d", (int)r, C, W, H, N, tw, th, nb);
     return 0;
 }
@@ -108,12 +109,14 @@ struct srt_ctx {
     std::vector<ConvParams> conv;   // 10 tensor-core layers
     RowConvParams rp[10];           // row-patch form of the small-N layers (down2, down3, up4, up5)
     bool use_rp[10]{};
+    RowConvParams d1[4];            // down1 on the tensor cores: groups of up to 4 stems fused into N
+    int n_d1 = 0;
     // activations
     float* E[7]{};    // E[1..6] raw skips (NHWC)
     float* A[6]{};    // A[1..5] activated, space-to-depth
     float* U[7]{};    // U[1..5] decoder outputs (NHWC), U[6] = up6 output [n][T][F]
     // batch buffers
-    float* d_mag = nullptr;       // [NB][T][F][2]
+    float* d_mag = nullptr;       // [NB][T/2][F/2][(py,px)][c] space-to-depth, TF32-rounded
     float4* d_spec = nullptr;     // [NB][T][2049]
     float* d_mask = nullptr;      // [S][NB][T][F][2]
     float2* d_frames = nullptr;   // [max(S,1)][B][T][4096]
@@ -127,7 +130,6 @@ struct srt_ctx {
     // staging for the host-pointer API
     float *d_pcm = nullptr, *d_out = nullptr;
     size_t pcm_cap = 0, out_cap = 0;
-    float *d_xin = nullptr;       // unet_host staging
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer API (H2D / D2H overlap compute)
     cudaEvent_t ev_in[8]{}, ev_c[8]{};
     // bookkeeping
@@ -273,7 +275,6 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     if (S == 0) return 0;
     if ((r = dalloc(c, &c->d_mag, (size_t)c->NB * T * F * 2))) return r;
     if ((r = dalloc(c, &c->d_mask, (size_t)S * c->NB * T * F * 2))) return r;
-    if ((r = dalloc(c, &c->d_xin, (size_t)c->B * T * F * 2))) return r;
     // ---- activations
     for (int i = 1; i <= 6; i++)
         if ((r = dalloc(c, &c->E[i], act_floats(c, i, kEnc[i])))) return r;
@@ -435,6 +436,48 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         if (!ok) { fprintf(stderr, "[spleeterrt_b200] row-patch tensor map rejected for layer %zu (%s); using the generic kernel\n", li, g_err.c_str()); continue; }
         c->use_rp[li] = true;
     }
+    // ---- down1 on the tensor cores: the magnitude image is shared by all stems, so up to 4 stems ride one MMA
+    // (SRT_DOWN1_TC=0 keeps the SIMT kernel)
+    const char* d1e = getenv("SRT_DOWN1_TC");
+    if (c->cfg.conv_impl != 1 && !(d1e && atoi(d1e) == 0)) {
+        const Down1Plan dp = build_down1_plan(NetGeom{T, F});
+        KBlock* dkb;
+        std::vector<RowChunk> chunk = {RowChunk{0, 0, 0, (int32_t)dp.kb.size()}};
+        RowChunk* dch;
+        if ((r = upload(c, &dkb, dp.kb)) || (r = upload(c, &dch, chunk))) return r;
+        std::vector<float> one(S * 16, 1.0f), zero(S * 16, 0.0f);
+        for (int s0 = 0; s0 < S;) {
+            const int g = (S - s0 >= 4) ? 4 : (S - s0 >= 2) ? 2 : 1;
+            RowConvParams& q = c->d1[c->n_d1];
+            std::memset(&q, 0, sizeof q);
+            std::vector<float> wpk((size_t)dp.kb.size() * 16 * g * kKB1);
+            pack_down1(dp, coeffs + s0, g, wpk.data());
+            float* dw;
+            if ((r = upload(c, &dw, wpk))) return r;
+            q.chunks = dch; q.n_chunks = 1; q.kb = dkb; q.nkb = (int)dp.kb.size();
+            q.w = dw; q.w_stem_stride = 0;
+            q.N = 16 * g; q.R = 4; q.kb_width = kKB1;
+            q.tiles_x = (dp.Ws + kTileM - 1) / kTileM;
+            q.tiles_y = (dp.Hs + q.R - 1) / q.R;
+            q.stems_per_tile = g; q.stem0 = s0;
+            q.dbg = getenv("SRT_RP_DBG") ? atoi(getenv("SRT_RP_DBG")) : 0;
+            ConvParams& e = q.ep;
+            e.Hs = dp.Hs; e.Ws = dp.Ws; e.B = c->B; e.S = 1; e.cout = 16;
+            e.bias = c->d_b1; e.bn_scale = c->d_s1; e.bn_offset = c->d_o1;
+            for (int s = 0; s < S; s++) e.act[s] = c->act_enc[s];
+            e.mode = 0; e.out_raw = c->E[1]; e.out_act = c->A[1];
+            e.round_raw = 0;            // the skip feeds the fp32 SIMT up6 kernel
+            e.round_act = 1;
+            if (make_tmap(&q.tmap[0], c->d_mag, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1)) {
+                fprintf(stderr, "[spleeterrt_b200] down1 tensor map rejected (%s); using the SIMT kernel\n", g_err.c_str());
+                c->n_d1 = 0;
+                break;
+            }
+            q.tmap[1] = q.tmap[0];
+            c->n_d1++;
+            s0 += g;
+        }
+    }
     return 0;
 }
 
@@ -480,23 +523,34 @@ extern "C" int srt_create(const srt_config* cfg, const float* const* coeffs, con
 // U-Net on Bv images whose magnitudes sit at d_mag (layout [Bv][T][F][2]); masks go to
 // mask_base[s][mask_img0 + b] with `mask_stride` images between stems.
 // ------------------------------------------------------------------------------------------
-static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, int mask_stride, int mask_img0)
+static int run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask_stride, int mask_img0)
 {
     const int S = c->S;
     c->last_Bv = Bv;
     {
         Timed t(c, 10);
-        Down1Params p{};
-        p.mag = d_mag; p.w = c->d_w1; p.bias = c->d_b1; p.bn_scale = c->d_s1; p.bn_offset = c->d_o1;
-        p.out_raw = c->E[1]; p.out_act = c->A[1];
-        p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
-        for (int s = 0; s < S; s++) {
-            p.stem = s;
-            p.act[0] = c->act_enc[s];
-            std::memcpy(p.wk, &c->h_w1[(size_t)s * 800], 800 * sizeof(float));
-            std::memcpy(p.bk, &c->h_b1[(size_t)s * 48], 48 * sizeof(float));
-            launch_down1(p, c->stream);
-            c->launches++;
+        if (c->n_d1 > 0) {
+            for (int g = 0; g < c->n_d1; g++) {
+                RowConvParams& q = c->d1[g];
+                q.ep.Bv = Bv;
+                q.src_img0 = mag_img0;
+                launch_conv_rp(q, c->stream);
+                c->launches++;
+            }
+        } else {
+            Down1Params p{};
+            p.mag = c->d_mag + (size_t)mag_img0 * c->T * c->F * 2;
+            p.w = c->d_w1; p.bias = c->d_b1; p.bn_scale = c->d_s1; p.bn_offset = c->d_o1;
+            p.out_raw = c->E[1]; p.out_act = c->A[1];
+            p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
+            for (int s = 0; s < S; s++) {
+                p.stem = s;
+                p.act[0] = c->act_enc[s];
+                std::memcpy(p.wk, &c->h_w1[(size_t)s * 800], 800 * sizeof(float));
+                std::memcpy(p.bk, &c->h_b1[(size_t)s * 48], 48 * sizeof(float));
+                launch_down1(p, c->stream);
+                c->launches++;
+            }
         }
     }
     for (size_t li = 0; li < c->conv.size(); li++) {
@@ -545,10 +599,11 @@ static int run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, in
 // without a host sync in between) and are cleared by srt_set_timing().
 namespace srt {
 namespace internal {
-int ctx_run_unet(srt_ctx* c, const float* d_mag, int Bv, float* mask_base, int mask_stride, int mask_img0)
+int ctx_run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask_stride, int mask_img0)
 {
-    return run_unet(c, d_mag, Bv, mask_base, mask_stride, mask_img0);
+    return run_unet(c, mag_img0, Bv, mask_base, mask_stride, mask_img0);
 }
+float* ctx_mag(srt_ctx* c) { return c->d_mag; }
 cudaStream_t ctx_stream(srt_ctx* c) { return c->stream; }
 const float2* ctx_twiddle(srt_ctx* c) { return c->d_twiddle; }
 void ctx_count_launch(srt_ctx* c, int n) { c->launches += n; }
@@ -569,7 +624,9 @@ extern "C" int srt_unet_device(srt_ctx* c, const float* d_mag, int n_img, float*
     if (n_img < 1 || n_img > c->B) return fail(SRT_ERR_CAPACITY, "n_img %d exceeds max_images %d", n_img, c->B);
     CK(cudaSetDevice(c->cfg.device));
     reset_spans(c);
-    return run_unet(c, d_mag, n_img, d_mask, n_img, 0);
+    launch_mag_to_s2d(d_mag, c->d_mag, c->T, c->F, n_img, c->stream);   // API layout -> space-to-depth, TF32-rounded
+    c->launches++;
+    return run_unet(c, 0, n_img, d_mask, n_img, 0);
 }
 
 extern "C" int srt_unet_host(srt_ctx* c, const float* x, int n_img, float* y)
@@ -579,14 +636,16 @@ extern "C" int srt_unet_host(srt_ctx* c, const float* x, int n_img, float* y)
     CK(cudaSetDevice(c->cfg.device));
     reset_spans(c);
     const size_t P = (size_t)c->T * c->F;
-    std::vector<float> xi((size_t)n_img * P * 2);
+    std::vector<float> xi((size_t)n_img * P * 2);   // space-to-depth, TF32-rounded (what the device path stores)
     for (int b = 0; b < n_img; b++)
-        for (size_t i = 0; i < P; i++) {
-            xi[((size_t)b * P + i) * 2 + 0] = x[((size_t)b * 2 + 0) * P + i];
-            xi[((size_t)b * P + i) * 2 + 1] = x[((size_t)b * 2 + 1) * P + i];
-        }
-    CK(cudaMemcpyAsync(c->d_xin, xi.data(), xi.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    int r = run_unet(c, c->d_xin, n_img, c->d_mask, c->NB, 0);
+        for (int t = 0; t < c->T; t++)
+            for (int f = 0; f < c->F; f++) {
+                const size_t o = ((size_t)b * P + mag_s2d_index(c->T, c->F, t, f)) * 2, i = (size_t)t * c->F + f;
+                xi[o + 0] = round_tf32(x[((size_t)b * 2 + 0) * P + i]);
+                xi[o + 1] = round_tf32(x[((size_t)b * 2 + 1) * P + i]);
+            }
+    CK(cudaMemcpyAsync(c->d_mag, xi.data(), xi.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    int r = run_unet(c, 0, n_img, c->d_mask, c->NB, 0);
     if (r) return r;
     std::vector<float> mi((size_t)n_img * P * 2);
     for (int s = 0; s < c->S; s++) {
@@ -691,7 +750,7 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     // ---- U-Net, max_images tiles per pass
     for (int i0 = 0; i0 < m.total; i0 += c->B) {
         const int Bv = std::min(c->B, m.total - i0);
-        if ((r = run_unet(c, c->d_mag + (size_t)i0 * T * c->F * 2, Bv, c->d_mask, c->NB, i0))) return r;
+        if ((r = run_unet(c, i0, Bv, c->d_mask, c->NB, i0))) return r;
     }
     // ---- mask * spectrum -> inverse FFT -> OLA, in groups of whole streams that fit the scratch
     int s0 = 0;

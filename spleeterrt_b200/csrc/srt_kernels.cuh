@@ -54,6 +54,10 @@ struct alignas(64) RowConvParams {
     int tiles_x, tiles_y;
     int bo_mode;                  // (diagnostic) descriptor base-offset convention, 0 = product setting
     int dbg;                      // (diagnostic, SRT_RP_DBG) 1: skip epilogue math+stores, 2: skip MMAs, 4: skip patch loads, 8: skip weight loads
+    int kb_width;                 // channels per k-block: 32 (SWIZZLE_128B rows) or 8 (down1: SWIZZLE_32B rows)
+    int src_img0;                 // image coordinate offset of the source tensor (down1 reads the shared magnitude buffer)
+    int stems_per_tile;           // 1, or (down1) stems fused into N: column c -> stem stem0 + c / cout
+    int stem0;
     ConvParams ep;                // geometry + epilogue (tmap / k-block fields unused)
 };
 void launch_conv_rp(const RowConvParams& p, cudaStream_t st);
@@ -62,7 +66,7 @@ void launch_conv_rp(const RowConvParams& p, cudaStream_t st);
 // SIMT edge layers
 // ---------------------------------------------------------------------------------------
 struct Down1Params {              // 5x5 s2 conv 2->16 on the magnitude image, spleeter.c:181-190
-    const float* mag;             // [B][T][F][2]
+    const float* mag;             // space-to-depth magnitudes of the launch's first image: [Bv][T/2][F/2][(py,px)][c], TF32-rounded
     const float* w;               // [S][16][2][5][5] (reference order)
     const float* bias;            // [S][16]
     const float* bn_scale;        // [S][16]
@@ -119,7 +123,7 @@ struct StftParams {
     const float* window;          // hann(i+1/2)/4096
     const float2* twiddle;        // exp(-2 pi i m / 4096)
     float4* spec;                 // [n_img][T][2049] (reL, imL, reR, imR) in the reference's convention
-    float* mag;                   // [n_img][T][F][2]
+    float* mag;                   // [n_img][T/2][F/2][(py,px)][c] space-to-depth, TF32-rounded (what down1 reads)
     int T, F, n_img;
     int front_pad;                // 4096 zeros in front (main.c:767) or 0 (raw stft())
 };
@@ -161,6 +165,8 @@ void launch_up7(const Up7Params& p, cudaStream_t st);
 void launch_stft(const StftParams& p, cudaStream_t st);
 void launch_istft(const IstftParams& p, cudaStream_t st);
 void launch_ola(const OlaParams& p, cudaStream_t st);
+// [n][T][F][2] (API layout) -> space-to-depth, TF32-rounded
+void launch_mag_to_s2d(const float* in, float* out, int T, int F, int n_img, cudaStream_t st);
 size_t conv_tc_smem_bytes(int n_tile, int* stages_out);
 
 __device__ __forceinline__ float apply_act(int act, float x)

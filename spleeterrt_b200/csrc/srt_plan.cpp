@@ -305,4 +305,48 @@ void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// down1 (tensor-core form)
+// ------------------------------------------------------------------------------------------
+Down1Plan build_down1_plan(NetGeom g)
+{
+    Down1Plan L{};
+    L.Hs = g.T / 2;
+    L.Ws = g.F / 2;
+    for (int dy = -1; dy <= 1; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+            L.kb.push_back(KBlock{0, (int8_t)dy, (int8_t)dx, 0, 0});
+            for (int j = 0; j < kKB1; j++) {
+                const int py = j >> 2, px = (j >> 1) & 1, c = j & 1;
+                KElemP e{-1, {-1, -1, -1, -1}, {-1, -1, -1, -1}};
+                for (int kh = 0; kh < 5; kh++)
+                    for (int kw = 0; kw < 5; kw++) {
+                        int d1, p1, d2, p2;
+                        enc_tap(kh, d1, p1);
+                        enc_tap(kw, d2, p2);
+                        if (d1 == dy && p1 == py && d2 == dx && p2 == px) { e.cin = c; e.kh[0] = (int8_t)kh; e.kw[0] = (int8_t)kw; }
+                    }
+                L.kelem.push_back(e);
+            }
+        }
+    return L;
+}
+
+void pack_down1(const Down1Plan& L, const float* const* coeffs, int nstems, float* out)
+{
+    const CoeffLayout cl = coeff_layout();
+    const int N = 16 * nstems;
+    for (size_t kb = 0; kb < L.kb.size(); kb++)
+        for (int n = 0; n < N; n++) {
+            const float* w = coeffs[n / 16] + cl.down_w[0];
+            const int o = n % 16;
+            for (int j = 0; j < kKB1; j++) {
+                const KElemP& e = L.kelem[kb * kKB1 + j];
+                float v = 0.0f;
+                if (e.cin >= 0) v = round_tf32(w[(((size_t)o * 2 + e.cin) * 5 + e.kh[0]) * 5 + e.kw[0]]);
+                out[kb * (size_t)N * kKB1 + swz32_index(n, j)] = v;
+            }
+        }
+}
+
 }  // namespace srt

@@ -129,6 +129,24 @@ struct RowPlan {
 };
 // rows per CTA for a given N (fixed by the shared-memory / TMEM budget, see srt_conv_rp.cu)
 inline int row_plan_R(int N) { return N <= 64 ? 3 : 2; }
+// ---- down1 on the tensor cores -------------------------------------------------------------
+// The magnitude image is stored space-to-depth: [img][T/2][F/2][(py,px)][c] = 8 floats (32 B) per S2D
+// pixel.  down1 (2 -> 16 ch, 5x5 stride 2) is then 9 stride-1 taps with K = 8 each.  All stems read the
+// same magnitude, so up to 4 stems are fused into one MMA (N = 16 * stems): the k-block is 8 channels wide
+// (one 32-byte SWIZZLE_32B row, a single K=8 MMA per tap).
+constexpr int kKB1 = 8;
+struct Down1Plan {
+    int Hs, Ws;                         // output (= S2D input) extent: T/2 x F/2
+    std::vector<KBlock> kb;             // 9 taps
+    std::vector<KElemP> kelem;          // 8 per tap (kh/kw in slot 0)
+};
+Down1Plan build_down1_plan(NetGeom g);
+// weights of `nstems` consecutive stems -> [tap][N = 16*nstems][8] fp32, SWIZZLE_32B pre-applied
+void pack_down1(const Down1Plan& L, const float* const* coeffs, int nstems, float* out);
+SRT_HD inline int swz32_index(int row, int j) { return row * 8 + ((((j >> 2) ^ ((row >> 2) & 1)) << 2) | (j & 3)); }
+// float2 index of magnitude (t, f) inside one space-to-depth image
+SRT_HD inline size_t mag_s2d_index(int T, int F, int t, int f) { return (((size_t)(t >> 1) * (F >> 1) + (f >> 1)) << 2) + ((t & 1) << 1) + (f & 1); }
+
 bool row_plan_supported(int layer_index);                 // down2, down3, up4, up5
 RowPlan build_row_plan(NetGeom g, int layer_index);
 void pack_row_layer(const RowPlan& L, const float* coeff, float* out);

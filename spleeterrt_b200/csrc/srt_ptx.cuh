@@ -125,7 +125,9 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uin
 // N, so advancing a descriptor must cost one integer add, not a rebuild.
 constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO=1024 B, version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3ffffu) >> 4) | (1u << 16); }
-__device__ __forceinline__ void mma_tf32_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate)
+constexpr uint32_t kDescHiSw32 = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);    // 32-byte rows: SBO=256 B, SWIZZLE_32B
+__device__ __forceinline__ void mma_tf32_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t desc_hi = kDescHiSw128)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
@@ -134,7 +136,7 @@ __device__ __forceinline__ void mma_tf32_ss_lo(uint32_t tmem_d, uint32_t a_lo, u
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}\n"
         :
-        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
         : "memory");
 }
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.

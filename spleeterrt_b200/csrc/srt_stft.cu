@@ -11,6 +11,7 @@
 // im = -Im FFT(x*hann)/4096 (conjugate), magnitude = hypot(re, im) * 4096.
 #include "srt_fft.cuh"
 #include "srt_kernels.cuh"
+#include "srt_ptx.cuh"
 
 namespace srt {
 
@@ -26,12 +27,12 @@ __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
     const int f = d.f0 + t;
     const int j = threadIdx.x;
     float4* srow = p.spec + ((size_t)img * p.T + t) * kBins;
-    float2* mrow = reinterpret_cast<float2*>(p.mag) + ((size_t)img * p.T + t) * p.F;
+    float2* mimg = reinterpret_cast<float2*>(p.mag) + (size_t)img * p.T * p.F;   // space-to-depth image
     const int nfr = p.n_frames[d.stream];
     if (f >= nfr) {
         // zero-padded tail of the last tile (main.c:507-514)
         for (int k = j; k < kBins; k += kFftThreads) srow[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = j; k < p.F; k += kFftThreads) mrow[k] = make_float2(0.f, 0.f);
+        for (int k = j; k < p.F; k += kFftThreads) mimg[mag_s2d_index(p.T, p.F, t, k)] = make_float2(0.f, 0.f);
         return;
     }
     const int n = p.n_samples[d.stream];
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
         o.w = 0.5f * (ar - br);          // -Im XR = -(-(ar - br)/2)
         if (k == 0 || k == kFFT / 2) { o.y = 0.f; o.w = 0.f; }
         srow[k] = o;
-        if (k < p.F) mrow[k] = make_float2(hypotf(o.x, o.y) * (float)kFFT, hypotf(o.z, o.w) * (float)kFFT);
+        if (k < p.F)
+            mimg[mag_s2d_index(p.T, p.F, t, k)] = make_float2(ptx::rna_tf32(hypotf(o.x, o.y) * (float)kFFT), ptx::rna_tf32(hypotf(o.z, o.w) * (float)kFFT));
     }
 }
 

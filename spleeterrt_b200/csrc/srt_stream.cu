@@ -24,6 +24,7 @@
 #include "srt_fft.cuh"
 #include "srt_internal.h"
 #include "srt_kernels.cuh"
+#include "srt_ptx.cuh"
 
 using namespace srt;
 
@@ -36,7 +37,7 @@ struct HopParams {
     const float* swin;        // synthesis window, pre-shifted: 2048 entries
     const float2* twiddle;
     float4* spec_new;         // [2049] row being recorded
-    float2* mag_new;          // [F] row being recorded
+    float2* mag_new;          // space-to-depth magnitude image being recorded (row = cursor)
     const float4* spec_old;   // [2049] row recorded two tiles ago
     const float* mask_old;    // masks of that tile: [S][T][F][2]
     int cursor, T, F, S;
@@ -80,7 +81,9 @@ __global__ void __launch_bounds__(kFftThreads) stream_hop_kernel(const HopParams
             o.w = 0.5f * (ar - br);
             if (k == 0 || k == kFFT / 2) { o.y = 0.f; o.w = 0.f; }
             p.spec_new[k] = o;
-            if (k < p.F) p.mag_new[k] = make_float2(hypotf(o.x, o.y) * (float)kFFT, hypotf(o.z, o.w) * (float)kFFT);
+            if (k < p.F)
+                p.mag_new[mag_s2d_index(p.T, p.F, p.cursor, k)] =
+                    make_float2(ptx::rna_tf32(hypotf(o.x, o.y) * (float)kFFT), ptx::rna_tf32(hypotf(o.z, o.w) * (float)kFFT));
         }
         return;
     }
@@ -133,7 +136,7 @@ struct srt_stream {
     cudaEvent_t ev_tile[2]{}, ev_nn[2]{};
     float *d_ring = nullptr, *d_awin = nullptr, *d_swin = nullptr, *d_mask = nullptr, *d_overlap = nullptr, *d_out = nullptr;
     float4* d_spec = nullptr;
-    float2* d_mag = nullptr;
+    float2* d_mag = nullptr;   // = the context's magnitude buffer (2 images), not owned
     float *h_in = nullptr, *h_out = nullptr;   // pinned staging
     float uw[8]{};
     // host state (mirrors mInputPos / mInputSamplesNeeded / nnMaskCursor / output buffers of the reference)
@@ -156,7 +159,7 @@ extern "C" void srt_stream_destroy(srt_stream* st)
     if (st->hop_stream) cudaStreamSynchronize(st->hop_stream);
     if (st->ctx) srt_synchronize(st->ctx);
     for (void* p : {(void*)st->d_ring, (void*)st->d_awin, (void*)st->d_swin, (void*)st->d_mask, (void*)st->d_overlap, (void*)st->d_out,
-                    (void*)st->d_spec, (void*)st->d_mag})
+                    (void*)st->d_spec})
         if (p) cudaFree(p);
     if (st->h_in) cudaFreeHost(st->h_in);
     if (st->h_out) cudaFreeHost(st->h_out);
@@ -179,7 +182,7 @@ extern "C" int srt_stream_create(const srt_config* cfg, const float* const* coef
     srt_config c2 = *cfg;
     c2.flavour = 1;            // VST flavour: exact sigmoid, unclamped ELU (VST/Source/spleeter.c:56-77)
     c2.max_images = 1;
-    c2.max_batch_images = 1;
+    c2.max_batch_images = 2;   // the context's magnitude buffer doubles as the tile double buffer
     c2.cuda_stream = nullptr;  // the nets get their own stream
     int modes[SRT_MAX_STEMS];
     for (int s = 0; s < cfg->n_stems; s++) modes[s] = 1;   // all ELU (Spleeter4Stems.c:444-447)
@@ -200,11 +203,12 @@ extern "C" int srt_stream_create(const srt_config* cfg, const float* const* coef
     const size_t nspec = (size_t)3 * T * kBins, nmag = (size_t)2 * T * F, nmask = (size_t)2 * S * T * F * 2;
     if (cudaMalloc(&st->d_ring, 2 * kFFT * 4) || cudaMalloc(&st->d_awin, kFFT * 4) || cudaMalloc(&st->d_swin, 2048 * 4) ||
         cudaMalloc(&st->d_mask, nmask * 4) || cudaMalloc(&st->d_overlap, (size_t)2 * 2 * S * 1024 * 4) || cudaMalloc(&st->d_out, (size_t)2 * S * 1024 * 4) ||
-        cudaMalloc(&st->d_spec, nspec * sizeof(float4)) || cudaMalloc(&st->d_mag, nmag * sizeof(float2)) ||
+        cudaMalloc(&st->d_spec, nspec * sizeof(float4)) ||
         cudaMallocHost(&st->h_in, 2 * 1024 * 4) || cudaMallocHost(&st->h_out, (size_t)2 * S * 1024 * 4))
         return bail(internal::set_error(SRT_ERR_CUDA, "stream buffers: out of memory"));
     cudaMemset(st->d_ring, 0, 2 * kFFT * 4);
     cudaMemset(st->d_spec, 0, nspec * sizeof(float4));
+    st->d_mag = reinterpret_cast<float2*>(internal::ctx_mag(st->ctx));
     cudaMemset(st->d_mag, 0, nmag * sizeof(float2));
     cudaMemset(st->d_overlap, 0, (size_t)2 * 2 * S * 1024 * 4);
     fill_kernel<<<(unsigned)((nmask + 255) / 256), 256>>>(st->d_mask, 1.0f, nmask);   // masks start at 1 (Spleeter4Stems.c:455-466)
@@ -244,7 +248,7 @@ static int do_hop(srt_stream* st)
     p.ring = st->d_ring; p.pos = st->in_pos;                                  // oldest sample follows the newest
     p.awin = st->d_awin; p.swin = st->d_swin; p.twiddle = internal::ctx_twiddle(st->ctx);
     p.spec_new = st->d_spec + ((size_t)(k % 3) * T + st->cursor) * kBins;
-    p.mag_new = st->d_mag + ((size_t)(k % 2) * T + st->cursor) * F;
+    p.mag_new = st->d_mag + (size_t)(k % 2) * T * F;
     p.spec_old = st->d_spec + ((size_t)((k + 1) % 3) * T + st->cursor) * kBins;   // tile k-2
     p.mask_old = st->d_mask + (size_t)(k % 2) * S * T * F * 2;                    // masks of tile k-2
     p.cursor = st->cursor; p.T = T; p.F = F; p.S = S;
@@ -263,8 +267,7 @@ static int do_hop(srt_stream* st)
         cudaStream_t nn = internal::ctx_stream(st->ctx);
         SCK(cudaEventRecord(st->ev_tile[k % 2], st->hop_stream));
         SCK(cudaStreamWaitEvent(nn, st->ev_tile[k % 2], 0));
-        int r = internal::ctx_run_unet(st->ctx, reinterpret_cast<const float*>(st->d_mag + (size_t)(k % 2) * T * F), 1,
-                                       st->d_mask + (size_t)(k % 2) * S * T * F * 2, 1, 0);
+        int r = internal::ctx_run_unet(st->ctx, (int)(k % 2), 1, st->d_mask + (size_t)(k % 2) * S * T * F * 2, 1, 0);
         if (r) return r;
         SCK(cudaEventRecord(st->ev_nn[k % 2], nn));
         if (k >= 1) SCK(cudaStreamWaitEvent(st->hop_stream, st->ev_nn[(k - 1) % 2], 0));

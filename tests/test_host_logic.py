@@ -64,6 +64,21 @@ def test_gather_gemm_model_matches_oracle(oracle, host_model, small_nets, T, F, 
             assert err < 2e-5, f"up{d+1} (row-patch={row}): rel err {err}"
 
 
+def test_down1_tensor_core_plan(oracle, host_model, small_nets):
+    """space-to-depth magnitude + 9 taps x 8 channels + stems fused into N reproduces down1 (skip1)."""
+    T, F = 64, 128
+    rng = np.random.default_rng(11)
+    x = (np.abs(rng.standard_normal((2, T, F))) * 3).astype(np.float32)
+    coeffs = [np.ascontiguousarray(c) for c, _ in small_nets]
+    cp = (C.c_void_p * 2)(*[c.ctypes.data for c in coeffs])
+    out = np.zeros((2, 16, T // 2, F // 2), np.float32)
+    assert host_model.srt_host_model_down1(T, F, cp, 2, x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+    for s, (coeff, mode) in enumerate(small_nets):
+        _, tp = oracle.unet(coeff, x, mode, taps=True)
+        ref = oracle.split_taps(tp, T, F)["skip1"]
+        assert np.abs(out[s] - ref).max() / np.abs(ref).max() < 1e-3      # the magnitudes are TF32-rounded on the way in
+
+
 def test_plan_shapes(host_model):
     info = (C.c_int * 10)()
     # shape A (T=512, F=1024), batch 32: tiles are full and the k-block counts match the design
