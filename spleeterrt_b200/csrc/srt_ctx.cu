@@ -273,7 +273,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     if ((r = dalloc(c, &c->d_spec, (size_t)c->NB * T * kBins))) return r;
     if ((r = dalloc(c, &c->d_frames, (size_t)(S ? S : 1) * c->B * T * kFFT))) return r;
     if (S == 0) return 0;
-    if ((r = dalloc(c, &c->d_mag, (size_t)c->NB * T * F * 2))) return r;
+    if ((r = dalloc(c, &c->d_mag, (size_t)2 * c->NB * T * F * 2))) return r;   // hi images, then lo images
     if ((r = dalloc(c, &c->d_mask, (size_t)S * c->NB * T * F * 2))) return r;
     // ---- activations
     for (int i = 1; i <= 6; i++)
@@ -442,7 +442,8 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     if (c->cfg.conv_impl != 1 && !(d1e && atoi(d1e) == 0)) {
         const Down1Plan dp = build_down1_plan(NetGeom{T, F});
         KBlock* dkb;
-        std::vector<RowChunk> chunk = {RowChunk{0, 0, 0, (int32_t)dp.kb.size()}};
+        const int ntap = (int)dp.kb.size() / 2;
+        std::vector<RowChunk> chunk = {RowChunk{0, 0, 0, ntap}, RowChunk{1, 0, ntap, ntap}};
         RowChunk* dch;
         if ((r = upload(c, &dkb, dp.kb)) || (r = upload(c, &dch, chunk))) return r;
         std::vector<float> one(S * 16, 1.0f), zero(S * 16, 0.0f);
@@ -454,7 +455,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             pack_down1(dp, coeffs + s0, g, wpk.data());
             float* dw;
             if ((r = upload(c, &dw, wpk))) return r;
-            q.chunks = dch; q.n_chunks = 1; q.kb = dkb; q.nkb = (int)dp.kb.size();
+            q.chunks = dch; q.n_chunks = 2; q.kb = dkb; q.nkb = (int)dp.kb.size();
             q.w = dw; q.w_stem_stride = 0;
             q.N = 16 * g; q.R = 4; q.kb_width = kKB1;
             q.tiles_x = (dp.Ws + kTileM - 1) / kTileM;
@@ -468,12 +469,12 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             e.mode = 0; e.out_raw = c->E[1]; e.out_act = c->A[1];
             e.round_raw = 0;            // the skip feeds the fp32 SIMT up6 kernel
             e.round_act = 1;
-            if (make_tmap(&q.tmap[0], c->d_mag, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1)) {
+            if (make_tmap(&q.tmap[0], c->d_mag, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1) ||
+                make_tmap(&q.tmap[1], c->d_mag + (size_t)c->NB * T * F * 2, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1)) {
                 fprintf(stderr, "[spleeterrt_b200] down1 tensor map rejected (%s); using the SIMT kernel\n", g_err.c_str());
                 c->n_d1 = 0;
                 break;
             }
-            q.tmap[1] = q.tmap[0];
             c->n_d1++;
             s0 += g;
         }
@@ -540,6 +541,7 @@ static int run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask
         } else {
             Down1Params p{};
             p.mag = c->d_mag + (size_t)mag_img0 * c->T * c->F * 2;
+            p.mag_lo = p.mag + (size_t)c->NB * c->T * c->F * 2;
             p.w = c->d_w1; p.bias = c->d_b1; p.bn_scale = c->d_s1; p.bn_offset = c->d_o1;
             p.out_raw = c->E[1]; p.out_act = c->A[1];
             p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
@@ -624,7 +626,7 @@ extern "C" int srt_unet_device(srt_ctx* c, const float* d_mag, int n_img, float*
     if (n_img < 1 || n_img > c->B) return fail(SRT_ERR_CAPACITY, "n_img %d exceeds max_images %d", n_img, c->B);
     CK(cudaSetDevice(c->cfg.device));
     reset_spans(c);
-    launch_mag_to_s2d(d_mag, c->d_mag, c->T, c->F, n_img, c->stream);   // API layout -> space-to-depth, TF32-rounded
+    launch_mag_to_s2d(d_mag, c->d_mag, c->d_mag + (size_t)c->NB * c->T * c->F * 2, c->T, c->F, n_img, c->stream);   // API layout -> space-to-depth hi/lo
     c->launches++;
     return run_unet(c, 0, n_img, d_mask, n_img, 0);
 }
@@ -636,15 +638,19 @@ extern "C" int srt_unet_host(srt_ctx* c, const float* x, int n_img, float* y)
     CK(cudaSetDevice(c->cfg.device));
     reset_spans(c);
     const size_t P = (size_t)c->T * c->F;
-    std::vector<float> xi((size_t)n_img * P * 2);   // space-to-depth, TF32-rounded (what the device path stores)
+    std::vector<float> xi((size_t)n_img * P * 2), xlo((size_t)n_img * P * 2);   // space-to-depth hi / lo parts (what the device path stores)
     for (int b = 0; b < n_img; b++)
         for (int t = 0; t < c->T; t++)
             for (int f = 0; f < c->F; f++) {
                 const size_t o = ((size_t)b * P + mag_s2d_index(c->T, c->F, t, f)) * 2, i = (size_t)t * c->F + f;
-                xi[o + 0] = round_tf32(x[((size_t)b * 2 + 0) * P + i]);
-                xi[o + 1] = round_tf32(x[((size_t)b * 2 + 1) * P + i]);
+                for (int ch = 0; ch < 2; ch++) {
+                    const float m = x[((size_t)b * 2 + ch) * P + i], hi = round_tf32(m);
+                    xi[o + ch] = hi;
+                    xlo[o + ch] = m - hi;
+                }
             }
     CK(cudaMemcpyAsync(c->d_mag, xi.data(), xi.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_mag + (size_t)c->NB * P * 2, xlo.data(), xlo.size() * 4, cudaMemcpyHostToDevice, c->stream));
     int r = run_unet(c, 0, n_img, c->d_mask, c->NB, 0);
     if (r) return r;
     std::vector<float> mi((size_t)n_img * P * 2);
@@ -742,7 +748,7 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
         p.pcmR = (const float* const*)(c->d_meta + o_pr);
         p.n_samples = d_n; p.n_frames = d_nfr; p.imgs = d_imgs;
         p.window = c->d_window; p.twiddle = c->d_twiddle;
-        p.spec = c->d_spec; p.mag = c->d_mag;
+        p.spec = c->d_spec; p.mag = c->d_mag; p.mag_lo_off = (size_t)c->NB * T * c->F * 2;
         p.T = T; p.F = c->F; p.n_img = m.total; p.front_pad = front_pad;
         launch_stft(p, c->stream);
         c->launches++;

@@ -8,7 +8,7 @@ namespace srt {
 namespace internal {
 // U-Net on Bv images starting at image mag_img0 of the context's magnitude buffer, masks to mask_base[s][mask_img0 + b]; enqueued on ctx's stream
 int ctx_run_unet(srt_ctx* ctx, int mag_img0, int Bv, float* mask_base, int mask_stride, int mask_img0);
-float* ctx_mag(srt_ctx* ctx);   // the context's space-to-depth magnitude buffer [max_batch_images][T/2][F/2][8]
+float* ctx_mag(srt_ctx* ctx);   // the context's space-to-depth magnitude buffer: [max_batch_images] hi images, then as many lo images
 cudaStream_t ctx_stream(srt_ctx* ctx);
 const float2* ctx_twiddle(srt_ctx* ctx);
 void ctx_count_launch(srt_ctx* ctx, int n);

@@ -66,7 +66,8 @@ void launch_conv_rp(const RowConvParams& p, cudaStream_t st);
 // SIMT edge layers
 // ---------------------------------------------------------------------------------------
 struct Down1Params {              // 5x5 s2 conv 2->16 on the magnitude image, spleeter.c:181-190
-    const float* mag;             // space-to-depth magnitudes of the launch's first image: [Bv][T/2][F/2][(py,px)][c], TF32-rounded
+    const float* mag;             // space-to-depth magnitudes of the launch's first image: [Bv][T/2][F/2][(py,px)][c], TF32 "hi" part
+    const float* mag_lo;          // the matching "lo" part (mag = hi + lo exactly)
     const float* w;               // [S][16][2][5][5] (reference order)
     const float* bias;            // [S][16]
     const float* bn_scale;        // [S][16]
@@ -123,7 +124,8 @@ struct StftParams {
     const float* window;          // hann(i+1/2)/4096
     const float2* twiddle;        // exp(-2 pi i m / 4096)
     float4* spec;                 // [n_img][T][2049] (reL, imL, reR, imR) in the reference's convention
-    float* mag;                   // [n_img][T/2][F/2][(py,px)][c] space-to-depth, TF32-rounded (what down1 reads)
+    float* mag;                   // [n_img][T/2][F/2][(py,px)][c] space-to-depth, split in two tensors: hi = tf32(mag) here,
+    size_t mag_lo_off;            // lo = mag - hi at mag + mag_lo_off floats (down1 contracts both: fp32-accurate first layer)
     int T, F, n_img;
     int front_pad;                // 4096 zeros in front (main.c:767) or 0 (raw stft())
 };
@@ -166,7 +168,7 @@ void launch_stft(const StftParams& p, cudaStream_t st);
 void launch_istft(const IstftParams& p, cudaStream_t st);
 void launch_ola(const OlaParams& p, cudaStream_t st);
 // [n][T][F][2] (API layout) -> space-to-depth, TF32-rounded
-void launch_mag_to_s2d(const float* in, float* out, int T, int F, int n_img, cudaStream_t st);
+void launch_mag_to_s2d(const float* in, float* out_hi, float* out_lo, int T, int F, int n_img, cudaStream_t st);
 size_t conv_tc_smem_bytes(int n_tile, int* stages_out);
 
 __device__ __forceinline__ float apply_act(int act, float x)

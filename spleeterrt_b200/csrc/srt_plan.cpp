@@ -313,9 +313,11 @@ Down1Plan build_down1_plan(NetGeom g)
     Down1Plan L{};
     L.Hs = g.T / 2;
     L.Ws = g.F / 2;
+    // two slabs with the same taps and weights: source 0 = tf32(mag), source 1 = mag - tf32(mag)
+    for (int part = 0; part < 2; part++)
     for (int dy = -1; dy <= 1; dy++)
         for (int dx = -1; dx <= 1; dx++) {
-            L.kb.push_back(KBlock{0, (int8_t)dy, (int8_t)dx, 0, 0});
+            L.kb.push_back(KBlock{(int8_t)part, (int8_t)dy, (int8_t)dx, 0, 0});
             for (int j = 0; j < kKB1; j++) {
                 const int py = j >> 2, px = (j >> 1) & 1, c = j & 1;
                 KElemP e{-1, {-1, -1, -1, -1}, {-1, -1, -1, -1}};

@@ -137,7 +137,7 @@ inline int row_plan_R(int N) { return N <= 64 ? 3 : 2; }
 constexpr int kKB1 = 8;
 struct Down1Plan {
     int Hs, Ws;                         // output (= S2D input) extent: T/2 x F/2
-    std::vector<KBlock> kb;             // 9 taps
+    std::vector<KBlock> kb;             // 2 x 9 taps: src 0 = hi part of the magnitude, src 1 = lo part (same weights)
     std::vector<KElemP> kelem;          // 8 per tap (kh/kw in slot 0)
 };
 Down1Plan build_down1_plan(NetGeom g);

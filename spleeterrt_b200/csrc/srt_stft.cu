@@ -32,7 +32,11 @@ __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
     if (f >= nfr) {
         // zero-padded tail of the last tile (main.c:507-514)
         for (int k = j; k < kBins; k += kFftThreads) srow[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = j; k < p.F; k += kFftThreads) mimg[mag_s2d_index(p.T, p.F, t, k)] = make_float2(0.f, 0.f);
+        for (int k = j; k < p.F; k += kFftThreads) {
+            const size_t mi = mag_s2d_index(p.T, p.F, t, k);
+            mimg[mi] = make_float2(0.f, 0.f);
+            mimg[mi + p.mag_lo_off / 2] = make_float2(0.f, 0.f);
+        }
         return;
     }
     const int n = p.n_samples[d.stream];
@@ -71,8 +75,13 @@ __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
         o.w = 0.5f * (ar - br);          // -Im XR = -(-(ar - br)/2)
         if (k == 0 || k == kFFT / 2) { o.y = 0.f; o.w = 0.f; }
         srow[k] = o;
-        if (k < p.F)
-            mimg[mag_s2d_index(p.T, p.F, t, k)] = make_float2(ptx::rna_tf32(hypotf(o.x, o.y) * (float)kFFT), ptx::rna_tf32(hypotf(o.z, o.w) * (float)kFFT));
+        if (k < p.F) {
+            const float mL = hypotf(o.x, o.y) * (float)kFFT, mR = hypotf(o.z, o.w) * (float)kFFT;
+            const float hL = ptx::rna_tf32(mL), hR = ptx::rna_tf32(mR);
+            const size_t mi = mag_s2d_index(p.T, p.F, t, k);
+            mimg[mi] = make_float2(hL, hR);
+            mimg[mi + p.mag_lo_off / 2] = make_float2(mL - hL, mR - hR);
+        }
     }
 }
 

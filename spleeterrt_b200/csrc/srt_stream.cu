@@ -37,7 +37,8 @@ struct HopParams {
     const float* swin;        // synthesis window, pre-shifted: 2048 entries
     const float2* twiddle;
     float4* spec_new;         // [2049] row being recorded
-    float2* mag_new;          // space-to-depth magnitude image being recorded (row = cursor)
+    float2* mag_new;          // space-to-depth magnitude image being recorded (row = cursor), hi part
+    size_t mag_lo_off;        // float2 offset of the lo part
     const float4* spec_old;   // [2049] row recorded two tiles ago
     const float* mask_old;    // masks of that tile: [S][T][F][2]
     int cursor, T, F, S;
@@ -81,9 +82,13 @@ __global__ void __launch_bounds__(kFftThreads) stream_hop_kernel(const HopParams
             o.w = 0.5f * (ar - br);
             if (k == 0 || k == kFFT / 2) { o.y = 0.f; o.w = 0.f; }
             p.spec_new[k] = o;
-            if (k < p.F)
-                p.mag_new[mag_s2d_index(p.T, p.F, p.cursor, k)] =
-                    make_float2(ptx::rna_tf32(hypotf(o.x, o.y) * (float)kFFT), ptx::rna_tf32(hypotf(o.z, o.w) * (float)kFFT));
+            if (k < p.F) {
+                const float mL = hypotf(o.x, o.y) * (float)kFFT, mR = hypotf(o.z, o.w) * (float)kFFT;
+                const float hL = ptx::rna_tf32(mL), hR = ptx::rna_tf32(mR);
+                const size_t mi = mag_s2d_index(p.T, p.F, p.cursor, k);
+                p.mag_new[mi] = make_float2(hL, hR);
+                p.mag_new[mi + p.mag_lo_off] = make_float2(mL - hL, mR - hR);
+            }
         }
         return;
     }
@@ -209,7 +214,7 @@ extern "C" int srt_stream_create(const srt_config* cfg, const float* const* coef
     cudaMemset(st->d_ring, 0, 2 * kFFT * 4);
     cudaMemset(st->d_spec, 0, nspec * sizeof(float4));
     st->d_mag = reinterpret_cast<float2*>(internal::ctx_mag(st->ctx));
-    cudaMemset(st->d_mag, 0, nmag * sizeof(float2));
+    cudaMemset(st->d_mag, 0, 2 * nmag * sizeof(float2));
     cudaMemset(st->d_overlap, 0, (size_t)2 * 2 * S * 1024 * 4);
     fill_kernel<<<(unsigned)((nmask + 255) / 256), 256>>>(st->d_mask, 1.0f, nmask);   // masks start at 1 (Spleeter4Stems.c:455-466)
     // windows: getAsymmetricWindow(analysis, synthesis, k = 4096, m = 1024, 1.0) (Spleeter4Stems.c:383-401, 414-416)
@@ -249,6 +254,7 @@ static int do_hop(srt_stream* st)
     p.awin = st->d_awin; p.swin = st->d_swin; p.twiddle = internal::ctx_twiddle(st->ctx);
     p.spec_new = st->d_spec + ((size_t)(k % 3) * T + st->cursor) * kBins;
     p.mag_new = st->d_mag + (size_t)(k % 2) * T * F;
+    p.mag_lo_off = (size_t)2 * T * F;   // lo images follow the two hi images
     p.spec_old = st->d_spec + ((size_t)((k + 1) % 3) * T + st->cursor) * kBins;   // tile k-2
     p.mask_old = st->d_mask + (size_t)(k % 2) * S * T * F * 2;                    // masks of tile k-2
     p.cursor = st->cursor; p.T = T; p.F = F; p.S = S;

@@ -71,11 +71,16 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const __grid_consta
     const int ow0 = blockIdx.x * D1_TW, oh0 = blockIdx.y * D1_TH;
     const int tid = threadIdx.x;
     const float2* img = reinterpret_cast<const float2*>(p.mag) + (size_t)b * p.T * p.F;
+    const float2* img_lo = reinterpret_cast<const float2*>(p.mag_lo) + (size_t)b * p.T * p.F;
     for (int i = tid; i < D1_PH * D1_PW; i += blockDim.x) {
         const int r = i / D1_PW, c = i % D1_PW;
         const int ih = 2 * oh0 - 1 + r, iw = 2 * ow0 - 1 + c;
         float2 v = make_float2(0.f, 0.f);
-        if (ih >= 0 && ih < p.T && iw >= 0 && iw < p.F) v = img[mag_s2d_index(p.T, p.F, ih, iw)];
+        if (ih >= 0 && ih < p.T && iw >= 0 && iw < p.F) {
+            const size_t mi = mag_s2d_index(p.T, p.F, ih, iw);
+            const float2 hi = img[mi], lo = img_lo[mi];
+            v = make_float2(hi.x + lo.x, hi.y + lo.y);
+        }
         patch[r][c] = v;
     }
     __syncthreads();
@@ -298,18 +303,20 @@ void launch_up7(const Up7Params& p, cudaStream_t st)
 }
 
 // API layout [n][T][F][2] -> internal space-to-depth layout, TF32-rounded (srt_unet_device)
-__global__ void mag_to_s2d_kernel(const float2* __restrict__ in, float2* __restrict__ out, int T, int F, int n_img)
+__global__ void mag_to_s2d_kernel(const float2* __restrict__ in, float2* __restrict__ out, float2* __restrict__ out_lo, int T, int F, int n_img)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, per = (size_t)T * F;
     if (i >= per * n_img) return;
     const int img = (int)(i / per), t = (int)((i % per) / F), f = (int)(i % F);
     const float2 v = in[i];
-    out[(size_t)img * per + mag_s2d_index(T, F, t, f)] = make_float2(ptx::rna_tf32(v.x), ptx::rna_tf32(v.y));
+    const float2 hi = make_float2(ptx::rna_tf32(v.x), ptx::rna_tf32(v.y));
+    out[(size_t)img * per + mag_s2d_index(T, F, t, f)] = hi;
+    out_lo[(size_t)img * per + mag_s2d_index(T, F, t, f)] = make_float2(v.x - hi.x, v.y - hi.y);
 }
-void launch_mag_to_s2d(const float* in, float* out, int T, int F, int n_img, cudaStream_t st)
+void launch_mag_to_s2d(const float* in, float* out, float* out_lo, int T, int F, int n_img, cudaStream_t st)
 {
     const size_t n = (size_t)T * F * n_img;
-    mag_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), T, F, n_img);
+    mag_to_s2d_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), reinterpret_cast<float2*>(out_lo), T, F, n_img);
 }
 
 }  // namespace srt

@@ -197,10 +197,14 @@ extern "C" int srt_host_model_down1(int T, int F, const float* const* coeffs, in
     const Down1Plan L = build_down1_plan(NetGeom{T, F});
     const CoeffLayout cl = coeff_layout();
     const int H = L.Hs, W = L.Ws, N = 16 * nstems;
-    std::vector<float> src((size_t)H * W * 8, 0.f);
+    std::vector<float> src[2] = {std::vector<float>((size_t)H * W * 8, 0.f), std::vector<float>((size_t)H * W * 8, 0.f)};
     for (int c = 0; c < 2; c++)
         for (int t = 0; t < T; t++)
-            for (int f = 0; f < F; f++) src[mag_s2d_index(T, F, t, f) * 2 + c] = round_tf32(mag[((size_t)c * T + t) * F + f]);
+            for (int f = 0; f < F; f++) {
+                const float m = mag[((size_t)c * T + t) * F + f], hi = round_tf32(m);
+                src[0][mag_s2d_index(T, F, t, f) * 2 + c] = hi;
+                src[1][mag_s2d_index(T, F, t, f) * 2 + c] = m - hi;
+            }
     std::vector<float> wpk(L.kb.size() * (size_t)N * kKB1);
     pack_down1(L, coeffs, nstems, wpk.data());
     for (int Y = 0; Y < H; Y++)
@@ -210,7 +214,7 @@ extern "C" int srt_host_model_down1(int T, int F, const float* const* coeffs, in
                 for (size_t k = 0; k < L.kb.size(); k++) {
                     const int yy = Y + L.kb[k].dy, xx = X + L.kb[k].dx;
                     if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-                    for (int j = 0; j < kKB1; j++) acc += src[((size_t)yy * W + xx) * 8 + j] * wpk[k * (size_t)N * kKB1 + swz32_index(n, j)];
+                    for (int j = 0; j < kKB1; j++) acc += src[L.kb[k].src][((size_t)yy * W + xx) * 8 + j] * wpk[k * (size_t)N * kKB1 + swz32_index(n, j)];
                 }
                 const int s = n / 16, o = n % 16;
                 out[(((size_t)s * 16 + o) * H + Y) * W + X] = acc + coeffs[s][cl.down_b[0] + o];

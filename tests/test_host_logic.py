@@ -76,7 +76,7 @@ def test_down1_tensor_core_plan(oracle, host_model, small_nets):
     for s, (coeff, mode) in enumerate(small_nets):
         _, tp = oracle.unet(coeff, x, mode, taps=True)
         ref = oracle.split_taps(tp, T, F)["skip1"]
-        assert np.abs(out[s] - ref).max() / np.abs(ref).max() < 1e-3      # the magnitudes are TF32-rounded on the way in
+        assert np.abs(out[s] - ref).max() / np.abs(ref).max() < 2e-5      # hi + lo split keeps the first layer fp32-accurate
 
 
 def test_plan_shapes(host_model):
