@@ -8,8 +8,8 @@
 //     whole-pixel offset (dx, dy) the k-block table prescribes; out-of-image pixels are
 //     zero-filled by the TMA unit (= the reference's zero padding).  128B-swizzled, K-major.
 //   * W_kb is a pre-packed, pre-swizzled [N][32] block streamed with a 1-D bulk copy.
-//   * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (accumulator lives in TMEM),
-//     warps 2..9 = epilogue (tcgen05.ld -> bias / BN / activation -> global, see srt_epilogue.cuh).
+//   * warps 0..7 = epilogue, warp 8 = TMA producer, warp 9 = tcgen05.mma issuer (accumulator lives in TMEM)
+//     (epilogue (tcgen05.ld -> bias / BN / activation -> global, see srt_epilogue.cuh).
 //   * ring of mbarrier-guarded stages; one output tile per CTA.
 #include "srt_epilogue.cuh"
 #include "srt_kernels.cuh"
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         const KBlock* src = p.kb + p.kb_off[phase];
         for (int i = threadIdx.x; i < nkb; i += kConvThreads) hdr->kb[i] = src[i];
     }
-    if (warp == 0 && lane == 0) {
+    if (warp == 8 && lane == 0) {
         ptx::tma_prefetch_desc(&p.tmap[0]);
         ptx::tma_prefetch_desc(&p.tmap[1]);
         for (int i = 0; i < stages; i++) {
@@ -74,13 +74,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         ptx::mbar_init(&hdr->tmem_full, 1);
         ptx::fence_barrier_init();
     }
-    if (warp == 1) ptx::tmem_alloc<kTmemCols>(&hdr->tmem_base);
+    if (warp == 9) ptx::tmem_alloc<kTmemCols>(&hdr->tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_d = hdr->tmem_base;
 
-    if (warp == 0) {
+    // the issue arbiter favours higher warp ids: producer and MMA issuer sit above the 8 epilogue warps
+    if (warp == 8) {
         // ===== TMA producer ==============================================================
         if (lane == 0) {
             const int x0 = tx * p.tw, y0 = ty * p.th, n0 = s * p.B + tz * p.nb;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
                 if (++stage == stages) { stage = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 9) {
         // ===== MMA issuer ================================================================
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N_TILE);
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
     } else {
         // ===== epilogue: TMEM -> registers -> bias/BN/act -> global ======================
-        const int q = warp & 3, half = (warp - 2) >> 2;   // TMEM lane quarter this warp may read; column half
+        const int q = warp & 3, half = warp >> 2;   // TMEM lane quarter this warp may read; column half
         const int m = q * 32 + lane;
         const int x = m % p.tw, y = (m / p.tw) % p.th, nn = m / (p.tw * p.th);
         const int X = tx * p.tw + x, Y = ty * p.th + y, b = tz * p.nb + nn;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 9) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<kTmemCols>(tmem_d);
     }

@@ -758,7 +758,23 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
         const int Bv = std::min(c->B, m.total - i0);
         if ((r = run_unet(c, i0, Bv, c->d_mask, c->NB, i0))) return r;
     }
-    // ---- mask * spectrum -> inverse FFT -> OLA, in groups of whole streams that fit the scratch
+    // ---- mask * spectrum -> inverse FFT -> window -> overlap-add -> un-framing, one fused kernel
+    // (SRT_FUSED_OLA=0 selects the two-kernel path through the scratch frames, kept for the tier-A istft())
+    const char* fo = getenv("SRT_FUSED_OLA");
+    if (!(fo && atoi(fo) == 0)) {
+        Timed t(c, 14);
+        IstftOlaParams p{};
+        p.spec = c->d_spec; p.mask = c->d_mask;
+        p.stream_img0 = (const int*)(c->d_meta + o_i0); p.n_frames = d_nfr; p.n_samples = d_n;
+        p.postwin = c->d_postwin; p.twiddle = c->d_twiddle; p.out = (float* const*)(c->d_meta + o_out);
+        for (int s = 0; s < S; s++) p.unaffected[s] = unaffected ? unaffected[s] : 0.1f;
+        p.T = T; p.F = c->F; p.S = S; p.mask_stem_stride = c->NB; p.stream_first = 0; p.front_pad = front_pad;
+        p.hops_per_cta = 16;
+        int max_fr = 0;
+        for (int i = 0; i < n_streams; i++) max_fr = std::max(max_fr, m.nfr[i]);
+        launch_istft_ola(p, n_streams, max_fr, c->stream);
+        c->launches++;
+    } else {
     int s0 = 0;
     while (s0 < n_streams) {
         int s1 = s0, imgs = 0;
@@ -793,6 +809,7 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
             c->launches++;
         }
         s0 = s1;
+    }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SRT_ERR_CUDA, "separate launch: %s", cudaGetErrorString(e));

@@ -158,6 +158,26 @@ struct OlaParams {
     int front_pad;
 };
 
+// mask*spectrum -> inverse FFT -> window -> overlap-add fused: one CTA walks G consecutive hops of one
+// (stream, stem) and keeps the 4-frame overlap in shared memory (no scratch frames, no second kernel)
+struct IstftOlaParams {
+    const float4* spec;           // [all images][T][2049]
+    const float* mask;            // [S][mask_stem_stride images][T][F][2]
+    const int* stream_img0;       // per stream: first image index
+    const int* n_frames;          // per stream
+    const int* n_samples;         // per stream
+    const float* postwin;
+    const float2* twiddle;
+    float* const* out;            // [stream][S*2] planar outputs
+    float unaffected[8];
+    int T, F, S;
+    int mask_stem_stride;
+    int stream_first;
+    int front_pad;
+    int hops_per_cta;
+};
+void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cudaStream_t st);
+
 // launchers (defined in the .cu files)
 void launch_conv_tc(const ConvParams& p, cudaStream_t st);
 void launch_conv_simt(const ConvParams& p, cudaStream_t st);

@@ -146,6 +146,91 @@ void launch_istft(const IstftParams& p, cudaStream_t st)
 }
 
 // =========================================================================================
+// Fused mask*spectrum -> inverse FFT -> synthesis window -> overlap-add -> un-framing.
+// One CTA owns hops [h0, h0+G) of one (stream, stem): it transforms frames h0-3 .. h0+G-1 in order and
+// accumulates them in a 4096-sample shared-memory ring (same summation order as stftFix.c:570-575), emitting
+// each 1024-sample segment as soon as its last contributing frame has been added.  (G+3)/G of the FFT work,
+// but no 32 KB-per-frame scratch round trip and no separate OLA kernel.
+// =========================================================================================
+__global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOlaParams p)
+{
+    extern __shared__ float ola_smem[];
+    float* sre = ola_smem;
+    float* sim = ola_smem + kPadLen;
+    float2* ring = reinterpret_cast<float2*>(ola_smem + 2 * kPadLen);
+    const int st = p.stream_first + blockIdx.z, s = blockIdx.y;
+    const int nfr = p.n_frames[st];
+    const int h0 = blockIdx.x * p.hops_per_cta;
+    if (h0 >= nfr) return;
+    const int h1 = min(h0 + p.hops_per_cta, nfr);
+    const int j = threadIdx.x;
+    const int n = p.n_samples[st], img0 = p.stream_img0[st];
+    float* outL = p.out[(size_t)st * p.S * 2 + s * 2];
+    float* outR = p.out[(size_t)st * p.S * 2 + s * 2 + 1];
+    const float uw = p.unaffected[s];
+    for (int i = j; i < kFFT; i += kFftThreads) ring[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+    const long lo = (long)h0 * kHop, hi = (long)h1 * kHop;
+    for (int f = max(h0 - 3, 0); f < h1; f++) {
+        const int img = img0 + f / p.T, t = f % p.T;
+        const float4* srow = p.spec + ((size_t)img * p.T + t) * kBins;
+        const float2* mrow = reinterpret_cast<const float2*>(p.mask) + (((size_t)s * p.mask_stem_stride + img) * p.T + t) * p.F;
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int k = j + 256 * r;
+            const int kk = k <= kFFT / 2 ? k : kFFT - k;
+            const float4 sp = srow[kk];
+            float mL = uw, mR = uw;
+            if (kk < p.F) { const float2 m = mrow[kk]; mL = m.x; mR = m.y; }
+            const float xlr = sp.x * mL, xli = -(sp.y * mL), xrr = sp.z * mR, xri = -(sp.w * mR);
+            float2 z;
+            if (k <= kFFT / 2) z = make_float2(xlr - xri, xli + xrr);
+            else z = make_float2(xlr + xri, -xli + xrr);
+            v[r] = make_float2(z.x, -z.y);
+        }
+        fft4096(v, sre, sim, p.twiddle, j);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int i = j + 256 * r;
+            const long pos = (long)f * kHop + i;
+            if (pos >= lo && pos < hi) {
+                const float w = __ldg(&p.postwin[i]);
+                float2 a = ring[pos & (kFFT - 1)];
+                a.x += v[r].x * w;
+                a.y += -v[r].y * w;
+                ring[pos & (kFFT - 1)] = a;
+            }
+        }
+        __syncthreads();
+        if (f >= h0) {   // segment f is complete: frames f-3 .. f have been added
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const long pos = (long)f * kHop + j + 256 * k;
+                const float2 a = ring[pos & (kFFT - 1)];
+                ring[pos & (kFFT - 1)] = make_float2(0.f, 0.f);
+                const long io = pos - p.front_pad;
+                if (io >= 0 && io < n) { outL[io] = a.x; outR[io] = a.y; }
+            }
+        }
+        // the next frame touches the ring only after the barriers inside its FFT
+    }
+}
+
+void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cudaStream_t st)
+{
+    if (n_streams == 0 || max_frames == 0) return;
+    const size_t smem = (2 * kPadLen + 2 * kFFT) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    dim3 grid((max_frames + p.hops_per_cta - 1) / p.hops_per_cta, p.S, n_streams);
+    istft_ola_kernel<<<grid, kFftThreads, smem, st>>>(p);
+}
+
+// =========================================================================================
 // overlap-add + un-framing (channel_joinFloat preshift, main.c:806): out[i] = ola[front_pad + i]
 // =========================================================================================
 __global__ void __launch_bounds__(256) ola_kernel(const OlaParams p)
