@@ -93,7 +93,7 @@ def reference_arm(args, rank):
         if have_ref:
             return O.ref_exec().separate(nets, L, R, T, F, unaffected=0.1)
         return O.separate(nets, L, R, T, F, unaffected=0.1)
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(max(min(args.warmup, 1), 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -286,6 +286,11 @@ def main():
         tc_flop = W.FLOP_PER_PIXEL_TC * P * n_tc_units
         tc_ms = sum(layer_ms[k] for k in W.LAYER_FLOP_PER_PIXEL) / args.steps
         tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and ns == 32:      # the capture was taken at the default batch
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["tc_layers"]["dram_bytes_per_step"], tj["source"]
         ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         per_layer = {k: {"ms": layer_ms[k] / args.steps,
                          "tflops": (W.LAYER_FLOP_PER_PIXEL[k] * P * n_tc_units) / (layer_ms[k] / args.steps * 1e-3) / 1e12
@@ -309,7 +314,7 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/tconv, 10 layers)", "bound": "tensor",
                          "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak if tf32_peak else None,
-                         "traffic": None, "peak_source": f"{pk['source']} bf16 sustained {pk['bf16_tflops_sustained']} TF/s / 2 (TF32 operands)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{pk['source']} bf16 sustained {pk['bf16_tflops_sustained']} TF/s / 2 (TF32 operands)",
                          "ms_per_step": tc_ms, "flop_per_step": tc_flop, "per_layer": per_layer},
             "stage_ms": other,
             "hbm_stages": {"stft_gbs": stft_bytes / (other["stft"] * 1e-3) / 1e9 if other["stft"] > 0 else None,
