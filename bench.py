@@ -77,6 +77,18 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
+def host_threads():
+    """threads for the CPU baseline: one per physical core (the naive OpenMP loops lose time on SMT siblings)"""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return n
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
 def reference_arm(args, rank):
     """The reference's own CPU implementation of the path (oracle/_ref build of the reference's C
     sources, naive CPU_GEMM backend), all host threads, bounded sample per step."""
@@ -86,8 +98,8 @@ def reference_arm(args, rank):
     have_ref = O.have_ref()
     nets = O.four_stem_weights()
     L, R = O.synth_pcm(0, n=N_SAMPLES)
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
 
     def step():
         if have_ref:
@@ -119,8 +131,13 @@ def cpu_baseline_sample():
     from oracle import oracle as O
     nets = O.four_stem_weights()
     L, R = O.synth_pcm(0, n=N_SAMPLES)
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:   # torch shares libgomp with the reference build: pin its thread count too
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
     have_ref = O.have_ref()
     t0 = time.perf_counter()
     if have_ref:

@@ -111,6 +111,7 @@ struct srt_ctx {
     bool use_rp[10]{};
     RowConvParams d1[4];            // down1 on the tensor cores: groups of up to 4 stems fused into N
     int n_d1 = 0;
+    bool split_weights = false;     // two-term weights (not TF32-exact)
     // activations
     float* E[7]{};    // E[1..6] raw skips (NHWC)
     float* A[6]{};    // A[1..5] activated, space-to-depth
@@ -327,7 +328,13 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         if ((r = upload(c, &c->d_w7, w7)) || (r = upload(c, &c->d_b7, b7))) return r;
     }
     // ---- tensor-core layers
-    c->plans = build_plans(NetGeom{T, F}, c->B);
+    // Weights that are exactly TF32-representable (the reference's fp16 model) need one MMA term; anything else
+    // (fp32 `.dat` dumps) is contracted as tf32(w) + tf32(w - tf32(w)) so rounding the weights never costs parity.
+    bool split = false;
+    for (int s = 0; s < S; s++) split = split || !weights_tf32_exact(coeffs[s]);
+    if (const char* we = getenv("SRT_WEIGHT_SPLIT")) split = atoi(we) != 0;
+    c->split_weights = split;
+    c->plans = build_plans(NetGeom{T, F}, c->B, split);
     c->conv.resize(c->plans.size());
     for (size_t li = 0; li < c->plans.size(); li++) {
         const LayerPlan& L = c->plans[li];
@@ -409,7 +416,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     const char* boe = getenv("SRT_RP_BO");
     for (size_t li = 0; li < c->plans.size(); li++) {
         if (!row_plan_supported((int)li) || c->cfg.conv_impl == 1) continue;
-        const RowPlan rpl = build_row_plan(NetGeom{T, F}, (int)li);
+        const RowPlan rpl = build_row_plan(NetGeom{T, F}, (int)li, c->split_weights);
         const bool want = rpe ? atoi(rpe) != 0 : rpl.Ws >= 96;
         if (!want) continue;
         RowConvParams& q = c->rp[li];
@@ -440,7 +447,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     // (SRT_DOWN1_TC=0 keeps the SIMT kernel)
     const char* d1e = getenv("SRT_DOWN1_TC");
     if (c->cfg.conv_impl != 1 && !(d1e && atoi(d1e) == 0)) {
-        const Down1Plan dp = build_down1_plan(NetGeom{T, F});
+        const Down1Plan dp = build_down1_plan(NetGeom{T, F}, c->split_weights);
         KBlock* dkb;
         const int ntap = (int)dp.kb.size() / 2;
         std::vector<RowChunk> chunk = {RowChunk{0, 0, 0, ntap}, RowChunk{1, 0, ntap, ntap}};

@@ -69,7 +69,40 @@ static int dec_taps(int par, int kh[3], int dy[3])
     return 3;
 }
 
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img)
+// duplicate every k-block (and its k-elements) as a part-1 twin right after it
+template <class KE>
+static void split_kblocks(std::vector<KBlock>& kb, std::vector<KE>& ke, int per)
+{
+    std::vector<KBlock> kb2;
+    std::vector<KE> ke2;
+    for (size_t k = 0; k < kb.size(); k++)
+        for (int part = 0; part < 2; part++) {
+            KBlock b = kb[k];
+            b.part = (int8_t)part;
+            kb2.push_back(b);
+            ke2.insert(ke2.end(), ke.begin() + k * per, ke.begin() + (k + 1) * per);
+        }
+    kb.swap(kb2);
+    ke.swap(ke2);
+}
+
+bool weights_tf32_exact(const float* coeff)
+{
+    const CoeffLayout cl = coeff_layout();
+    for (int i = 0; i < 6; i++) {
+        const size_t n = (size_t)25 * kEnc[i] * kEnc[i + 1];
+        for (size_t j = 0; j < n; j++)
+            if (round_tf32(coeff[cl.down_w[i] + j]) != coeff[cl.down_w[i] + j]) return false;
+    }
+    for (int i = 0; i < 5; i++) {
+        const size_t n = (size_t)25 * kDecIn[i] * kDecOut[i];
+        for (size_t j = 0; j < n; j++)
+            if (round_tf32(coeff[cl.up_w[i] + j]) != coeff[cl.up_w[i] + j]) return false;
+    }
+    return true;
+}
+
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights)
 {
     std::vector<LayerPlan> plans;
     // ---- encoder: down2 .. down6 --------------------------------------------------------
@@ -155,6 +188,9 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img)
             }
         plans.push_back(L);
     }
+    if (split_weights)
+        for (auto& L : plans)
+            for (int p = 0; p < L.phases; p++) split_kblocks(L.kb[p], L.kelem[p], kKB);
     for (auto& L : plans) {
         size_t off = 0;
         for (int p = 0; p < L.phases; p++) {
@@ -184,7 +220,7 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
                             const size_t idx = L.transposed
                                 ? (((size_t)e.cin * L.cout + o) * 5 + e.kh) * 5 + e.kw      // [I][O][kh][kw]
                                 : (((size_t)o * L.cin + e.cin) * 5 + e.kh) * 5 + e.kw;     // [O][I][kh][kw]
-                            v = round_tf32(w[idx]);
+                            v = weight_part(w[idx], L.kb[p][kb].part);
                         }
                         blk[swz128_index(n, j)] = v;
                     }
@@ -205,7 +241,7 @@ static int dec_kh(int par, int d)
     return d == 1 ? 0 : (d == 0 ? 2 : 4);
 }
 
-RowPlan build_row_plan(NetGeom g, int layer_index)
+RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights)
 {
     RowPlan L{};
     L.index = layer_index;
@@ -278,6 +314,11 @@ RowPlan build_row_plan(NetGeom g, int layer_index)
                 L.chunks.push_back(ch);
             }
     }
+    if (split_weights) {
+        // twins stay inside their chunk: chunk k-block ranges double
+        split_kblocks(L.kb, L.kelem, kKB);
+        for (auto& ch : L.chunks) { ch.kb0 *= 2; ch.nkb *= 2; }
+    }
     L.R = row_plan_R(L.N);
     L.w_floats_per_stem = L.kb.size() * (size_t)L.N * kKB;
     return L;
@@ -297,7 +338,7 @@ void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
                 if (e.cin >= 0 && e.kh[ph] >= 0) {
                     const size_t idx = L.transposed ? (((size_t)e.cin * L.cout + o) * 5 + e.kh[ph]) * 5 + e.kw[ph]
                                                     : (((size_t)o * L.cin + e.cin) * 5 + e.kh[ph]) * 5 + e.kw[ph];
-                    v = round_tf32(w[idx]);
+                    v = weight_part(w[idx], L.kb[kb].part);
                 }
                 blk[swz128_index(n, j)] = v;
             }
@@ -308,7 +349,7 @@ void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
 // ------------------------------------------------------------------------------------------
 // down1 (tensor-core form)
 // ------------------------------------------------------------------------------------------
-Down1Plan build_down1_plan(NetGeom g)
+Down1Plan build_down1_plan(NetGeom g, bool split_weights)
 {
     Down1Plan L{};
     L.Hs = g.T / 2;
@@ -317,7 +358,7 @@ Down1Plan build_down1_plan(NetGeom g)
     for (int part = 0; part < 2; part++)
     for (int dy = -1; dy <= 1; dy++)
         for (int dx = -1; dx <= 1; dx++) {
-            L.kb.push_back(KBlock{(int8_t)part, (int8_t)dy, (int8_t)dx, 0, 0});
+            L.kb.push_back(KBlock{(int8_t)part, (int8_t)dy, (int8_t)dx, 0, 0});   // src = magnitude part (hi / lo)
             for (int j = 0; j < kKB1; j++) {
                 const int py = j >> 2, px = (j >> 1) & 1, c = j & 1;
                 KElemP e{-1, {-1, -1, -1, -1}, {-1, -1, -1, -1}};
@@ -331,6 +372,10 @@ Down1Plan build_down1_plan(NetGeom g)
                 L.kelem.push_back(e);
             }
         }
+    if (split_weights) {
+        // keep the (hi-magnitude taps | lo-magnitude taps) chunk structure: split each half separately
+        split_kblocks(L.kb, L.kelem, kKB1);
+    }
     return L;
 }
 
@@ -345,7 +390,7 @@ void pack_down1(const Down1Plan& L, const float* const* coeffs, int nstems, floa
             for (int j = 0; j < kKB1; j++) {
                 const KElemP& e = L.kelem[kb * kKB1 + j];
                 float v = 0.0f;
-                if (e.cin >= 0) v = round_tf32(w[(((size_t)o * 2 + e.cin) * 5 + e.kh[0]) * 5 + e.kw[0]]);
+                if (e.cin >= 0) v = weight_part(w[(((size_t)o * 2 + e.cin) * 5 + e.kh[0]) * 5 + e.kw[0]], L.kb[kb].part);
                 out[kb * (size_t)N * kKB1 + swz32_index(n, j)] = v;
             }
         }

@@ -37,7 +37,7 @@ enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_ELU_CLAMP = 3, A
 struct KBlock {
     int8_t src;      // 0 or 1 (decoder: 0 = skip tensor, 1 = up tensor)
     int8_t dy, dx;   // offset in tile-space pixels
-    int8_t pad;
+    int8_t part;     // 0: weights tf32(w); 1: weights tf32(w - tf32(w)) (second term for weights that are not TF32-exact)
     int32_t c_off;   // channel coordinate in the source tensor (multiple of 32, or of 16 for paired taps)
 };
 
@@ -84,7 +84,9 @@ struct CoeffLayout {
 CoeffLayout coeff_layout();
 
 // Build the 10 tensor-core layers for a T x F image and a batch of n_img images per launch.
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img);
+// split_weights: every k-block appears twice (part 0 / part 1) so that fp32 weights that are not exactly
+// representable in TF32 (the VST's fp32 `.dat` dumps) contribute w = tf32(w) + tf32(w - tf32(w)).
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false);
 
 // Pack one stem's weights for a layer into the k-block-major, 128B-swizzled layout the MMA
 // B operand is read from.  `coeff` is one spleeterCoeff blob.  Values are rounded to TF32
@@ -93,6 +95,9 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img);
 void pack_layer(const LayerPlan& L, const float* coeff, float* out);
 
 float round_tf32(float x);
+// value stored for a weight in a k-block of the given part
+inline float weight_part(float w, int part) { const float hi = round_tf32(w); return part == 0 ? hi : round_tf32(w - hi); }
+bool weights_tf32_exact(const float* coeff);   // all tensor-core conv weights of one net representable in TF32?
 
 // ---------------------------------------------------------------------------------------
 // "Row-patch" form of the small-N layers (down2, down3, up4, up5).  A CTA owns R output rows x
@@ -140,7 +145,7 @@ struct Down1Plan {
     std::vector<KBlock> kb;             // 2 x 9 taps: src 0 = hi part of the magnitude, src 1 = lo part (same weights)
     std::vector<KElemP> kelem;          // 8 per tap (kh/kw in slot 0)
 };
-Down1Plan build_down1_plan(NetGeom g);
+Down1Plan build_down1_plan(NetGeom g, bool split_weights = false);
 // weights of `nstems` consecutive stems -> [tap][N = 16*nstems][8] fp32, SWIZZLE_32B pre-applied
 void pack_down1(const Down1Plan& L, const float* const* coeffs, int nstems, float* out);
 SRT_HD inline int swz32_index(int row, int j) { return row * 8 + ((((j >> 2) ^ ((row >> 2) & 1)) << 2) | (j & 3)); }
@@ -148,7 +153,7 @@ SRT_HD inline int swz32_index(int row, int j) { return row * 8 + ((((j >> 2) ^ (
 SRT_HD inline size_t mag_s2d_index(int T, int F, int t, int f) { return (((size_t)(t >> 1) * (F >> 1) + (f >> 1)) << 2) + ((t & 1) << 1) + (f & 1); }
 
 bool row_plan_supported(int layer_index);                 // down2, down3, up4, up5
-RowPlan build_row_plan(NetGeom g, int layer_index);
+RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights = false);
 void pack_row_layer(const RowPlan& L, const float* coeff, float* out);
 
 // index of (row n, k-element j) inside a swizzled [rows][32] fp32 block

@@ -11,6 +11,9 @@
 
 using namespace srt;
 
+static bool g_split = false;   // two-term weights (weights not exactly representable in TF32)
+extern "C" void srt_host_model_set_split(int on) { g_split = on != 0; }
+
 static float act_apply(int act, float x)
 {
     switch (act) {
@@ -30,7 +33,7 @@ static float act_apply(int act, float x)
 extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
                                     float* out, int want_act)
 {
-    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1);
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split);
     if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
     const LayerPlan& L = plans[plan_index];
     const CoeffLayout cl = coeff_layout();
@@ -122,7 +125,7 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                                         float* out, int want_act)
 {
     if (!row_plan_supported(plan_index)) return -1;
-    const RowPlan L = build_row_plan(NetGeom{T, F}, plan_index);
+    const RowPlan L = build_row_plan(NetGeom{T, F}, plan_index, g_split);
     const CoeffLayout cl = coeff_layout();
     const int H = L.Hs, W = L.Ws;
     std::vector<std::vector<float>> src(L.nsrc);
@@ -194,7 +197,7 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
 // mag: planar [2][T][F]; coeffs: nstems blobs; out: [nstems][16][T/2][F/2] raw conv + bias
 extern "C" int srt_host_model_down1(int T, int F, const float* const* coeffs, int nstems, const float* mag, float* out)
 {
-    const Down1Plan L = build_down1_plan(NetGeom{T, F});
+    const Down1Plan L = build_down1_plan(NetGeom{T, F}, g_split);
     const CoeffLayout cl = coeff_layout();
     const int H = L.Hs, W = L.Ws, N = 16 * nstems;
     std::vector<float> src[2] = {std::vector<float>((size_t)H * W * 8, 0.f), std::vector<float>((size_t)H * W * 8, 0.f)};

@@ -274,3 +274,17 @@ def test_five_stem_batch(srt, oracle, small_nets):
         assert g.shape == (5, 2, L.size)
         for s in range(5):
             assert rms(g[s] - ref[s]) < 1e-4
+
+
+def test_fp32_weights_use_two_term_split(srt, oracle, small_nets):
+    """fp32 weights that are not fp16/TF32-representable (the VST's `.dat` dumps): the library detects them and
+    contracts tf32(w) + tf32(w - tf32(w)); stems stay within 1e-4 RMS of the oracle."""
+    rng = np.random.default_rng(31)
+    nets = [((c * (1 + 1e-3 * rng.standard_normal(c.shape))).astype(np.float32), m) for c, m in small_nets]
+    L, R = oracle.synth_pcm(2, n=30000)
+    sep = srt.Separator(nets, 64, 512, max_images=1)
+    got = sep.separate([(L, R)])[0]
+    sep.close()
+    ref = oracle.separate(nets, L, R, 64, 512)
+    for s in range(len(nets)):
+        assert rms(got[s] - ref[s]) < 1e-4, f"stem {s}: {rms(got[s] - ref[s])}"

@@ -79,6 +79,31 @@ def test_down1_tensor_core_plan(oracle, host_model, small_nets):
         assert np.abs(out[s] - ref).max() / np.abs(ref).max() < 2e-5      # hi + lo split keeps the first layer fp32-accurate
 
 
+def test_two_term_weights_for_fp32_blobs(oracle, host_model, small_nets):
+    """Weights that are not TF32-exact (fp32 `.dat` dumps): the k-block twins tf32(w) + tf32(w - tf32(w)) recover them."""
+    T, F = 64, 128
+    rng = np.random.default_rng(21)
+    coeff = (small_nets[0][0] * (1 + 1e-3 * rng.standard_normal(small_nets[0][0].shape))).astype(np.float32)
+    x = (np.abs(rng.standard_normal((2, T, F))) * 3).astype(np.float32)
+    _, tp = oracle.unet(coeff, x, 1, taps=True)
+    taps = oracle.split_taps(tp, T, F)
+    v = oracle.coeff_views(coeff)
+    bn = v["down2.bn"]
+    act_in = _act(3, bn[1][:, None, None] * taps["skip2"] + bn[0][:, None, None]).astype(np.float32)
+    errs = {}
+    for split in (0, 1):
+        host_model.srt_host_model_set_split(split)
+        for name, idx, row in (("down3", 1, False), ("down3-row", 1, True)):
+            got = _run_layer(host_model, T, F, idx, coeff, 3, act_in, None, taps["skip3"].shape, row=row)
+            errs[(name, split)] = np.abs(got - taps["skip3"]).max() / np.abs(taps["skip3"]).max()
+        got = _run_layer(host_model, T, F, 9, coeff, 3, taps["skip2"], taps["up4"], taps["up5"].shape, row=True)
+        errs[("up5-row", split)] = np.abs(got - taps["up5"]).max() / np.abs(taps["up5"]).max()
+    host_model.srt_host_model_set_split(0)
+    for name in ("down3", "down3-row", "up5-row"):
+        assert errs[(name, 1)] < 2e-5, errs
+        assert errs[(name, 0)] > 3 * errs[(name, 1)], errs      # single-term weights are visibly worse
+
+
 def test_plan_shapes(host_model):
     info = (C.c_int * 10)()
     # shape A (T=512, F=1024), batch 32: tiles are full and the k-block counts match the design

@@ -56,6 +56,41 @@ __global__ void probe(int N, int nacc, int iters, int a_shift_rows, long long* o
     if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tbase);
 }
 
+// two issuing warps (warp 0 and warp 1), each on its own accumulators: is the ~60-100 cycle floor per issuing
+// thread or per SM?
+template <int KIND>
+__global__ void probe2(int N, int nacc, int iters, long long* out)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t tbase;
+    const uint32_t base = (ptx::smem_u32(smem) + 1023u) & ~1023u;
+    for (int i = threadIdx.x; i < 40 * 1024 / 4; i += blockDim.x) reinterpret_cast<float*>(smem)[i] = 0.0f;
+    if (threadIdx.x == 0) { ptx::mbar_init(&bar[0], 1); ptx::mbar_init(&bar[1], 1); ptx::fence_barrier_init(); }
+    if (threadIdx.x < 32) ptx::tmem_alloc<512>(&tbase);
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const int w = threadIdx.x >> 5;
+    if (w < 2 && (threadIdx.x & 31) == 0) {
+        const uint32_t idesc = ptx::umma_idesc_tf32(128, N);
+        const uint32_t alo = ptx::umma_desc_lo(base), blo = ptx::umma_desc_lo(base + 20 * 1024);
+        const uint32_t t0a = tbase + w * nacc * N;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i++)
+            for (int a = 0; a < nacc; a++)
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) mma<KIND>(t0a + a * N, alo + kk * 2, blo + kk * 2, idesc, 1);
+        ptx::mma_commit(&bar[w]);
+        ptx::mbar_wait(&bar[w], 0);
+        out[w] = clock64() - t0;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) ptx::tmem_dealloc<512>(tbase);
+}
+
 int main()
 {
     long long* d;
@@ -78,5 +113,17 @@ int main()
                     const double n = (double)iters * nacc * 4;
                     printf("%s %3d %d %d | %7.1f | %7.1f\n", kind ? "f16 " : "tf32", N, nacc, shift, h[0] / n, h[1] / n);
                 }
+    cudaFuncSetAttribute(probe2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    printf("two issuing warps: N nacc(per warp) | cycles per MMA per warp | aggregate cycles per MMA\n");
+    for (int N : {32, 64, 128})
+        for (int nacc : {1, 2}) {
+            if (2 * nacc * N > 512) continue;
+            const int iters = 200;
+            probe2<0><<<1, 128, 64 * 1024>>>(N, nacc, iters, d);
+            long long h[2];
+            if (cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("error\n"); return 1; }
+            const double n = (double)iters * nacc * 4;
+            printf("tf32 %3d %d | %7.1f %7.1f | %7.1f\n", N, nacc, h[0] / n, h[1] / n, (h[0] > h[1] ? h[0] : h[1]) / (2 * n));
+        }
     return 0;
 }
