@@ -83,6 +83,18 @@ int srt_unet_device(srt_ctx* ctx, const float* d_mag, int n_img, float* d_mask);
 int srt_separate_batch(srt_ctx* ctx, const float* const* pcmL, const float* const* pcmR,
                        const size_t* n_samples, int n_streams, const float* unaffected,
                        float* const* stems_out);
+/* Asynchronous flavour of srt_separate_batch for a server that keeps the GPU and both PCIe
+ * directions busy: enqueues the upload, the kernels and the download of one batch and returns a
+ * ticket without waiting.  Three batches may be in flight per context (triple-buffered staging):
+ * batch k+1 uploads while batch k computes and batch k-1 is still being copied back.  A fourth
+ * call blocks until the oldest batch has drained.  pcm and stems_out buffers must stay valid (and
+ * should be pinned, srt_host_alloc) until srt_batch_wait(ticket) returns; results are complete
+ * only then.  Copies of channels that sit back to back in host memory are merged into one DMA.
+ * (The reference has no counterpart: main.c processes one file per process invocation.) */
+int srt_separate_batch_async(srt_ctx* ctx, const float* const* pcmL, const float* const* pcmR,
+                             const size_t* n_samples, int n_streams, const float* unaffected,
+                             float* const* stems_out, int* ticket_out);
+int srt_batch_wait(srt_ctx* ctx, int ticket);
 int srt_separate_device(srt_ctx* ctx, const float* const* d_pcmL, const float* const* d_pcmR,
                         const size_t* n_samples, int n_streams, const float* unaffected,
                         float* const* d_stems_out);

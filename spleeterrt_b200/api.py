@@ -16,7 +16,8 @@ COEFF_FLOATS = 9822725
 # every symbol include/*.h declares (checked by the CPU test-suite against the built library)
 HEADER_SYMBOLS = {
     "srt_b200.h": ["srt_create", "srt_destroy", "srt_last_error", "srt_half_to_float", "srt_unet_host",
-                   "srt_unet_device", "srt_separate_batch", "srt_separate_device", "srt_stft_rows",
+                   "srt_unet_device", "srt_separate_batch", "srt_separate_batch_async", "srt_batch_wait",
+                   "srt_separate_device", "srt_stft_rows",
                    "srt_stft_host", "srt_istft_host", "srt_launch_count", "srt_last_timing", "srt_set_timing",
                    "srt_debug_tensor", "srt_host_alloc", "srt_host_free", "srt_synchronize",
                    "srt_stream_create", "srt_stream_process", "srt_stream_destroy", "srt_stream_launch_count"],
@@ -61,6 +62,8 @@ def load_library():
     lib.srt_unet_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.srt_separate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.srt_separate_device.argtypes = lib.srt_separate_batch.argtypes
+    lib.srt_separate_batch_async.argtypes = lib.srt_separate_batch.argtypes + [C.POINTER(C.c_int)]
+    lib.srt_batch_wait.argtypes = [C.c_void_p, C.c_int]
     lib.srt_stft_rows.restype = C.c_size_t
     lib.srt_stft_rows.argtypes = [C.c_size_t]
     lib.srt_stft_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
@@ -191,9 +194,37 @@ class Separator:
         self._check(self.lib.srt_separate_batch(self.h, pl, pr, n, ns, uw, po))
         return outs
 
+    def separate_async(self, streams, unaffected=None):
+        """Like separate(), but only enqueues the batch (srt_separate_batch_async).  Returns a pending handle;
+        result(handle) waits and returns the stems.  Up to three batches are in flight per Separator; a fourth submit first drains the oldest."""
+        ns = len(streams)
+        Ls = [np.ascontiguousarray(l, np.float32) for l, _ in streams]
+        Rs = [np.ascontiguousarray(r, np.float32) for _, r in streams]
+        n = (C.c_size_t * ns)(*[l.size for l in Ls])
+        pl = (C.c_void_p * ns)(*[l.ctypes.data for l in Ls])
+        pr = (C.c_void_p * ns)(*[r.ctypes.data for r in Rs])
+        outs = [np.empty((self.S, 2, l.size), np.float32) for l in Ls]
+        po = (C.c_void_p * (ns * self.S * 2))(*[o[s, c].ctypes.data for o in outs for s in range(self.S) for c in range(2)])
+        uw = (C.c_float * self.S)(*[float(u) for u in unaffected]) if unaffected is not None else None
+        ticket = self.separate_raw_async(pl, pr, n, ns, uw, po)
+        return {"ticket": ticket, "outs": outs, "keepalive": (Ls, Rs, n, pl, pr, po, uw)}
+
+    def result(self, pending):
+        self.wait(pending["ticket"])
+        return pending["outs"]
+
     def separate_raw(self, pl, pr, n, ns, uw, po, device=False):
         fn = self.lib.srt_separate_device if device else self.lib.srt_separate_batch
         self._check(fn(self.h, pl, pr, n, ns, uw, po))
+
+    def separate_raw_async(self, pl, pr, n, ns, uw, po):
+        """Enqueue one host-pointer batch (srt_separate_batch_async); returns the ticket for wait()."""
+        ticket = C.c_int(-1)
+        self._check(self.lib.srt_separate_batch_async(self.h, pl, pr, n, ns, uw, po, C.byref(ticket)))
+        return ticket.value
+
+    def wait(self, ticket):
+        self._check(self.lib.srt_batch_wait(self.h, ticket))
 
     # ---- transforms -----------------------------------------------------------------------
     def stft(self, L, R):

@@ -89,6 +89,10 @@ struct Span {
     cudaEvent_t a, b;
 };
 
+constexpr int kMetaSlots = 16;    // per-call metadata ring
+constexpr int kTicketMod = 3 << 28;   // tickets wrap here (multiple of kBatchSlots)
+constexpr int kBatchSlots = 3;    // host-pointer batches in flight (upload of k+1 | kernels of k | download of k-1)
+
 struct srt_ctx {
     srt_config cfg{};
     int S = 0, T = 0, F = 0, B = 0, NB = 0;   // B = U-Net batch capacity, NB = batch images capacity
@@ -122,15 +126,23 @@ struct srt_ctx {
     float* d_mask = nullptr;      // [S][NB][T][F][2]
     float2* d_frames = nullptr;   // [max(S,1)][B][T][4096]
     // per-call metadata (device + pinned host mirror)
-    // a ring of 4 slots so back-to-back calls never wait on the host for the previous call
-    uint8_t *d_meta_base = nullptr, *h_meta_base = nullptr;
+    // a ring of kMetaSlots slots so back-to-back (and in-flight asynchronous) calls never wait on the host
+    uint8_t *d_meta_base = nullptr, *h_meta_base = nullptr, *h_meta_dev = nullptr;   // h_meta_dev: device view of the pinned mirror
     uint8_t *d_meta = nullptr, *h_meta = nullptr;   // current slot
     size_t meta_cap = 0;                            // bytes per slot
-    cudaEvent_t meta_ev[4]{};
+    cudaEvent_t meta_ev[kMetaSlots]{};
     int meta_slot = 0;
-    // staging for the host-pointer API
+    // staging for the host-pointer transform helpers (srt_stft_host / srt_istft_host)
     float *d_pcm = nullptr, *d_out = nullptr;
     size_t pcm_cap = 0, out_cap = 0;
+    // staging for srt_separate_batch[_async]: three slots, so batch k+1 uploads while batch k computes and
+    // batch k-1 is still being copied back
+    float *d_bpcm[kBatchSlots]{}, *d_bout[kBatchSlots]{};
+    size_t bpcm_cap[kBatchSlots]{}, bout_cap[kBatchSlots]{};
+    cudaEvent_t ev_cdone[kBatchSlots]{}, ev_d2h[kBatchSlots]{};   // last compute / last D2H that used the slot
+    bool slot_busy[kBatchSlots]{};
+    int slot_ticket[kBatchSlots]{};                               // ticket of the batch that owns the slot
+    long long batch_seq = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer API (H2D / D2H overlap compute)
     cudaEvent_t ev_in[8]{}, ev_c[8]{};
     // bookkeeping
@@ -215,10 +227,18 @@ extern "C" void srt_destroy(srt_ctx* c)
     for (void* p : c->allocs) cudaFree(p);
     if (c->d_meta_base) cudaFree(c->d_meta_base);
     if (c->h_meta_base) cudaFreeHost(c->h_meta_base);
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < kMetaSlots; i++)
         if (c->meta_ev[i]) cudaEventDestroy(c->meta_ev[i]);
+    if (c->s_in) cudaStreamSynchronize(c->s_in);
+    if (c->s_out) cudaStreamSynchronize(c->s_out);
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_out) cudaFree(c->d_out);
+    for (int i = 0; i < kBatchSlots; i++) {
+        if (c->d_bpcm[i]) cudaFree(c->d_bpcm[i]);
+        if (c->d_bout[i]) cudaFree(c->d_bout[i]);
+        if (c->ev_cdone[i]) cudaEventDestroy(c->ev_cdone[i]);
+        if (c->ev_d2h[i]) cudaEventDestroy(c->ev_d2h[i]);
+    }
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -686,7 +706,7 @@ struct BatchMeta {
 static size_t padded_len(size_t n) { return (size_t)kFFT * ((n + kFFT - 1) / kFFT) + 2 * kFFT; }   // main.c:762-763
 
 // Picks the next metadata slot (device block + pinned host mirror).  Waits only if that slot's
-// previous upload, four calls ago, has not been consumed yet.
+// previous upload, kMetaSlots calls ago, has not been consumed yet.
 static int ensure_meta(srt_ctx* c, size_t bytes)
 {
     if (bytes > c->meta_cap) {
@@ -694,20 +714,31 @@ static int ensure_meta(srt_ctx* c, size_t bytes)
         if (c->d_meta_base) cudaFree(c->d_meta_base);
         if (c->h_meta_base) cudaFreeHost(c->h_meta_base);
         c->meta_cap = (bytes * 2 + 4095) & ~(size_t)4095;
-        CK(cudaMalloc((void**)&c->d_meta_base, c->meta_cap * 4));
-        CK(cudaMallocHost((void**)&c->h_meta_base, c->meta_cap * 4));
-        for (int i = 0; i < 4; i++)
+        CK(cudaMalloc((void**)&c->d_meta_base, c->meta_cap * kMetaSlots));
+        CK(cudaHostAlloc((void**)&c->h_meta_base, c->meta_cap * kMetaSlots, cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer((void**)&c->h_meta_dev, c->h_meta_base, 0));
+        for (int i = 0; i < kMetaSlots; i++)
             if (!c->meta_ev[i]) CK(cudaEventCreateWithFlags(&c->meta_ev[i], cudaEventDisableTiming));
     }
-    c->meta_slot = (c->meta_slot + 1) & 3;
+    c->meta_slot = (c->meta_slot + 1) % kMetaSlots;
     CK(cudaEventSynchronize(c->meta_ev[c->meta_slot]));
     c->d_meta = c->d_meta_base + (size_t)c->meta_slot * c->meta_cap;
     c->h_meta = c->h_meta_base + (size_t)c->meta_slot * c->meta_cap;
     return 0;
 }
+// The metadata block goes up with a one-CTA kernel that reads the mapped pinned mirror, not with a memcpy: a
+// copy-engine transfer on the compute stream queues behind the bulk PCM uploads of the next batches (one merged
+// DMA of ~100 MB takes 2-3 ms) and stalled the first kernel of every batch (tools/e2e_probe.py, r1).
+__global__ void meta_upload_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n16)
+{
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+}
 static int commit_meta(srt_ctx* c, size_t bytes)
 {
-    CK(cudaMemcpyAsync(c->d_meta, c->h_meta, bytes, cudaMemcpyHostToDevice, c->stream));
+    const size_t slot_off = (size_t)c->meta_slot * c->meta_cap;
+    meta_upload_kernel<<<1, 256, 0, c->stream>>>((const uint4*)(c->h_meta_dev + slot_off), (uint4*)c->d_meta, (int)((bytes + 15) / 16));
+    CK(cudaGetLastError());
+    c->launches++;
     CK(cudaEventRecord(c->meta_ev[c->meta_slot], c->stream));
     return 0;
 }
@@ -833,39 +864,16 @@ extern "C" int srt_separate_device(srt_ctx* c, const float* const* d_pcmL, const
     return separate_core(c, d_pcmL, d_pcmR, n_samples, n_streams, unaffected, d_stems_out, kFFT);
 }
 
-extern "C" int srt_separate_batch(srt_ctx* c, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
-                                  int n_streams, const float* unaffected, float* const* stems_out)
+// Enqueues one host-pointer batch into staging slot `slot`: H2D on s_in, compute on the context's stream,
+// D2H on s_out, software-pipelined over groups of streams (PCIe is full duplex; the copies would
+// otherwise serialise with the kernels).  Returns without waiting; ev_d2h[slot] marks completion.
+// Hazards across in-flight batches (kBatchSlots = 3):
+//   H2D into d_bpcm[slot]  waits for the compute that last read it        (ev_cdone[slot])
+//   compute into d_bout[slot] waits for the D2H that last read it         (ev_d2h[slot])
+// everything else (spectra, activations, masks) lives on the context's stream and is ordered by it.
+static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
+                         int n_streams, const float* unaffected, float* const* stems_out)
 {
-    if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
-    if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
-    CK(cudaSetDevice(c->cfg.device));
-    reset_spans(c);
-    size_t tot = 0;
-    for (int i = 0; i < n_streams; i++) tot += (n_samples[i] + 3) & ~(size_t)3;
-    if (tot * 2 > c->pcm_cap) {
-        CK(cudaStreamSynchronize(c->stream));
-        if (c->d_pcm) cudaFree(c->d_pcm);
-        c->pcm_cap = tot * 2;
-        CK(cudaMalloc((void**)&c->d_pcm, c->pcm_cap * 4));
-    }
-    if (tot * 2 * c->S > c->out_cap) {
-        CK(cudaStreamSynchronize(c->stream));
-        if (c->d_out) cudaFree(c->d_out);
-        c->out_cap = tot * 2 * c->S;
-        CK(cudaMalloc((void**)&c->d_out, c->out_cap * 4));
-    }
-    std::vector<const float*> dl(n_streams), dr(n_streams);
-    std::vector<float*> dout((size_t)n_streams * c->S * 2);
-    size_t off = 0;
-    for (int i = 0; i < n_streams; i++) {
-        const size_t np = (n_samples[i] + 3) & ~(size_t)3;
-        dl[i] = c->d_pcm + off * 2;
-        dr[i] = c->d_pcm + off * 2 + np;
-        for (int q = 0; q < c->S * 2; q++) dout[(size_t)i * c->S * 2 + q] = c->d_out + off * 2 * c->S + (size_t)q * np;
-        off += np;
-    }
-    // Software pipeline over groups of streams: H2D of group g+1 and D2H of group g-1 run on their own
-    // streams while group g computes (PCIe is full duplex; the copies would otherwise serialise with the kernels).
     if (!c->s_in) {
         CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -873,20 +881,81 @@ extern "C" int srt_separate_batch(srt_ctx* c, const float* const* pcmL, const fl
             CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_c[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < kBatchSlots; i++) {
+            CK(cudaEventCreateWithFlags(&c->ev_cdone[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+        }
     }
+    size_t tot = 0;
+    for (int i = 0; i < n_streams; i++) tot += (n_samples[i] + 3) & ~(size_t)3;
+    if (tot * 2 > c->bpcm_cap[slot]) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->s_in));
+        if (c->d_bpcm[slot]) cudaFree(c->d_bpcm[slot]);
+        c->bpcm_cap[slot] = tot * 2;
+        CK(cudaMalloc((void**)&c->d_bpcm[slot], c->bpcm_cap[slot] * 4));
+    }
+    if (tot * 2 * c->S > c->bout_cap[slot]) {
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->s_out));
+        if (c->d_bout[slot]) cudaFree(c->d_bout[slot]);
+        c->bout_cap[slot] = tot * 2 * c->S;
+        CK(cudaMalloc((void**)&c->d_bout[slot], c->bout_cap[slot] * 4));
+    }
+    float* const d_pcm = c->d_bpcm[slot];
+    float* const d_out = c->d_bout[slot];
+    std::vector<const float*> dl(n_streams), dr(n_streams);
+    std::vector<float*> dout((size_t)n_streams * c->S * 2);
+    size_t off = 0;
+    for (int i = 0; i < n_streams; i++) {
+        const size_t np = (n_samples[i] + 3) & ~(size_t)3;
+        dl[i] = d_pcm + off * 2;
+        dr[i] = d_pcm + off * 2 + np;
+        for (int q = 0; q < c->S * 2; q++) dout[(size_t)i * c->S * 2 + q] = d_out + off * 2 * c->S + (size_t)q * np;
+        off += np;
+    }
+    // Groups shorten the latency of a lone call (the first download starts after 1/groups of the kernels) but
+    // cost batch efficiency; once other batches are in flight the overlap comes from them, so the batch goes
+    // through whole (r1 tools/e2e_probe.py: blocking 18.4 / 14.1 / 12.5 ms and pipelined 9.6 / 9.6 / 10.3 ms per
+    // 32-stream step for 1 / 2 / 4 groups).
+    bool others_in_flight = false;
+    for (int i = 0; i < kBatchSlots; i++)
+        if (i != slot && c->slot_busy[i] && cudaEventQuery(c->ev_d2h[i]) == cudaErrorNotReady) others_in_flight = true;
+    (void)cudaGetLastError();   // cudaErrorNotReady is not sticky, but keep the error state clean
     const char* ge = getenv("SRT_E2E_GROUPS");
-    int groups = ge ? atoi(ge) : 4;
+    int groups = ge ? atoi(ge) : (others_in_flight ? 1 : 4);
     groups = std::max(1, std::min(std::min(groups, 8), n_streams));
     const int per = (n_streams + groups - 1) / groups;
-    // the context's stream may still own the staging buffers from a previous device-API call
-    CK(cudaEventRecord(c->ev_c[0], c->stream));
-    CK(cudaStreamWaitEvent(c->s_in, c->ev_c[0], 0));
+    CK(cudaStreamWaitEvent(c->s_in, c->ev_cdone[slot], 0));     // no-op until the slot has been used once
+    CK(cudaStreamWaitEvent(c->stream, c->ev_d2h[slot], 0));
+    // Copies whose source and destination both continue the previous one are merged: a caller that keeps its
+    // streams (and stems) back to back in one pinned allocation gets one DMA per group instead of one per
+    // channel (55 vs 49.5 GB/s D2H on the bench box, profiles/r1_pcie_probe.json).
+    struct Run {
+        char* dst; const char* src; size_t bytes;
+    };
+    auto flush = [](std::vector<Run>& runs, cudaMemcpyKind kind, cudaStream_t st) -> cudaError_t {
+        for (const Run& r : runs) {
+            cudaError_t e = cudaMemcpyAsync(r.dst, r.src, r.bytes, kind, st);
+            if (e != cudaSuccess) return e;
+        }
+        runs.clear();
+        return cudaSuccess;
+    };
+    auto add = [](std::vector<Run>& runs, void* dst, const void* src, size_t bytes) {
+        if (!runs.empty() && runs.back().dst + runs.back().bytes == (char*)dst && runs.back().src + runs.back().bytes == (const char*)src)
+            runs.back().bytes += bytes;
+        else
+            runs.push_back(Run{(char*)dst, (const char*)src, bytes});
+    };
+    std::vector<Run> runs;
     for (int g = 0; g < groups; g++) {
         const int i0 = g * per, i1 = std::min(n_streams, i0 + per);
         for (int i = i0; i < i1; i++) {
-            CK(cudaMemcpyAsync((void*)dl[i], pcmL[i], n_samples[i] * 4, cudaMemcpyHostToDevice, c->s_in));
-            CK(cudaMemcpyAsync((void*)dr[i], pcmR[i], n_samples[i] * 4, cudaMemcpyHostToDevice, c->s_in));
+            add(runs, (void*)dl[i], pcmL[i], n_samples[i] * 4);
+            add(runs, (void*)dr[i], pcmR[i], n_samples[i] * 4);
         }
+        CK(flush(runs, cudaMemcpyHostToDevice, c->s_in));
         CK(cudaEventRecord(c->ev_in[g], c->s_in));
     }
     for (int g = 0; g < groups; g++) {
@@ -899,9 +968,64 @@ extern "C" int srt_separate_batch(srt_ctx* c, const float* const* pcmL, const fl
         CK(cudaStreamWaitEvent(c->s_out, c->ev_c[g], 0));
         for (int i = i0; i < i1; i++)
             for (int q = 0; q < c->S * 2; q++)
-                CK(cudaMemcpyAsync(stems_out[(size_t)i * c->S * 2 + q], dout[(size_t)i * c->S * 2 + q], n_samples[i] * 4, cudaMemcpyDeviceToHost, c->s_out));
+                add(runs, stems_out[(size_t)i * c->S * 2 + q], dout[(size_t)i * c->S * 2 + q], n_samples[i] * 4);
+        CK(flush(runs, cudaMemcpyDeviceToHost, c->s_out));
     }
-    CK(cudaStreamSynchronize(c->s_out));
+    CK(cudaEventRecord(c->ev_cdone[slot], c->stream));
+    CK(cudaEventRecord(c->ev_d2h[slot], c->s_out));
+    c->slot_busy[slot] = true;
+    return 0;
+}
+
+static int batch_wait_slot(srt_ctx* c, int slot)
+{
+    if (!c->slot_busy[slot]) return 0;
+    CK(cudaEventSynchronize(c->ev_d2h[slot]));
+    c->slot_busy[slot] = false;
+    return 0;
+}
+
+extern "C" int srt_separate_batch_async(srt_ctx* c, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
+                                        int n_streams, const float* unaffected, float* const* stems_out, int* ticket_out)
+{
+    if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
+    if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
+    if (!ticket_out) return fail(SRT_ERR_ARG, "ticket_out is NULL");
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    const int slot = (int)(c->batch_seq % kBatchSlots);
+    int r = batch_wait_slot(c, slot);   // one batch too many in flight: the slot's previous owner must have drained
+    if (r) return r;
+    if ((r = batch_enqueue(c, slot, pcmL, pcmR, n_samples, n_streams, unaffected, stems_out))) {
+        // leave nothing half-enqueued behind an error return
+        cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out);
+        return r;
+    }
+    const int ticket = (int)(c->batch_seq % kTicketMod);   // kTicketMod is a multiple of kBatchSlots: ticket % slots == slot
+    c->slot_ticket[slot] = ticket;
+    c->batch_seq++;
+    *ticket_out = ticket;
+    return 0;
+}
+
+extern "C" int srt_batch_wait(srt_ctx* c, int ticket)
+{
+    if (!c) return fail(SRT_ERR_STATE, "null context");
+    const long long age = ((c->batch_seq % kTicketMod) - 1 - ticket + kTicketMod) % kTicketMod;   // 0 = newest batch
+    if (ticket < 0 || ticket >= kTicketMod || c->batch_seq == 0 || age >= c->batch_seq) return fail(SRT_ERR_ARG, "bad ticket %d", ticket);
+    CK(cudaSetDevice(c->cfg.device));
+    const int slot = ticket % kBatchSlots;
+    if (c->slot_ticket[slot] != ticket) return 0;   // an older batch: drained when its slot was handed on
+    return batch_wait_slot(c, slot);
+}
+
+extern "C" int srt_separate_batch(srt_ctx* c, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
+                                  int n_streams, const float* unaffected, float* const* stems_out)
+{
+    int ticket = -1;
+    int r = srt_separate_batch_async(c, pcmL, pcmR, n_samples, n_streams, unaffected, stems_out, &ticket);
+    if (r) return r;
+    if ((r = srt_batch_wait(c, ticket))) return r;
     CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -1046,6 +1170,10 @@ extern "C" int srt_synchronize(srt_ctx* c)
 {
     if (!c) return SRT_ERR_STATE;
     CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < kBatchSlots; i++) {
+        int r = batch_wait_slot(c, i);
+        if (r) return r;
+    }
     return 0;
 }
 extern "C" void* srt_host_alloc(size_t bytes)

@@ -65,43 +65,47 @@ __device__ __forceinline__ void twiddle_powers(float2* v, float2 w)
     for (int r = 1; r < 16; r++) v[r] = cmul(v[r], p[r]);
 }
 
-// 4096-point forward FFT.  In: v[r] = x[j + 256 r].  Out: v[r] = X[j + 256 r].
-__device__ __forceinline__ void fft4096(float2* v, float* sre, float* sim, const float2* __restrict__ tw, int j)
+// Shared-memory state of one transform: the padded exchange buffer (complex, so each exchange is one 64-bit
+// access per point; every pattern below touches 16 consecutive float2 per half-warp -> conflict-free) and the
+// pass-2 twiddles.  Pass 2 needs w^r with w = W4096^(16 (j & 15)): only 16 x 15 distinct values, kept as a
+// [r][j & 15] table (one conflict-free LDS.64 per factor instead of the power chain).
+struct FftSmem {
+    float2 x[kPadLen];
+    float2 tw2[16 * 16];
+};
+
+// Fills the pass-2 table.  Call once per CTA, before the first fft4096 (any barrier inside it publishes the table).
+__device__ __forceinline__ void fft_smem_init(FftSmem& sm, const float2* __restrict__ tw, int j)
 {
+    const int r = j >> 4, jj = j & 15;
+    sm.tw2[j] = __ldg(&tw[(jj * r * 16) & (kFFT - 1)]);
+}
+
+// 4096-point forward FFT.  In: v[r] = x[j + 256 r].  Out: v[r] = X[j + 256 r].
+__device__ __forceinline__ void fft4096(float2* v, FftSmem& sm, const float2* __restrict__ tw, int j)
+{
+    float2* sx = sm.x;
     // pass 1 (Ns = 1)
     fft16(v);
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const int i = 17 * j + r;   // pad_idx(16 j + r)
-        sre[i] = v[r].x;
-        sim[i] = v[r].y;
-    }
+    for (int r = 0; r < 16; r++) sx[17 * j + r] = v[r];   // pad_idx(16 j + r)
     __syncthreads();
     // pass 2 (Ns = 16)
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const int i = pad_idx(j + 256 * r);
-        v[r] = make_float2(sre[i], sim[i]);
-    }
-    twiddle_powers(v, __ldg(&tw[(j & 15) * 16]));
+    for (int r = 0; r < 16; r++) v[r] = sx[pad_idx(j + 256 * r)];
+#pragma unroll
+    for (int r = 1; r < 16; r++) v[r] = cmul(v[r], sm.tw2[r * 16 + (j & 15)]);
     fft16(v);
     __syncthreads();
     {
         const int base = (j >> 4) * 256 + (j & 15);
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-            const int i = pad_idx(base + 16 * r);
-            sre[i] = v[r].x;
-            sim[i] = v[r].y;
-        }
+        for (int r = 0; r < 16; r++) sx[pad_idx(base + 16 * r)] = v[r];
     }
     __syncthreads();
     // pass 3 (Ns = 256)
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const int i = pad_idx(j + 256 * r);
-        v[r] = make_float2(sre[i], sim[i]);
-    }
+    for (int r = 0; r < 16; r++) v[r] = sx[pad_idx(j + 256 * r)];
     twiddle_powers(v, __ldg(&tw[j]));
     fft16(v);
 }

@@ -21,7 +21,7 @@ namespace srt {
 // =========================================================================================
 __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
 {
-    __shared__ float sre[kPadLen], sim[kPadLen];
+    __shared__ FftSmem sm;
     const int img = blockIdx.x / p.T, t = blockIdx.x % p.T;
     const ImgDesc d = p.imgs[img];
     const int f = d.f0 + t;
@@ -55,19 +55,16 @@ __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
         }
         v[r] = x;
     }
-    fft4096(v, sre, sim, p.twiddle, j);
+    fft_smem_init(sm, p.twiddle, j);
+    fft4096(v, sm, p.twiddle, j);
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const int i = pad_idx(j + 256 * r);
-        sre[i] = v[r].x;
-        sim[i] = v[r].y;
-    }
+    for (int r = 0; r < 16; r++) sm.x[pad_idx(j + 256 * r)] = v[r];
     __syncthreads();
     // Z = FFT(l + i r):  XL[k] = (Z[k] + conj Z[N-k]) / 2,  XR[k] = (Z[k] - conj Z[N-k]) / (2i)
     for (int k = j; k < kBins; k += kFftThreads) {
-        const int ia = pad_idx(k), ib = pad_idx((kFFT - k) & (kFFT - 1));
-        const float ar = sre[ia], ai = sim[ia], br = sre[ib], bi = sim[ib];
+        const float2 za = sm.x[pad_idx(k)], zb = sm.x[pad_idx((kFFT - k) & (kFFT - 1))];
+        const float ar = za.x, ai = za.y, br = zb.x, bi = zb.y;
         float4 o;
         o.x = 0.5f * (ar + br);          // Re XL
         o.y = -0.5f * (ai - bi);         // -Im XL   (reference stores the conjugate)
@@ -98,7 +95,7 @@ void launch_stft(const StftParams& p, cudaStream_t st)
 // =========================================================================================
 __global__ void __launch_bounds__(kFftThreads, 4) istft_kernel(const IstftParams p)
 {
-    __shared__ float sre[kPadLen], sim[kPadLen];
+    __shared__ FftSmem sm;
     const int li = blockIdx.x / p.T, t = blockIdx.x % p.T;
     const int img = p.img_first + li;
     const int s = blockIdx.y;
@@ -128,7 +125,8 @@ __global__ void __launch_bounds__(kFftThreads, 4) istft_kernel(const IstftParams
         else z = make_float2(xlr + xri, -xli + xrr);                      // conj(XL) + i conj(XR)
         v[r] = make_float2(z.x, -z.y);                                    // conj(Z): inverse via forward FFT
     }
-    fft4096(v, sre, sim, p.twiddle, j);
+    fft_smem_init(sm, p.twiddle, j);
+    fft4096(v, sm, p.twiddle, j);
     float2* out = p.frames_out + (((size_t)s * p.frames_stem_stride + li) * p.T + t) * kFFT;
 #pragma unroll
     for (int r = 0; r < 16; r++) {
@@ -154,10 +152,9 @@ void launch_istft(const IstftParams& p, cudaStream_t st)
 // =========================================================================================
 __global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOlaParams p)
 {
-    extern __shared__ float ola_smem[];
-    float* sre = ola_smem;
-    float* sim = ola_smem + kPadLen;
-    float2* ring = reinterpret_cast<float2*>(ola_smem + 2 * kPadLen);
+    extern __shared__ __align__(16) unsigned char ola_smem[];
+    FftSmem& sm = *reinterpret_cast<FftSmem*>(ola_smem);
+    float2* ring = reinterpret_cast<float2*>(ola_smem + sizeof(FftSmem));
     const int st = p.stream_first + blockIdx.z, s = blockIdx.y;
     const int nfr = p.n_frames[st];
     const int h0 = blockIdx.x * p.hops_per_cta;
@@ -169,6 +166,7 @@ __global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOl
     float* outR = p.out[(size_t)st * p.S * 2 + s * 2 + 1];
     const float uw = p.unaffected[s];
     for (int i = j; i < kFFT; i += kFftThreads) ring[i] = make_float2(0.f, 0.f);
+    fft_smem_init(sm, p.twiddle, j);
     __syncthreads();
     const long lo = (long)h0 * kHop, hi = (long)h1 * kHop;
     for (int f = max(h0 - 3, 0); f < h1; f++) {
@@ -189,7 +187,7 @@ __global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOl
             else z = make_float2(xlr + xri, -xli + xrr);
             v[r] = make_float2(z.x, -z.y);
         }
-        fft4096(v, sre, sim, p.twiddle, j);
+        fft4096(v, sm, p.twiddle, j);
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             const int i = j + 256 * r;
@@ -220,7 +218,7 @@ __global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOl
 void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cudaStream_t st)
 {
     if (n_streams == 0 || max_frames == 0) return;
-    const size_t smem = (2 * kPadLen + 2 * kFFT) * sizeof(float);
+    const size_t smem = sizeof(FftSmem) + (size_t)kFFT * sizeof(float2);
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -50,10 +50,11 @@ struct HopParams {
 
 __global__ void __launch_bounds__(kFftThreads) stream_hop_kernel(const HopParams p)
 {
-    __shared__ float sre[kPadLen], sim[kPadLen];
+    __shared__ FftSmem sm;
     const int j = threadIdx.x;
     const int role = blockIdx.x;
     float2 v[16];
+    fft_smem_init(sm, p.twiddle, j);
     if (role == p.S) {
         // ---- analysis of the newest frame (Spleeter4Stems.c:261-267, 322-349) --------------------
 #pragma unroll
@@ -63,18 +64,14 @@ __global__ void __launch_bounds__(kFftThreads) stream_hop_kernel(const HopParams
             const float w = __ldg(&p.awin[i]);
             v[r] = make_float2(p.ring[k] * w, p.ring[kFFT + k] * w);
         }
-        fft4096(v, sre, sim, p.twiddle, j);
+        fft4096(v, sm, p.twiddle, j);
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-            const int i = pad_idx(j + 256 * r);
-            sre[i] = v[r].x;
-            sim[i] = v[r].y;
-        }
+        for (int r = 0; r < 16; r++) sm.x[pad_idx(j + 256 * r)] = v[r];
         __syncthreads();
         for (int k = j; k < kBins; k += kFftThreads) {
-            const int ia = pad_idx(k), ib = pad_idx((kFFT - k) & (kFFT - 1));
-            const float ar = sre[ia], ai = sim[ia], br = sre[ib], bi = sim[ib];
+            const float2 za = sm.x[pad_idx(k)], zb = sm.x[pad_idx((kFFT - k) & (kFFT - 1))];
+            const float ar = za.x, ai = za.y, br = zb.x, bi = zb.y;
             float4 o;
             o.x = 0.5f * (ar + br);
             o.y = -0.5f * (ai - bi);
@@ -109,7 +106,7 @@ __global__ void __launch_bounds__(kFftThreads) stream_hop_kernel(const HopParams
         else z = make_float2(xlr + xri, -xli + xrr);
         v[r] = make_float2(z.x, -z.y);
     }
-    fft4096(v, sre, sim, p.twiddle, j);
+    fft4096(v, sm, p.twiddle, j);
     // keep samples 2048..4095 (SAMPLESHIFT), synthesis window, 50 % overlap-add (:303-320)
 #pragma unroll
     for (int r = 8; r < 16; r++) {

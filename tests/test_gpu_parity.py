@@ -194,6 +194,26 @@ def test_separate_ragged_batch_chunked(srt, oracle, small_nets):
     sep.close()
 
 
+def test_async_batches_in_flight_match_blocking_call(srt, oracle, small_nets):
+    """srt_separate_batch_async: four different batches submitted back to back (three staging slots, the
+    fourth submit drains the first) give bit-identical stems to the blocking call, in any wait order."""
+    T, F = 64, 256
+    sep = srt.Separator(small_nets[:2], T, F, max_images=2, max_batch_images=4)
+    batches = [[tuple(x[:n] for x in oracle.synth_pcm(10 * b + i, n=50000)) for i, n in enumerate(lens)]
+               for b, lens in enumerate([(30000, 50000), (8192,), (41000, 4100, 12345), (20480, 20480)])]
+    want = [sep.separate(b, unaffected=[0.25, 0.25]) for b in batches]
+    pend = [sep.separate_async(b, unaffected=[0.25, 0.25]) for b in batches]
+    for k in (2, 0, 3, 1):
+        got = sep.result(pend[k])
+        for g, w in zip(got, want[k]):
+            assert np.array_equal(g, w)
+    ref = oracle.separate(small_nets[:2], *batches[1][0], T, F, unaffected=0.25)
+    assert rms(want[1][0] - ref) < 1e-4
+    with pytest.raises(srt.SrtError):
+        sep.wait(10 ** 6)      # never issued
+    sep.close()
+
+
 def test_unity_mask_is_identity_full_size(srt, oracle):
     """Size-independent property at benchmark shape (T=512, F=1024, 10 s): all-zero weights with
     a +100 head bias give mask == 1, so every stem reproduces the input (SURVEY §4 'VST stream' pin)."""
