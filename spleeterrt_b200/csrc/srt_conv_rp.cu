@@ -39,7 +39,7 @@ struct RpHeader {
 };
 
 template <int N, int R, int WS, int KB>
-constexpr size_t rp_smem_bytes() { return sizeof(RpHeader) + 1024 + (size_t)2 * (R + 2) * kPatchW * KB * 4 + (size_t)WS * N * KB * 4; }
+constexpr size_t rp_smem_bytes() { return sizeof(RpHeader) + 1024 + (size_t)2 * (R + 2) * kPatchW * KB * 4 + (size_t)WS * N * KB * 4 + 8 * 2048; }   // + per-warp store staging
 
 struct RpTile {
     int s, n, x0, y0;
@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
     constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128 : 2 * kAccCols <= 256 ? 256 : 512;
     static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
     uint8_t* wring = patch + 2 * kPatchBytes;
+    float4* stage_all = reinterpret_cast<float4*>(wring + (size_t)WS * kWBytes);   // 8 epilogue warps x 2 KB (store16_warp)
     const uint32_t wring_base = patch_base + 2 * kPatchBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,12 +211,13 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 for (int c0 = half * kHalfCols; c0 < (half + 1) * kHalfCols && c0 < N; c0 += 16) {
                     float v[16];
                     ptx::tmem_ld16(acc + (uint32_t)(r * N + c0), v);
-                    if (valid && !(p.dbg & 1)) {
+                    if (!(p.dbg & 1)) {   // warp-uniform: the stores are warp-cooperative
+                        float4* stage = stage_all + warp * 128;
                         if (p.stems_per_tile > 1 || p.stem0 > 0) {   // down1: the column selects the stem (its own output image)
                             const int se = p.stem0 + c0 / p.ep.cout;
-                            epilogue16(p.ep, se, se * p.ep.B + tl.n, Y, X, 0, c0 % p.ep.cout, v);
-                        } else if (p.ep.mode == 2) epilogue16(p.ep, tl.s, tl.n, Y, X, c0 / p.ep.cout, c0 % p.ep.cout, v);
-                        else epilogue16(p.ep, tl.s, tl.n, Y, X, 0, c0, v);
+                            epilogue16(p.ep, se, se * p.ep.B + tl.n, Y, X, 0, c0 % p.ep.cout, v, stage, valid);
+                        } else if (p.ep.mode == 2) epilogue16(p.ep, tl.s, tl.n, Y, X, c0 / p.ep.cout, c0 % p.ep.cout, v, stage, valid);
+                        else epilogue16(p.ep, tl.s, tl.n, Y, X, 0, c0, v, stage, valid);
                     }
                 }
             }
@@ -256,9 +258,9 @@ void launch_conv_rp(const RowConvParams& p, cudaStream_t st)
         if (p.N == 64 && p.R == 4) launch_rp<64, 4, 9, 8>(p, st);
         else if (p.N == 32 && p.R == 4) launch_rp<32, 4, 9, 8>(p, st);
         else if (p.N == 16 && p.R == 4) launch_rp<16, 4, 9, 8>(p, st);
-    } else if (p.N == 32 && p.R == 3) launch_rp<32, 3, 12, 32>(p, st);
-    else if (p.N == 64 && p.R == 3) launch_rp<64, 3, 6, 32>(p, st);
-    else if (p.N == 128 && p.R == 2) launch_rp<128, 2, 5, 32>(p, st);
+    } else if (p.N == 32 && p.R == 3) launch_rp<32, 3, 8, 32>(p, st);
+    else if (p.N == 64 && p.R == 3) launch_rp<64, 3, 4, 32>(p, st);
+    else if (p.N == 128 && p.R == 2) launch_rp<128, 2, 4, 32>(p, st);
 }
 
 }  // namespace srt

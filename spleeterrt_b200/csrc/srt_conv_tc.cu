@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         for (int c0 = half * kHalfCols; c0 < (half + 1) * kHalfCols && c0 < N_TILE; c0 += 16) {
             float v[16];
             ptx::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (valid) epilogue16(p, s, n, Y, X, phase, nt * N_TILE + c0, v);
+            // tmem_full means every MMA has finished reading the stage ring: its first 16 KB become the warps' staging buffers
+            epilogue16(p, s, n, Y, X, phase, nt * N_TILE + c0, v, reinterpret_cast<float4*>(tiles) + warp * 128, valid);
         }
     }
     ptx::tc_fence_before();

@@ -109,6 +109,9 @@ struct srt_ctx {
     float *d_w7 = nullptr, *d_b7 = nullptr;                                            // up7
     std::vector<float> h_w1, h_b1;  // down1 weights [stem][tap][cin][cout] and {bias, scale, offset}
     std::vector<float> h_w6, h_w7;  // up6 / up7 weights, host copies (ride in the kernel parameter bank)
+    Up6TcParams up6tc{};            // tensor-core up6 (srt_up6_tc.cu)
+    bool use_up6tc = false;
+    int sm_count = 148;
     std::vector<LayerPlan> plans;
     std::vector<ConvParams> conv;   // 10 tensor-core layers
     RowConvParams rp[10];           // row-patch form of the small-N layers (down2, down3, up4, up5)
@@ -346,6 +349,48 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         }
         if ((r = upload(c, &c->d_w6, w6)) || (r = upload(c, &c->d_b6, b6)) || (r = upload(c, &c->d_s6, s6)) || (r = upload(c, &c->d_o6, o6))) return r;
         if ((r = upload(c, &c->d_w7, w7)) || (r = upload(c, &c->d_b7, b7))) return r;
+        // ---- tensor-core up6: GEMM + col2im (SRT_UP6_TC=0 keeps the SIMT kernel; conv_impl 1 is the all-SIMT check path)
+        const char* u6e = getenv("SRT_UP6_TC");
+        if (c->cfg.conv_impl != 1 && !(u6e && atoi(u6e) == 0) && S <= 8 && up6_tc_fits(S)) {
+            Up6TcParams& q = c->up6tc;
+            std::memset(&q, 0, sizeof q);
+            bool exact = true;
+            for (float v : w6) exact = exact && round_tf32(v) == v;
+            q.w_terms = exact ? 1 : 2;
+            std::vector<float> wpk((size_t)S * kUp6TcWFloatsPerStem, 0.0f);
+            for (int s = 0; s < S; s++)
+                for (int b = 0; b < 4; b++)
+                    for (int term = 0; term < 2; term++)
+                        for (int tap = 0; tap < 25; tap++)
+                            for (int j = 0; j < 8; j++) {
+                                const int cin = (b >> 1) * 16 + (b & 1) * 8 + j;   // [skip1 | up5] (spleeter.c:289)
+                                wpk[(size_t)s * kUp6TcWFloatsPerStem + (b * 2 + term) * 256 + swz32_index(tap, j)] =
+                                    weight_part(w6[(size_t)s * 800 + cin * 25 + tap], term);
+                            }
+            float* dw;
+            if ((r = upload(c, &dw, wpk))) return r;
+            q.w = dw;
+            q.out = c->U[6];
+            q.T = T; q.F = F; q.B = c->B; q.S = S;
+            const char* pfe = getenv("SRT_UP6_PREFETCH");
+            const char* dbe = getenv("SRT_UP6_DBG");
+            q.prefetch_rows = pfe ? atoi(pfe) : 12;
+            q.dbg = dbe ? atoi(dbe) : 0;
+            const char* ste = getenv("SRT_UP6_STAGES");
+            const char* ace = getenv("SRT_UP6_ACC");
+            q.stages = ste ? std::max(2, std::min(4, atoi(ste))) : 4;
+            q.acc_slots = ace ? std::max(2, std::min(8, atoi(ace))) : 4;
+            const int W = F / 2;
+            q.blocks_x = (W + 125) / 126;
+            q.bw = (W + q.blocks_x - 1) / q.blocks_x;
+            for (int s = 0; s < S; s++) {
+                q.bias[s] = b6[s]; q.bn_scale[s] = s6[s]; q.bn_offset[s] = o6[s];
+                q.act[s] = c->act_dec[s];
+            }
+            if ((r = make_tmap(&q.tmap[0], c->E[1], 16, W, T / 2, S * c->B, 128, 1, 1, 8))) return r;
+            if ((r = make_tmap(&q.tmap[1], c->U[5], 16, W, T / 2, S * c->B, 128, 1, 1, 8))) return r;
+            c->use_up6tc = true;
+        }
     }
     // ---- tensor-core layers
     // Weights that are exactly TF32-representable (the reference's fp16 model) need one MMA term; anything else
@@ -530,6 +575,7 @@ extern "C" int srt_create(const srt_config* cfg, const float* const* coeffs, con
     if (prop.major != 10) return fail(SRT_ERR_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", cfg->device, prop.major, prop.minor);
     srt_ctx* c = new srt_ctx();
     c->cfg = *cfg;
+    c->sm_count = prop.multiProcessorCount;
     c->S = cfg->n_stems;
     c->T = cfg->time_step;
     c->F = cfg->n_stems ? cfg->bin_limit : 0;
@@ -592,7 +638,19 @@ static int run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask
         else launch_conv_tc(p, c->stream);
         c->launches++;
     }
-    {
+    if (c->use_up6tc) {
+        Timed t(c, 11);
+        Up6TcParams& q = c->up6tc;
+        q.Bv = Bv;
+        // row chunks: enough units for ~8 waves of persistent CTAs, chunks no shorter than 32 rows
+        const int H = c->T / 2;
+        int chunks = 1;
+        while (q.blocks_x * chunks * Bv * S < 8 * c->sm_count && H / (chunks * 2) >= 32) chunks *= 2;
+        q.rows_per_unit = (((H + chunks - 1) / chunks) + 1) & ~1;
+        q.chunks = (H + q.rows_per_unit - 1) / q.rows_per_unit;
+        launch_up6_tc(q, c->stream);
+        c->launches++;
+    } else {
         Timed t(c, 11);
         Up6Params p{};
         p.skip = c->E[1]; p.up = c->U[5]; p.w = c->d_w6; p.bias = c->d_b6; p.bn_scale = c->d_s6; p.bn_offset = c->d_o6;
@@ -864,6 +922,8 @@ extern "C" int srt_separate_device(srt_ctx* c, const float* const* d_pcmL, const
     return separate_core(c, d_pcmL, d_pcmR, n_samples, n_streams, unaffected, d_stems_out, kFFT);
 }
 
+static int batch_wait_slot(srt_ctx* c, int slot);
+
 // Enqueues one host-pointer batch into staging slot `slot`: H2D on s_in, compute on the context's stream,
 // D2H on s_out, software-pipelined over groups of streams (PCIe is full duplex; the copies would
 // otherwise serialise with the kernels).  Returns without waiting; ev_d2h[slot] marks completion.
@@ -888,19 +948,29 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
     }
     size_t tot = 0;
     for (int i = 0; i < n_streams; i++) tot += (n_samples[i] + 3) & ~(size_t)3;
-    if (tot * 2 > c->bpcm_cap[slot]) {
+    if (tot * 2 > c->bpcm_cap[slot] || tot * 2 * c->S > c->bout_cap[slot]) {
+        // grow every slot at once, so only the first call of a new size pays for allocation
+        for (int i = 0; i < kBatchSlots; i++) {
+            int r = batch_wait_slot(c, i);
+            if (r) return r;
+        }
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaStreamSynchronize(c->s_in));
-        if (c->d_bpcm[slot]) cudaFree(c->d_bpcm[slot]);
-        c->bpcm_cap[slot] = tot * 2;
-        CK(cudaMalloc((void**)&c->d_bpcm[slot], c->bpcm_cap[slot] * 4));
-    }
-    if (tot * 2 * c->S > c->bout_cap[slot]) {
-        CK(cudaStreamSynchronize(c->stream));
         CK(cudaStreamSynchronize(c->s_out));
-        if (c->d_bout[slot]) cudaFree(c->d_bout[slot]);
-        c->bout_cap[slot] = tot * 2 * c->S;
-        CK(cudaMalloc((void**)&c->d_bout[slot], c->bout_cap[slot] * 4));
+        for (int i = 0; i < kBatchSlots; i++) {
+            if (tot * 2 > c->bpcm_cap[i]) {
+                if (c->d_bpcm[i]) cudaFree(c->d_bpcm[i]);
+                c->d_bpcm[i] = nullptr; c->bpcm_cap[i] = 0;
+                CK(cudaMalloc((void**)&c->d_bpcm[i], tot * 2 * 4));
+                c->bpcm_cap[i] = tot * 2;
+            }
+            if (tot * 2 * c->S > c->bout_cap[i]) {
+                if (c->d_bout[i]) cudaFree(c->d_bout[i]);
+                c->d_bout[i] = nullptr; c->bout_cap[i] = 0;
+                CK(cudaMalloc((void**)&c->d_bout[i], tot * 2 * c->S * 4));
+                c->bout_cap[i] = tot * 2 * c->S;
+            }
+        }
     }
     float* const d_pcm = c->d_bpcm[slot];
     float* const d_out = c->d_bout[slot];

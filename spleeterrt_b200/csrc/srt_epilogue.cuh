@@ -29,6 +29,31 @@ __device__ __forceinline__ void store16(float* dst, const float* v)
     for (int q = 0; q < 4; q++) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+// Warp-cooperative store of one 16-channel chunk per lane (lane = pixel).  A lane's 64 bytes are contiguous in
+// global memory but neighbouring lanes are a whole pixel (>= 64 B, usually >= 128 B) apart, so a plain STG.128
+// touches 32 different lines per instruction: ncu (profiles/r1k) counts 32 sectors per store request and the
+// stage-skip sweep (tools/stage_sweep.py rp) shows the epilogue alone costs as much as all the MMAs of the small-N
+// layers - the LSU, not the math.  Here the chunk is transposed through a 2 KB per-warp shared-memory buffer so
+// that four consecutive lanes write one pixel's 64 bytes: 8 lines per instruction instead of 32.
+//   dst   : this lane's destination (16 floats), or nullptr if the pixel is outside the tensor
+//   stage : 128 float4 of shared memory owned by this warp (XOR-swizzled, conflict-free both ways)
+// All 32 lanes must call it.
+__device__ __forceinline__ void store16_warp(float* dst, const float* v, float4* stage)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < 4; k++) stage[lane * 4 + (k ^ ((lane >> 1) & 3))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = j * 32 + lane, px = i >> 2, piece = i & 3;
+        const float4 t = stage[px * 4 + (piece ^ ((px >> 1) & 3))];
+        float* d = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), px));
+        if (d) *reinterpret_cast<float4*>(d + piece * 4) = t;
+    }
+    __syncwarp();
+}
+
 // Branch-free activations for the tensor-core epilogues.  The epilogue warps are instruction-latency
 // bound (ncu / tools/rp_dbg_sweep.sh: the epilogue, not the MMAs, dominated the small-N layers), so the
 // activation kind is resolved once per 16-channel chunk and ELU uses ex2.approx (__expf): its absolute
@@ -63,7 +88,11 @@ __device__ __forceinline__ void enc16(const float* raw, const float* sc, const f
 }
 
 // v[16]: accumulators for channels [c0, c0+16) of pixel (n, Y, X) in tile space.
-__device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, int Y, int X, int phase, int c0, float* v)
+// stage == nullptr: per-thread stores, callable from divergent code (`valid` must be true; SIMT check kernel).
+// stage != nullptr: warp-cooperative stores through the warp's 2 KB staging buffer; all 32 lanes call, lanes
+// whose pixel is outside the tensor pass valid = false.
+__device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, int Y, int X, int phase, int c0, float* v,
+                                           float4* stage = nullptr, bool valid = true)
 {
     const int act = p.act[s];
     float bias[16];
@@ -76,7 +105,9 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
         else if (act == ACT_RELU) dec16<ACT_RELU>(v, bias, sc, of, p.round_act, o);
         else dec16<ACT_ELU>(v, bias, sc, of, p.round_act, o);
         const int oy = 2 * Y + (phase >> 1), ox = 2 * X + (phase & 1);
-        store16(p.out_dec + (((size_t)n * (2 * p.Hs) + oy) * (2 * p.Ws) + ox) * p.cout + c0, o);
+        float* dst = p.out_dec + (((size_t)n * (2 * p.Hs) + oy) * (2 * p.Ws) + ox) * p.cout + c0;
+        if (stage) store16_warp(valid ? dst : nullptr, o, stage);
+        else store16(dst, o);
         return;
     }
     float raw[16];
@@ -89,13 +120,17 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
         if (act == ACT_ELU_CLAMP) enc16<ACT_ELU_CLAMP>(raw, sc, of, p.round_act, a);
         else if (act == ACT_LEAKY) enc16<ACT_LEAKY>(raw, sc, of, p.round_act, a);
         else enc16<ACT_ELU>(raw, sc, of, p.round_act, a);
-        store16(p.out_act + ((((size_t)n * (p.Hs / 2) + Y / 2) * (p.Ws / 2) + X / 2) * 4 + (Y & 1) * 2 + (X & 1)) * p.cout + c0, a);
+        float* dst = p.out_act + ((((size_t)n * (p.Hs / 2) + Y / 2) * (p.Ws / 2) + X / 2) * 4 + (Y & 1) * 2 + (X & 1)) * p.cout + c0;
+        if (stage) store16_warp(valid ? dst : nullptr, a, stage);
+        else store16(dst, a);
     }
     if (p.round_raw) {
 #pragma unroll
         for (int i = 0; i < 16; i++) raw[i] = ptx::rna_tf32(raw[i]);
     }
-    store16(p.out_raw + (((size_t)n * p.Hs + Y) * p.Ws + X) * p.cout + c0, raw);
+    float* dst = p.out_raw + (((size_t)n * p.Hs + Y) * p.Ws + X) * p.cout + c0;
+    if (stage) store16_warp(valid ? dst : nullptr, raw, stage);
+    else store16(dst, raw);
 }
 
 }  // namespace srt

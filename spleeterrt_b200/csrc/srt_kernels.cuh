@@ -95,6 +95,26 @@ struct Up6Params {                // 5x5 s2 transposed conv 32->1 + act + BN, sp
     float wk[800];                // [32][25] of that stem: FFMA reads them as immediates, no shared-memory traffic
 };
 
+// Tensor-core up6 (srt_up6_tc.cu).  Weights: per stem [box = src*2 + channel half][term: 0 = tf32(w), 1 = tf32(w - tf32(w))]
+// [32 rows = taps (25 used)][8 channels], SWIZZLE_32B pre-swizzled (swz32_index): 8 blocks of 256 floats.
+constexpr int kUp6TcWFloatsPerStem = 8 * 256;
+struct Up6TcParams {
+    CUtensorMap tmap[2];          // skip1, up5: {16, F/2, T/2, S*B}, box {8, 128, 1, 1}, SWIZZLE_32B
+    const float* w;               // [S][kUp6TcWFloatsPerStem]
+    float* out;                   // [S*B][T][F]
+    int T, F, B, Bv, S;
+    int blocks_x, bw;             // column blocks per row and output pixels (input resolution) per block (<= 126)
+    int chunks, rows_per_unit;    // row chunks per image, input rows per chunk (even)
+    int w_terms;                  // 1: weights TF32-exact; 2: also the residual term
+    int prefetch_rows;            // L2 prefetch distance in rows (0 = off)
+    int stages, acc_slots;        // ring depths in use (<= 4 input rows, <= 8 TMEM accumulators)
+    int dbg;                      // SRT_UP6_DBG stage-skip bits (1 gather, 2 MMA, 4 TMA, 8 split): timing experiments only
+    float bias[8], bn_scale[8], bn_offset[8];
+    int act[8];
+};
+void launch_up6_tc(const Up6TcParams& p, cudaStream_t st);
+bool up6_tc_fits(int S);
+
 struct Up7Params {                // 4x4 dilation-2 conv 1->2 + bias + sigmoid, spleeter.c:295-300
     const float* in;              // [S*B][T][F]
     const float* w;               // [S][2][16]

@@ -68,6 +68,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     }
 }
 
+// Warp-collective wait: one lane polls, the rest of the warp parks at the warp barrier.  Measured on B200
+// (tools/stage_sweep.py up6, r1): NOT faster than every lane polling (0.905 vs 0.855 ms) - the hand-off latency of
+// a pipeline stage is not poll traffic.  Kept for experiments.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity)
+{
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
 // ---- TMA ------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc)
 {
@@ -83,6 +92,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* desc, ui
         :
         : "r"(smem_u32(smem_dst)), "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+// Same box, but only pulled into L2 (no shared-memory destination, no barrier): hides HBM latency for a
+// shallow shared-memory ring.
+__device__ __forceinline__ void tma_prefetch_4d(const void* desc, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];\n"
+                 :
+                 : "l"(desc), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
 }
 // 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16).
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)

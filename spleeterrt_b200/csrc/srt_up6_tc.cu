@@ -1,0 +1,275 @@
+// srt_up6_tc.cu — up6 (5x5 stride-2 transposed conv, [skip1 | up5] 32 ch -> 1 ch, + act + BN;
+// Executable/spleeter.c:289-294) as "GEMM, then col2im" on the tensor cores — the reference's own
+// formulation (gemm + col2im_dilated_cpu, im2col_dilated.c:42-65), re-tiled for one SM:
+//
+//     G[pixel][tap] = sum_c X[pixel][c] * W[c][tap]          25 taps (padded to N = 32), K = 32
+//     out[2h + kh - 1][2w + kw - 1] += G[(h, w)][kh*5 + kw]  each output sums 4/6/6/9 neighbours
+//
+// The SIMT kernel (srt_unet_simt.cu) spends 1600 FMAs per input pixel on this layer and is FP32-pipe
+// bound (23 TF/s, 1.16 ms per 32-stream step).  Here the GEMM is 8 MMAs per 128 pixels and the scatter
+// becomes a 25-value gather per input pixel out of shared memory, so the layer is bound by reading its
+// two 16-channel inputs once (HBM).
+//
+// A persistent CTA walks "units" = (stem, image, column block, row chunk).  Inside a unit it walks
+// input rows top to bottom; per row:
+//   warp 12      TMA: 4 boxes {8 ch, 128 px} (2 sources x 2 channel halves, SWIZZLE_32B, OOB = zero)
+//   warps 8-11   split: a -> hi = tf32_rn(a) (in place), lo = a - hi (second tile).  The two inputs are
+//                fp32 and this layer feeds the mask almost directly, so plain TF32 operands would double
+//                the stem error of small nets (oracle emulation); hi + lo keeps fp32 accuracy.
+//   warp 13      MMA: G_row = A_hi*W_hi + A_lo*W_hi (+ A_hi*W_lo for weights that are not TF32-exact),
+//                N = 32, two rows interleaved on two TMEM accumulators
+//   warps 0-7    TMEM -> G ring in shared memory ([4 rows][25 taps][128 px]), then the gather for the
+//                previous input row (needs rows y-1, y, y+1), bias + act + BN, float2 stores.
+// Column blocks overlap by one pixel on each side (the tile starts at x0 - 1), rows chunks by one row.
+#include "srt_kernels.cuh"
+#include "srt_plan.h"
+#include "srt_ptx.cuh"
+
+namespace srt {
+
+constexpr int kU6Threads = 448;            // 8 epilogue + 4 split + TMA + MMA warps
+constexpr int kU6Stages = 4;               // input rows in flight
+constexpr int kU6AccSlots = 8;             // TMEM accumulators (32 columns each)
+constexpr int kU6RowBytes = 4 * 128 * 32;  // 4 boxes x 128 pixels x 8 channels fp32 = 16 KB
+constexpr int kU6GSlot = 25 * 128;         // floats per G row
+
+struct U6Header {
+    uint64_t a_full[kU6Stages], a_ready[kU6Stages], a_empty[kU6Stages];
+    uint64_t acc_full[kU6AccSlots], acc_empty[kU6AccSlots];
+    uint32_t tmem_base, pad;
+};
+
+static size_t up6_tc_smem_bytes(int S)
+{
+    return sizeof(U6Header) + 1024 + (size_t)2 * kU6Stages * kU6RowBytes + (size_t)S * kUp6TcWFloatsPerStem * 4 + (size_t)4 * kU6GSlot * 4;
+}
+
+struct U6Unit {
+    int s, n, x0, r0, r1;
+};
+__device__ __forceinline__ U6Unit u6_unit(const Up6TcParams& p, int u)
+{
+    U6Unit o;
+    const int tx = u % p.blocks_x;
+    u /= p.blocks_x;
+    const int rc = u % p.chunks;
+    u /= p.chunks;
+    const int b = u % p.Bv;
+    o.s = u / p.Bv;
+    o.n = o.s * p.B + b;
+    o.x0 = tx * p.bw;
+    o.r0 = rc * p.rows_per_unit;
+    o.r1 = min(p.T / 2, o.r0 + p.rows_per_unit);
+    return o;
+}
+
+__global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_constant__ Up6TcParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    U6Header* hdr = reinterpret_cast<U6Header*>(smem_raw);
+    const uint32_t a_base = (ptx::smem_u32(smem_raw) + (uint32_t)sizeof(U6Header) + 1023u) & ~1023u;
+    uint8_t* a_raw = smem_raw + (a_base - ptx::smem_u32(smem_raw));   // [stage][box][128][8] fp32, hi after the split
+    uint8_t* a_lo = a_raw + kU6Stages * kU6RowBytes;                  // same layout, residuals
+    const uint32_t lo_base = a_base + kU6Stages * kU6RowBytes;
+    float* wsm = reinterpret_cast<float*>(a_lo + kU6Stages * kU6RowBytes);   // [S][box][term][32][8] pre-swizzled
+    const uint32_t w_base = lo_base + kU6Stages * kU6RowBytes;
+    float* G = wsm + (size_t)p.S * kUp6TcWFloatsPerStem;                     // [4][25][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = p.T / 2, W = p.F / 2;
+    const int n_units = p.blocks_x * p.chunks * p.Bv * p.S;
+
+    for (int i = threadIdx.x; i < p.S * kUp6TcWFloatsPerStem; i += kU6Threads) wsm[i] = p.w[i];
+    ptx::fence_proxy_async();   // the weights are read by the tensor core (async proxy)
+    if (warp == 12 && lane == 0) {
+        ptx::tma_prefetch_desc(&p.tmap[0]);
+        ptx::tma_prefetch_desc(&p.tmap[1]);
+        for (int i = 0; i < kU6Stages; i++) {
+            ptx::mbar_init(&hdr->a_full[i], 1);
+            ptx::mbar_init(&hdr->a_ready[i], 4);    // one arrival per split warp
+            ptx::mbar_init(&hdr->a_empty[i], 1);
+        }
+        for (int i = 0; i < kU6AccSlots; i++) {
+            ptx::mbar_init(&hdr->acc_full[i], 1);
+            ptx::mbar_init(&hdr->acc_empty[i], 8);  // one arrival per epilogue warp
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 13) ptx::tmem_alloc<kU6AccSlots * 32>(&hdr->tmem_base);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_d = hdr->tmem_base;
+
+    if (warp == 12) {
+        // ===== TMA producer =========================================================================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const U6Unit t = u6_unit(p, u);
+                for (int y = t.r0 - 1; y <= t.r1; y++) {
+                    // the ring holds only kU6Stages rows (~2 us of HBM latency would cap it at one row per ~700 cycles):
+                    // pull the rows further ahead into L2 first
+                    if (p.prefetch_rows > 0 && y + p.prefetch_rows <= t.r1) {
+#pragma unroll
+                        for (int b = 0; b < 4; b++) ptx::tma_prefetch_4d(&p.tmap[b >> 1], (b & 1) * 8, t.x0 - 1, y + p.prefetch_rows, t.n);
+                    }
+                    ptx::mbar_wait(&hdr->a_empty[st], ph ^ 1);
+                    if (p.dbg & 4) ptx::mbar_arrive(&hdr->a_full[st]);
+                    else {
+                        ptx::mbar_arrive_expect_tx(&hdr->a_full[st], kU6RowBytes);
+                        uint8_t* dst = a_raw + (size_t)st * kU6RowBytes;
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            ptx::tma_load_4d(dst + b * 4096, &p.tmap[b >> 1], &hdr->a_full[st], (b & 1) * 8, t.x0 - 1, y, t.n);
+                    }
+                    if (++st == p.stages) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ===== split: hi (in place) / lo ============================================================
+        const int ts = threadIdx.x - 256;   // 0..127
+        int st = 0;
+        uint32_t ph = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const U6Unit t = u6_unit(p, u);
+            for (int y = t.r0 - 1; y <= t.r1; y++) {
+                if (p.dbg & 16) ptx::mbar_wait_warp(&hdr->a_full[st], ph);
+                else ptx::mbar_wait(&hdr->a_full[st], ph);
+                float4* raw = reinterpret_cast<float4*>(a_raw + (size_t)st * kU6RowBytes);
+                float4* lo = reinterpret_cast<float4*>(a_lo + (size_t)st * kU6RowBytes);
+                if (!(p.dbg & 8))
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const float4 a = raw[ts + 128 * i];
+                    const float4 h = make_float4(ptx::rna_tf32(a.x), ptx::rna_tf32(a.y), ptx::rna_tf32(a.z), ptx::rna_tf32(a.w));
+                    raw[ts + 128 * i] = h;
+                    lo[ts + 128 * i] = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&hdr->a_ready[st]);
+                if (++st == p.stages) { st = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 13) {
+        // ===== MMA issuer: rows in pairs, so consecutive MMAs hit different accumulators ============
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, 32);
+            int st = 0, as = 0;
+            uint32_t ph = 0, aph = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const U6Unit t = u6_unit(p, u);
+                const uint32_t w_lo = ptx::umma_desc_lo(w_base + (uint32_t)t.s * kUp6TcWFloatsPerStem * 4);
+                for (int y = t.r0 - 1; y <= t.r1; y += 2) {   // the row count r1 - r0 + 2 is even
+                    int stj[2], asj[2];
+                    for (int j = 0; j < 2; j++) {
+                        stj[j] = st; asj[j] = as;
+                        ptx::mbar_wait(&hdr->a_ready[st], ph);
+                        ptx::mbar_wait(&hdr->acc_empty[as], aph ^ 1);
+                        if (++st == p.stages) { st = 0; ph ^= 1; }
+                        if (++as == p.acc_slots) { as = 0; aph ^= 1; }
+                    }
+                    ptx::tc_fence_after();
+                    // terms: (A_hi, W_hi), (A_lo, W_hi), and (A_hi, W_lo) when the weights carry a residual
+                    for (int term = 0; term < ((p.dbg & 2) ? 0 : 1 + p.w_terms); term++) {
+                        const uint32_t abase = (term == 1) ? lo_base : a_base;
+                        const uint32_t wterm = (term == 2) ? 1u : 0u;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const uint32_t b_lo = w_lo + (uint32_t)(((b * 2 + wterm) * 1024) >> 4);
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                const uint32_t a_lo_d = ptx::umma_desc_lo(abase + (uint32_t)stj[j] * kU6RowBytes + (uint32_t)b * 4096);
+                                ptx::mma_tf32_ss_lo(tmem_d + (uint32_t)(asj[j] * 32), a_lo_d, b_lo, idesc, (term | b) ? 1u : 0u, ptx::kDescHiSw32);
+                            }
+                        }
+                    }
+                    for (int j = 0; j < 2; j++) {
+                        ptx::mma_commit(&hdr->a_empty[stj[j]]);
+                        ptx::mma_commit(&hdr->acc_full[asj[j]]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps 0..7 =================================================================
+        const int q = warp & 3, half = warp >> 2;
+        const int m = q * 32 + lane;              // TMEM lane = pixel of the tile
+        const int gm = threadIdx.x & 127;         // gather: pixel
+        const int po = threadIdx.x >> 7;          // gather: output row parity
+        int as = 0;
+        uint32_t aph = 0;
+        int grow = 0;                             // rows this CTA has pushed through the G ring
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const U6Unit t = u6_unit(p, u);
+            const float bias = p.bias[t.s], sc = p.bn_scale[t.s], of = p.bn_offset[t.s];
+            const int act = p.act[t.s];
+            const int X = t.x0 - 1 + gm;
+            const bool col_ok = gm >= 1 && gm <= p.bw && X < W;
+            for (int y = t.r0 - 1; y <= t.r1; y++, grow++) {
+                if (p.dbg & 16) ptx::mbar_wait_warp(&hdr->acc_full[as], aph);
+                else ptx::mbar_wait(&hdr->acc_full[as], aph);
+                ptx::tc_fence_after();
+                float v[16];
+                ptx::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 32 + half * 16), v);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&hdr->acc_empty[as]);
+                if (++as == p.acc_slots) { as = 0; aph ^= 1; }
+                float* gs = G + (size_t)(grow & 3) * kU6GSlot;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (half * 16 + i < 25) gs[(half * 16 + i) * 128 + m] = v[i];
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                const int yo = y - 1;             // rows yo-1, yo, yo+1 are now in the ring
+                if (yo >= t.r0 && col_ok && !(p.dbg & 1)) {
+                    // out(2 yo + po, 2 X + qo) = sum_{dy, dx} G[yo + dy][(po + 1 - 2 dy) * 5 + (qo + 1 - 2 dx)][X + dx]
+                    float o0 = 0.0f, o1 = 0.0f;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++) {
+                        if (po == 0 && dy == 1) continue;      // kh = -1
+                        const int kh = po + 1 - 2 * dy;
+                        const float* gr = G + (size_t)((grow - 1 + dy) & 3) * kU6GSlot + (kh * 5) * 128 + gm;
+                        o0 += gr[1 * 128] + gr[3 * 128 - 1];                       // qo = 0: kw = 1 (dx 0), 3 (dx -1)
+                        o1 += gr[0 * 128 + 1] + gr[2 * 128] + gr[4 * 128 - 1];     // qo = 1: kw = 0 (dx +1), 2 (dx 0), 4 (dx -1)
+                    }
+                    float2 r;
+                    r.x = sc * apply_act(act, o0 + bias) + of;
+                    r.y = sc * apply_act(act, o1 + bias) + of;
+                    *reinterpret_cast<float2*>(p.out + ((size_t)t.n * p.T + 2 * yo + po) * p.F + 2 * X) = r;
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 13) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<kU6AccSlots * 32>(tmem_d);
+    }
+}
+
+void launch_up6_tc(const Up6TcParams& p, cudaStream_t st)
+{
+    const size_t smem = up6_tc_smem_bytes(p.S);
+    static int sms = 0;
+    static size_t configured = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    if (smem > configured) {
+        cudaFuncSetAttribute(up6_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    const int n_units = p.blocks_x * p.chunks * p.Bv * p.S;
+    up6_tc_kernel<<<n_units < sms ? n_units : sms, kU6Threads, smem, st>>>(p);
+}
+
+bool up6_tc_fits(int S) { return up6_tc_smem_bytes(S) <= 232448; }
+
+}  // namespace srt
