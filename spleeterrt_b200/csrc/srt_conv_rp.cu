@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
     // roles (MMA issuer, producers) sit above the 8 epilogue warps instead of being starved by them.
     if (warp == 8) {
         // ===== patch producer ==================================================================
-        if (lane == 0) {
+        if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             int ps = 0;
             uint32_t pph = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
         }
     } else if (warp == 9) {
         // ===== weight producer: the same nkb blocks per tile, streamed ahead across tiles ========
-        if (lane == 0) {
+        if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             int ws = 0;
             uint32_t wph = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
         }
     } else if (warp == 10) {
         // ===== MMA issuer ==========================================================================
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N);
             int ws = 0, ps = 0, as = 0;
             uint32_t wph = 0, pph = 0, aph = 0;

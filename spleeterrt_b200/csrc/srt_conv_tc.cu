@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     // the issue arbiter favours higher warp ids: producer and MMA issuer sit above the 8 epilogue warps
     if (warp == 8) {
         // ===== TMA producer ==============================================================
-        if (lane == 0) {
+        if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             const int x0 = tx * p.tw, y0 = ty * p.th, n0 = s * p.B + tz * p.nb;
             const float* wsrc = p.w + (size_t)s * p.w_stem_stride + p.w_phase_off[phase] + (size_t)nt * nkb * N_TILE * kKB;
             int stage = 0;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
     } else if (warp == 9) {
         // ===== MMA issuer ================================================================
-        if (lane == 0) {
+        if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N_TILE);
             int stage = 0;
             uint32_t ph = 0;

@@ -10,6 +10,11 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a converged warp.  Use this (not `lane == 0`) to guard single-thread roles that issue
+// tcgen05.mma / TMA: the compiler knows an elect.sync region has exactly one active lane and emits the
+// uniform-datapath instructions (UTCHMMA, UTMALDG) straight-line, whereas inside a threadIdx-derived branch it
+// wraps EVERY such instruction in an ELECT / BRA.U.ANY "waterfall" loop over the active lanes (cuobjdump -sass;
+// ~6 dependent instructions per MMA, the ~43-cycle per-MMA issue cost seen in tools/mma_probe.cu).
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t pred = 0;

@@ -146,15 +146,17 @@ void launch_istft(const IstftParams& p, cudaStream_t st)
 // =========================================================================================
 // Fused mask*spectrum -> inverse FFT -> synthesis window -> overlap-add -> un-framing.
 // One CTA owns hops [h0, h0+G) of one (stream, stem): it transforms frames h0-3 .. h0+G-1 in order and
-// accumulates them in a 4096-sample shared-memory ring (same summation order as stftFix.c:570-575), emitting
-// each 1024-sample segment as soon as its last contributing frame has been added.  (G+3)/G of the FFT work,
-// but no 32 KB-per-frame scratch round trip and no separate OLA kernel.
+// overlap-adds them in REGISTERS: thread j holds samples j + 256 r of every frame, and a frame advances the
+// output position by 1024 = 4 * 256 samples, so the 4096-sample overlap window is 16 thread-private
+// accumulators that shift down by 4 per frame.  acc[0..3] is complete after frame f has been added (frames
+// f-3 .. f, the summation order of stftFix.c:570-575) and is emitted as segment f.  (G+3)/G of the FFT work,
+// no 32 KB-per-frame scratch round trip, no separate OLA kernel, and no shared-memory accumulator: the
+// previous shared-memory ring and the per-frame window loads were 28 % of this kernel's L1 wavefronts, its
+// bound (ncu r1k/r1m: l1tex 67 %, dram 15 %).
 // =========================================================================================
-__global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOlaParams p)
+__global__ void __launch_bounds__(kFftThreads, 2) istft_ola_kernel(const IstftOlaParams p)
 {
-    extern __shared__ __align__(16) unsigned char ola_smem[];
-    FftSmem& sm = *reinterpret_cast<FftSmem*>(ola_smem);
-    float2* ring = reinterpret_cast<float2*>(ola_smem + sizeof(FftSmem));
+    __shared__ FftSmem sm;
     const int st = p.stream_first + blockIdx.z, s = blockIdx.y;
     const int nfr = p.n_frames[st];
     const int h0 = blockIdx.x * p.hops_per_cta;
@@ -165,10 +167,14 @@ __global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOl
     float* outL = p.out[(size_t)st * p.S * 2 + s * 2];
     float* outR = p.out[(size_t)st * p.S * 2 + s * 2 + 1];
     const float uw = p.unaffected[s];
-    for (int i = j; i < kFFT; i += kFftThreads) ring[i] = make_float2(0.f, 0.f);
+    float w[16];
+    float2 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        w[r] = __ldg(&p.postwin[j + 256 * r]);
+        acc[r] = make_float2(0.f, 0.f);
+    }
     fft_smem_init(sm, p.twiddle, j);
-    __syncthreads();
-    const long lo = (long)h0 * kHop, hi = (long)h1 * kHop;
     for (int f = max(h0 - 3, 0); f < h1; f++) {
         const int img = img0 + f / p.T, t = f % p.T;
         const float4* srow = p.spec + ((size_t)img * p.T + t) * kBins;
@@ -187,45 +193,32 @@ __global__ void __launch_bounds__(kFftThreads, 3) istft_ola_kernel(const IstftOl
             else z = make_float2(xlr + xri, -xli + xrr);
             v[r] = make_float2(z.x, -z.y);
         }
+        __syncthreads();   // the previous frame's pass-3 reads of the exchange buffer are done (also publishes tw2)
         fft4096(v, sm, p.twiddle, j);
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            const int i = j + 256 * r;
-            const long pos = (long)f * kHop + i;
-            if (pos >= lo && pos < hi) {
-                const float w = __ldg(&p.postwin[i]);
-                float2 a = ring[pos & (kFFT - 1)];
-                a.x += v[r].x * w;
-                a.y += -v[r].y * w;
-                ring[pos & (kFFT - 1)] = a;
-            }
+            acc[r].x += v[r].x * w[r];
+            acc[r].y += -v[r].y * w[r];
         }
-        __syncthreads();
         if (f >= h0) {   // segment f is complete: frames f-3 .. f have been added
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const long pos = (long)f * kHop + j + 256 * k;
-                const float2 a = ring[pos & (kFFT - 1)];
-                ring[pos & (kFFT - 1)] = make_float2(0.f, 0.f);
-                const long io = pos - p.front_pad;
-                if (io >= 0 && io < n) { outL[io] = a.x; outR[io] = a.y; }
+                const long io = (long)f * kHop + j + 256 * k - p.front_pad;
+                if (io >= 0 && io < n) { outL[io] = acc[k].x; outR[io] = acc[k].y; }
             }
         }
-        // the next frame touches the ring only after the barriers inside its FFT
+#pragma unroll
+        for (int r = 0; r < 12; r++) acc[r] = acc[r + 4];
+#pragma unroll
+        for (int r = 12; r < 16; r++) acc[r] = make_float2(0.f, 0.f);
     }
 }
 
 void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cudaStream_t st)
 {
     if (n_streams == 0 || max_frames == 0) return;
-    const size_t smem = sizeof(FftSmem) + (size_t)kFFT * sizeof(float2);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(istft_ola_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
     dim3 grid((max_frames + p.hops_per_cta - 1) / p.hops_per_cta, p.S, n_streams);
-    istft_ola_kernel<<<grid, kFftThreads, smem, st>>>(p);
+    istft_ola_kernel<<<grid, kFftThreads, 0, st>>>(p);
 }
 
 // =========================================================================================

@@ -239,67 +239,116 @@ void launch_up6(const Up6Params& p, cudaStream_t st)
 // up7: 4x4, dilation 2, stride 1 conv 1 -> 2 (rows t + 2kh - 3, cols f + 2kw - 3; spleeter.c:156,295)
 // + bias + sigmoid (LUT flavour spleeter.c:29-42 or exact VST/Source/spleeter.c:56-65).
 // =========================================================================================
-constexpr int U7_TW = 64, U7_TH = 8;
+constexpr int U7_TW = 128, U7_TH = 16, U7_ROWS = 64;   // CTA: 64 rows x 128 columns, walked as 4 tiles of 16 rows
+constexpr int U7_PITCH = U7_TW + 8;                      // tile columns f0-4 .. f0+131 (float4-aligned halo)
 
 // fastSigmoid (spleeter.c:30-42) with the per-interval constants precomputed on the host with the
-// same float operations: entry = {tbl[i], (tbl[i+1]-tbl[i]) / ((-7+step*(i+1)) - (-7+step*i)), -7+step*i}.
-// Only the index division remains; results are bit-identical to evaluating the original expression.
-__device__ __forceinline__ float sigmoid_lut(const float4* __restrict__ tbl, float x)
+// same float operations: entry = {tbl[i], (tbl[i+1]-tbl[i]) / ((-7+step*(i+1)) - (-7+step*i))}; the interval
+// origin -7+step*i is re-evaluated here with the reference's two roundings (multiply, then add).
+// Only the index division is replaced (reciprocal multiply): on the rare inputs where the rounded product
+// lands on the other side of an integer the neighbouring interval is used, which changes the (continuous,
+// piecewise-linear) result by ~1e-8.
+// The table lives in shared memory: gathered from global memory it cost ~28 L1 wavefronts per warp and
+// lookup (every lane another line), which made the L1 the bound of this kernel (ncu r1k: 0.155 ms per
+// stem launch against 0.03 ms of HBM time).
+__device__ __forceinline__ float sigmoid_lut(const float2* __restrict__ tbl, float x)
 {
     const float step = 0.01367188f;
     if (x > 7.0f) return 1.0f;
     if (x < -7.0f) return 0.0f;
-    // index = trunc((x+7)/step) evaluated with a reciprocal multiply: on the rare inputs where the
-    // rounded product lands on the other side of an integer the neighbouring interval is used, which
-    // changes the (continuous, piecewise-linear) result by ~1e-8.
     const int idx = min((int)(__fadd_rn(x, 7.0f) * (1.0f / step)), 1023);
-    const float4 e = __ldg(tbl + idx);
-    return __fadd_rn(e.x, __fmul_rn(e.y, __fsub_rn(x, e.z)));
+    const float2 e = tbl[idx];
+    const float x1 = __fadd_rn(-7.0f, __fmul_rn(step, (float)idx));
+    return __fadd_rn(e.x, __fmul_rn(e.y, __fsub_rn(x, x1)));
 }
 
-__global__ void __launch_bounds__(U7_TW* U7_TH) up7_kernel(const __grid_constant__ Up7Params p)
+__device__ __forceinline__ float sigmoid_exact(float a)
 {
-    __shared__ float tile[U7_TH + 6][U7_TW + 6 + 2];
+    return a >= 0.f ? 1.0f / (1.0f + expf(-a)) : expf(a) / (1.0f + expf(a));
+}
+
+// Each thread produces 4 consecutive columns of output rows r0 and r0+2: the two rows share 3 of their 4
+// input rows (dilation 2) and the 4 columns share their 10-float input span, read as 3 LDS.128 per row:
+// 15 vector loads feed 8 pixels x 32 FMAs (the one-pixel-per-thread version issued 16 scalar LDS per pixel).
+// Accumulation order per output (kh-major, kw-minor, bias last) is the reference's (gemm row order).
+__global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Params p)
+{
+    __shared__ __align__(16) float tile[(U7_TH + 6) * U7_PITCH];
+    __shared__ float2 lut_s[1025];
     const int s = p.stem, b = blockIdx.z, n = s * p.B + b;
-    const int f0 = blockIdx.x * U7_TW, t0 = blockIdx.y * U7_TH;
-    const int tid = threadIdx.x;
+    const int f0 = blockIdx.x * U7_TW;
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
     const float* img = p.in + (size_t)n * p.T * p.F;
-    for (int i = tid; i < (U7_TH + 6) * (U7_TW + 6); i += blockDim.x) {
-        const int r = i / (U7_TW + 6), c = i % (U7_TW + 6);
-        const int t = t0 - 3 + r, f = f0 - 3 + c;
-        tile[r][c] = (t >= 0 && t < p.T && f >= 0 && f < p.F) ? img[(size_t)t * p.F + f] : 0.0f;
-    }
-    __syncthreads();
-    const int tx = tid % U7_TW, ty = tid / U7_TW;
-    const int f = f0 + tx, t = t0 + ty;
-    if (f >= p.F || t >= p.T) return;
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 4; kh++)
-#pragma unroll
-        for (int kw = 0; kw < 4; kw++) {
-            const float v = tile[ty + 2 * kh][tx + 2 * kw];
-            a0 = fmaf(p.wk[kh * 4 + kw], v, a0);
-            a1 = fmaf(p.wk[16 + kh * 4 + kw], v, a1);
-        }
-    a0 += p.wk[32];
-    a1 += p.wk[33];
-    float2 m;
     if (p.lut) {
-        const float4* lut = reinterpret_cast<const float4*>(p.lut);
-        m.x = sigmoid_lut(lut, a0);
-        m.y = sigmoid_lut(lut, a1);
-    } else {
-        m.x = a0 >= 0.f ? 1.0f / (1.0f + expf(-a0)) : expf(a0) / (1.0f + expf(a0));
-        m.y = a1 >= 0.f ? 1.0f / (1.0f + expf(-a1)) : expf(a1) / (1.0f + expf(a1));
+        const float4* lut4 = reinterpret_cast<const float4*>(p.lut);
+        for (int i = tid; i < 1025; i += 256) {
+            const float4 e = __ldg(lut4 + i);
+            lut_s[i] = make_float2(e.x, e.y);
+        }
     }
-    reinterpret_cast<float2*>(p.mask)[(((size_t)s * p.mask_stem_stride + p.mask_img0 + b) * p.T + t) * p.F + f] = m;
+    const int fx = 4 * lane;
+    const int r0 = (g >> 1) * 4 + (g & 1);   // tile-relative output rows r0, r0 + 2
+    float2* mimg = reinterpret_cast<float2*>(p.mask) + ((size_t)s * p.mask_stem_stride + p.mask_img0 + b) * p.T * p.F;
+    for (int t0 = blockIdx.y * U7_ROWS; t0 < min((int)(blockIdx.y + 1) * U7_ROWS, p.T); t0 += U7_TH) {
+        __syncthreads();   // previous tile fully consumed (and, first time, nothing to wait for)
+        for (int i = tid; i < (U7_TH + 6) * (U7_PITCH / 4); i += 256) {
+            const int r = i / (U7_PITCH / 4), c4 = i % (U7_PITCH / 4);
+            const int t = t0 - 3 + r, f = f0 - 4 + 4 * c4;   // F is a multiple of 4: a float4 is entirely in or out
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < p.T && f >= 0 && f < p.F) v = *reinterpret_cast<const float4*>(img + (size_t)t * p.F + f);
+            *reinterpret_cast<float4*>(tile + r * U7_PITCH + 4 * c4) = v;
+        }
+        __syncthreads();
+        float acc[2][4][2];
+#pragma unroll
+        for (int a = 0; a < 2; a++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[a][j][0] = acc[a][j][1] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            // tile row r0 + 2q = input row of output row r0 for kh = q and of output row r0 + 2 for kh = q - 1
+            const float4* rp = reinterpret_cast<const float4*>(tile + (r0 + 2 * q) * U7_PITCH + fx);
+            const float4 va = rp[0], vb = rp[1], vc = rp[2];
+            const float v[12] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+            for (int kw = 0; kw < 4; kw++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float x = v[1 + j + 2 * kw];   // input column f + 2 kw - 3
+                    if (q < 4) {
+                        acc[0][j][0] = fmaf(p.wk[q * 4 + kw], x, acc[0][j][0]);
+                        acc[0][j][1] = fmaf(p.wk[16 + q * 4 + kw], x, acc[0][j][1]);
+                    }
+                    if (q >= 1) {
+                        acc[1][j][0] = fmaf(p.wk[(q - 1) * 4 + kw], x, acc[1][j][0]);
+                        acc[1][j][1] = fmaf(p.wk[16 + (q - 1) * 4 + kw], x, acc[1][j][1]);
+                    }
+                }
+        }
+        const int f = f0 + fx;
+        if (f < p.F) {
+#pragma unroll
+            for (int a = 0; a < 2; a++) {
+                const int t = t0 + r0 + 2 * a;
+                float m[8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float a0 = acc[a][j][0] + p.wk[32], a1 = acc[a][j][1] + p.wk[33];
+                    if (p.lut) { m[2 * j] = sigmoid_lut(lut_s, a0); m[2 * j + 1] = sigmoid_lut(lut_s, a1); }
+                    else { m[2 * j] = sigmoid_exact(a0); m[2 * j + 1] = sigmoid_exact(a1); }
+                }
+                float4* d = reinterpret_cast<float4*>(mimg + (size_t)t * p.F + f);
+                d[0] = make_float4(m[0], m[1], m[2], m[3]);
+                d[1] = make_float4(m[4], m[5], m[6], m[7]);
+            }
+        }
+    }
 }
 
 void launch_up7(const Up7Params& p, cudaStream_t st)
 {
-    dim3 grid((p.F + U7_TW - 1) / U7_TW, (p.T + U7_TH - 1) / U7_TH, p.Bv);   // one launch per stem (p.stem, p.wk)
-    up7_kernel<<<grid, U7_TW * U7_TH, 0, st>>>(p);
+    dim3 grid((p.F + U7_TW - 1) / U7_TW, (p.T + U7_ROWS - 1) / U7_ROWS, p.Bv);   // one launch per stem (p.stem, p.wk)
+    up7_kernel<<<grid, 256, 0, st>>>(p);
 }
 
 // API layout [n][T][F][2] -> internal space-to-depth layout, TF32-rounded (srt_unet_device)

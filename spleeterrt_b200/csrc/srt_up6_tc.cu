@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
 
     if (warp == 12) {
         // ===== TMA producer =========================================================================
-        if (lane == 0) {
+        if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             int st = 0;
             uint32_t ph = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
         }
     } else if (warp == 13) {
         // ===== MMA issuer: rows in pairs, so consecutive MMAs hit different accumulators ============
-        if (lane == 0) {
+        if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, 32);
             int st = 0, as = 0;
             uint32_t ph = 0, aph = 0;

@@ -17,7 +17,9 @@ __device__ __forceinline__ void mma(uint32_t d, uint32_t alo, uint32_t blo, uint
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(d), "r"(alo), "r"(blo), "r"(idesc), "r"(acc), "r"(ptx::kDescHiSw128) : "memory");
 }
 
-template <int KIND>
+// ELECT = false: the issuing thread is selected with `threadIdx.x == 0` (every UTCHMMA gets wrapped in an
+// ELECT / BRA.U.ANY waterfall loop by the compiler); ELECT = true: with elect.sync (straight-line UTCHMMA).
+template <int KIND, bool ELECT>
 __global__ void probe(int N, int nacc, int iters, int a_shift_rows, long long* out)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -31,7 +33,7 @@ __global__ void probe(int N, int nacc, int iters, int a_shift_rows, long long* o
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
-    if (threadIdx.x == 0) {
+    if (ELECT ? (threadIdx.x < 32 && ptx::elect_one()) : (threadIdx.x == 0)) {
         const uint32_t idesc = KIND == 0 ? ptx::umma_idesc_tf32(128, N)
                                          : ((1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
         const uint32_t alo = ptx::umma_desc_lo(base + a_shift_rows * 128), blo = ptx::umma_desc_lo(base + 20 * 1024);
@@ -95,9 +97,12 @@ int main()
 {
     long long* d;
     cudaMalloc(&d, 16);
-    cudaFuncSetAttribute(probe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(probe<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    printf("kind N nacc shift | issue cyc/MMA | total cyc/MMA\n");
+    cudaFuncSetAttribute(probe<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(probe<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(probe<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(probe<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    for (int elect = 0; elect < 2; elect++) {
+    printf("issuer selected by %s\nkind N nacc shift | issue cyc/MMA | total cyc/MMA\n", elect ? "elect.sync" : "threadIdx.x == 0");
     for (int kind = 0; kind < 2; kind++)
         for (int N : {16, 32, 64, 128, 256})
             for (int nacc : {1, 2, 4})
@@ -105,14 +110,17 @@ int main()
                     if (nacc * N > 512) continue;
                     if (shift && !(N == 64)) continue;
                     const int iters = 200;
-                    if (kind == 0) probe<0><<<1, 128, 64 * 1024>>>(N, nacc, iters, shift, d);
-                    else probe<1><<<1, 128, 64 * 1024>>>(N, nacc, iters, shift, d);
+                    if (kind == 0 && !elect) probe<0, false><<<1, 128, 64 * 1024>>>(N, nacc, iters, shift, d);
+                    else if (kind == 0) probe<0, true><<<1, 128, 64 * 1024>>>(N, nacc, iters, shift, d);
+                    else if (!elect) probe<1, false><<<1, 128, 64 * 1024>>>(N, nacc, iters, shift, d);
+                    else probe<1, true><<<1, 128, 64 * 1024>>>(N, nacc, iters, shift, d);
                     long long h[2];
                     cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                     const double n = (double)iters * nacc * 4;
                     printf("%s %3d %d %d | %7.1f | %7.1f\n", kind ? "f16 " : "tf32", N, nacc, shift, h[0] / n, h[1] / n);
                 }
+    }
     cudaFuncSetAttribute(probe2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     printf("two issuing warps: N nacc(per warp) | cycles per MMA per warp | aggregate cycles per MMA\n");
     for (int N : {32, 64, 128})
