@@ -18,6 +18,8 @@ GPU box with gpurun):
      with -DCPU_GEMM=1 (in-repo naive sgemm, Executable/gemm.c:64-80) and the
      zeroing-malloc shim (gemm_cpu multiplies uninitialised C by BETA=0,
      Executable/gemm.c:71-72 -> NaN on a dirty heap).
+  3. compiles the reference's unmodified CLI host Executable/main.c once and links it against
+     (a) libref_exec.so and (b) libspleeterrt_b200.so  ->  oracle/_ref/spleeter_cli_{ref,b200}
 
 It is a no-op when /root/reference is absent (GPU box): the prebuilt files are used.
 """
@@ -84,8 +86,45 @@ def build(force=False):
         cc(so, [os.path.join(vst, f) for f in
                 ("Spleeter4Stems.c", "spleeter.c", "im2col_dilated.c", "codelet.c", "cpthread.c")]
            + [os.path.join(ex, "gemm.c")], extra=["-I" + vst])
-    decode_weights(force)
+    wbin = decode_weights(force)
+    build_cli(wbin, force)
     return True
+
+
+def build_cli(wbin, force=False):
+    """The reference's UNMODIFIED CLI host (Executable/main.c), compiled once and linked twice:
+         oracle/_ref/spleeter_cli_ref   against the reference's own objects (libref_exec.so)
+         oracle/_ref/spleeter_cli_b200  against libspleeterrt_b200.so (the drop-in claim, SURVEY 8b tier A)
+    main.c does `#include "model.c"`, 108 MB of C source that the reference ships as model.7z.  Its
+    content is data (`static const int32_t coeffQuantized[9822725]`), so instead of compiling the
+    decoded text for 69 s the same array is placed in .rodata with `.incbin` from the decoded blob.
+    tests/test_cli_dropin.py runs both binaries on the same WAV (BASELINE.json configs[0])."""
+    ex = os.path.join(REF, "Executable")
+    mdir = os.path.join(OUT, "model_incbin")
+    os.makedirs(mdir, exist_ok=True)
+    main_o = os.path.join(OUT, "main_cli.o")
+    ref_cli = os.path.join(OUT, "spleeter_cli_ref")
+    b200_cli = os.path.join(OUT, "spleeter_cli_b200")
+    pkg = os.path.join(os.path.dirname(HERE), "spleeterrt_b200")
+    lib = os.path.join(pkg, "libspleeterrt_b200.so")
+    if force or not os.path.exists(main_o):
+        with open(os.path.join(mdir, "model.c"), "w") as f:
+            f.write('#include <stdint.h>\n'
+                    '__asm__(".section .rodata\\n.balign 64\\n.globl coeffQuantized\\ncoeffQuantized:\\n'
+                    '.incbin \\"%s\\"\\n.previous\\n");\n'
+                    'extern const int32_t coeffQuantized[9822725];\n' % wbin)
+        subprocess.check_call(["gcc", "-O2", "-w", "-c", "-I", mdir, "-I", ex, os.path.join(ex, "main.c"), "-o", main_o])
+    host = [os.path.join(ex, "libsamplerate", "samplerate.c"), os.path.join(ex, "libsamplerate", "src_sinc.c")]
+    if force or not os.path.exists(ref_cli):
+        stub = os.path.join(mdir, "stub.c")
+        with open(stub, "w") as f:
+            f.write("void openblas_set_num_threads(int n) { (void)n; }\n")   # main.c:689 expects OpenBLAS on Linux
+        subprocess.check_call(["gcc", "-O2", "-w", "-fopenmp", "-I", ex, main_o, *host, stub, "-L", OUT, "-lref_exec",
+                               "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread", "-o", ref_cli])
+    if os.path.exists(lib) and (force or not os.path.exists(b200_cli) or os.path.getmtime(b200_cli) < os.path.getmtime(main_o)):
+        subprocess.check_call(["gcc", "-O2", "-w", "-I", ex, main_o, *host, os.path.join(ex, "cpthread.c"),
+                               "-L", pkg, "-lspleeterrt_b200", "-Wl,-rpath,$ORIGIN/../../spleeterrt_b200",
+                               "-lm", "-lpthread", "-o", b200_cli])
 
 
 if __name__ == "__main__":

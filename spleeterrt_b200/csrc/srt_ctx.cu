@@ -865,9 +865,26 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
         p.postwin = c->d_postwin; p.twiddle = c->d_twiddle; p.out = (float* const*)(c->d_meta + o_out);
         for (int s = 0; s < S; s++) p.unaffected[s] = unaffected ? unaffected[s] : 0.1f;
         p.T = T; p.F = c->F; p.S = S; p.mask_stem_stride = c->NB; p.stream_first = 0; p.front_pad = front_pad;
-        p.hops_per_cta = 16;
         int max_fr = 0;
         for (int i = 0; i < n_streams; i++) max_fr = std::max(max_fr, m.nfr[i]);
+        // Hops per CTA: a CTA spends h + 3 transforms on h hops (3 warm-up frames of overlap), and the grid runs
+        // in waves of 2 CTAs per SM (128 registers x 256 threads).  Pick the h that minimises waves x (h + 3):
+        // small h for a single stream (fill the SMs), large h for a full batch (amortise the warm-up) while
+        // keeping the last wave full.  SRT_ISTFT_HOPS overrides.
+        {
+            const long long slots = 2LL * c->sm_count;
+            long long best_cost = -1;
+            int best_h = 16;
+            for (int h = 4; h <= 64; h++) {
+                long long ctas = 0;
+                for (int i = 0; i < n_streams; i++) ctas += (m.nfr[i] + h - 1) / h;
+                ctas *= S;
+                const long long cost = ((ctas + slots - 1) / slots) * (h + 3);
+                if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_h = h; }
+            }
+            const char* he = getenv("SRT_ISTFT_HOPS");
+            p.hops_per_cta = he ? std::max(1, atoi(he)) : best_h;
+        }
         launch_istft_ola(p, n_streams, max_fr, c->stream);
         c->launches++;
     } else {

@@ -55,16 +55,26 @@ __device__ __forceinline__ void store16_warp(float* dst, const float* v, float4*
 }
 
 // Branch-free activations for the tensor-core epilogues.  The epilogue warps are instruction-latency
-// bound (ncu / tools/rp_dbg_sweep.sh: the epilogue, not the MMAs, dominated the small-N layers), so the
-// activation kind is resolved once per 16-channel chunk and ELU uses ex2.approx (__expf): its absolute
-// error (~1e-7) is far below the TF32 rounding applied to the stored value right after.
+// bound (ncu / tools/stage_sweep.py: the epilogue, not the MMAs, dominates down1 and costs as much as the
+// MMAs of the small-N layers), so the activation kind is resolved once per 16-channel chunk and ELU is
+// 5 instructions: FMUL, MUFU.EX2 (ex2.approx.ftz), FADD, FSETP, FSEL.  __expf() compiles to the non-ftz
+// ex2.approx plus a denormal-range fix-up (FSETP/PLOP3/FMUL x0.5/square: ~13 instructions per element,
+// cuobjdump).  With .ftz the result for x*log2(e) < -126 is 0, i.e. ELU = -1: the value the reference's
+// clamp returns there (spleeter.c:51-56).  Absolute error ~1e-7, far below the TF32 rounding applied to
+// the stored value right after.
+__device__ __forceinline__ float exp_fast(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x)
 {
     if (ACT == ACT_LEAKY) return x >= 0.0f ? x : 0.2f * x;
     if (ACT == ACT_RELU) return fmaxf(x, 0.0f);
-    if (ACT == ACT_ELU_CLAMP) { const float e = x < -15.0f ? -1.0f : __expf(x) - 1.0f; return x >= 0.0f ? x : e; }
-    if (ACT == ACT_ELU) { const float e = __expf(x) - 1.0f; return x >= 0.0f ? x : e; }
+    if (ACT == ACT_ELU_CLAMP) { const float e = x < -15.0f ? -1.0f : exp_fast(x) - 1.0f; return x >= 0.0f ? x : e; }
+    if (ACT == ACT_ELU) { const float e = exp_fast(x) - 1.0f; return x >= 0.0f ? x : e; }
     return x;
 }
 

@@ -7,6 +7,8 @@ SETS = {
            ("only_epi", {"SRT_RP_DBG": "14"})],
     "up6": [("base", {}), ("lane0_poll", {"SRT_UP6_DBG": "16"}), ("all_off", {"SRT_UP6_DBG": "15"}), ("no_mma", {"SRT_UP6_DBG": "2"}),
             ("no_gather", {"SRT_UP6_DBG": "1"}), ("simt", {"SRT_UP6_TC": "0"})],
+    "istft": [("auto", {}), ("hops16", {"SRT_ISTFT_HOPS": "16"}), ("hops28", {"SRT_ISTFT_HOPS": "28"}), ("hops40", {"SRT_ISTFT_HOPS": "40"}),
+              ("hops55", {"SRT_ISTFT_HOPS": "55"})],
 }
 if len(sys.argv) > 2 and sys.argv[1] == "--child":
     import torch
