@@ -26,7 +26,7 @@
 
 namespace srt {
 
-constexpr int kRpThreads = 352;   // 3 control warps + 8 epilogue warps
+// threads per CTA = (EPW epilogue warps + 3 control warps) * 32; EPW = 8, or 16 where shared memory allows (down1)
 constexpr int kRpMaxChunks = 8, kRpMaxKB = 80, kRpMaxWStages = 12;
 
 struct RpHeader {
@@ -38,8 +38,8 @@ struct RpHeader {
     KBlock kb[kRpMaxKB];
 };
 
-template <int N, int R, int WS, int KB>
-constexpr size_t rp_smem_bytes() { return sizeof(RpHeader) + 1024 + (size_t)2 * (R + 2) * kPatchW * KB * 4 + (size_t)WS * N * KB * 4 + 8 * 2048; }   // + per-warp store staging
+template <int N, int R, int WS, int KB, int EPW>
+constexpr size_t rp_smem_bytes() { return sizeof(RpHeader) + 1024 + (size_t)2 * (R + 2) * kPatchW * KB * 4 + (size_t)WS * N * KB * 4 + EPW * 2048; }   // + per-warp store staging
 
 struct RpTile {
     int s, n, x0, y0;
@@ -59,9 +59,11 @@ __device__ __forceinline__ RpTile rp_tile(const RowConvParams& p, int t, int R)
     return o;
 }
 
-template <int N, int R, int WS, int KB>
-__global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_constant__ RowConvParams p)
+template <int N, int R, int WS, int KB, int EPW>
+__global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid_constant__ RowConvParams p)
 {
+    constexpr int kRpThreads = (EPW + 3) * 32;
+    constexpr int kWarpPatch = EPW, kWarpWeights = EPW + 1, kWarpMma = EPW + 2;   // control warps sit above the epilogue warps
     extern __shared__ uint8_t smem_raw[];
     RpHeader* hdr = reinterpret_cast<RpHeader*>(smem_raw);
     const uint32_t patch_base = (ptx::smem_u32(smem_raw) + (uint32_t)sizeof(RpHeader) + 1023u) & ~1023u;
@@ -75,7 +77,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
     constexpr int kTmemCols = 2 * kAccCols <= 32 ? 32 : 2 * kAccCols <= 64 ? 64 : 2 * kAccCols <= 128 ? 128 : 2 * kAccCols <= 256 ? 256 : 512;
     static_assert(2 * kAccCols <= 512, "two accumulator sets must fit TMEM");
     uint8_t* wring = patch + 2 * kPatchBytes;
-    float4* stage_all = reinterpret_cast<float4*>(wring + (size_t)WS * kWBytes);   // 8 epilogue warps x 2 KB (store16_warp)
+    float4* stage_all = reinterpret_cast<float4*>(wring + (size_t)WS * kWBytes);   // EPW epilogue warps x 2 KB (store16_warp)
     const uint32_t wring_base = patch_base + 2 * kPatchBytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -83,14 +85,14 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
 
     for (int i = threadIdx.x; i < p.n_chunks; i += kRpThreads) hdr->chunks[i] = p.chunks[i];
     for (int i = threadIdx.x; i < p.nkb; i += kRpThreads) hdr->kb[i] = p.kb[i];
-    if (warp == 8 && lane == 0) {
+    if (warp == kWarpPatch && lane == 0) {
         ptx::tma_prefetch_desc(&p.tmap[0]);
         ptx::tma_prefetch_desc(&p.tmap[1]);
         for (int i = 0; i < 2; i++) {
             ptx::mbar_init(&hdr->patch_full[i], 1);
             ptx::mbar_init(&hdr->patch_empty[i], 1);
             ptx::mbar_init(&hdr->acc_full[i], 1);
-            ptx::mbar_init(&hdr->acc_empty[i], 8);   // one arrival per epilogue warp
+            ptx::mbar_init(&hdr->acc_empty[i], EPW);   // one arrival per epilogue warp
         }
         for (int i = 0; i < WS; i++) {
             ptx::mbar_init(&hdr->w_full[i], 1);
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 10) ptx::tmem_alloc<kTmemCols>(&hdr->tmem_base);
+    if (warp == kWarpMma) ptx::tmem_alloc<kTmemCols>(&hdr->tmem_base);
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
 
     // Role -> warp mapping: the SM's issue arbiter favours higher warp ids, so the latency-critical single-thread
     // roles (MMA issuer, producers) sit above the 8 epilogue warps instead of being starved by them.
-    if (warp == 8) {
+    if (warp == kWarpPatch) {
         // ===== patch producer ==================================================================
         if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             int ps = 0;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kWarpWeights) {
         // ===== weight producer: the same nkb blocks per tile, streamed ahead across tiles ========
         if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             int ws = 0;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == kWarpMma) {
         // ===== MMA issuer ==========================================================================
         if (ptx::elect_one()) {
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N);
@@ -188,9 +190,18 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
             }
         }
     } else {
-        // ===== epilogue: warps 0..7; warp%4 selects the TMEM lane quarter, warp/4 the column half =====
-        const int q = warp & 3, half = warp >> 2;
+        // ===== epilogue: warps 0..EPW-1; warp%4 selects the TMEM lane quarter, warp/4 the share of the tile's
+        // (row, 16-column chunk) units.  EPW = 8: two warps per quarter split the columns in two contiguous halves, so
+        // each thread writes whole 128-byte lines (fused decoder layers: both column parities of one output row;
+        // encoder: half of the pixel's channels).  EPW = 16: four warps per quarter take contiguous runs of units
+        // (down1: one tile row each) - the epilogue is instruction-latency bound (ncu r1m: issue slots 50 % busy
+        // with 2 epilogue warps per scheduler), so twice the warps is what speeds it up.
+        const int q = warp & 3, part = warp >> 2;
         const int m = q * 32 + lane;
+        constexpr int kParts = EPW / 4;
+        constexpr int kChunksPerRow = N / 16;
+        constexpr int kUnits = R * kChunksPerRow;                    // 16-column chunks per tile and lane
+        constexpr bool kSplitCols = (kParts == 2 && N >= 32);        // the original column-half mapping
         int as = 0;
         uint32_t aph = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -199,26 +210,30 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
             ptx::mbar_wait(&hdr->acc_full[as], aph);
             ptx::tc_fence_after();
             const uint32_t acc = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccCols);
+            float4* stage = stage_all + warp * 128;
+            constexpr int kPerPart = kSplitCols ? kUnits / 2 : (kUnits + kParts - 1) / kParts;
 #pragma unroll 1
-            for (int r = 0; r < R; r++) {
+            for (int i = 0; i < kPerPart; i++) {
+                int r, c0;
+                if (kSplitCols) {            // unit i of this warp: row i / (chunks per half), chunk inside the warp's column half
+                    r = i / (kChunksPerRow / 2);
+                    c0 = (part * (kChunksPerRow / 2) + i % (kChunksPerRow / 2)) * 16;
+                } else {
+                    const int u = part * kPerPart + i;
+                    if (u >= kUnits) break;
+                    r = u / kChunksPerRow;
+                    c0 = (u % kChunksPerRow) * 16;
+                }
                 const int Y = tl.y0 + r;
                 const bool valid = X < p.ep.Ws && Y < p.ep.Hs;
-#pragma unroll 1
-                // the two epilogue warps of a lane quarter split the columns in two contiguous halves, so each
-                // thread writes whole 128-byte lines (for the fused decoder layers: both column parities of one
-                // output row; for the encoder: half of the pixel's channels)
-                constexpr int kHalfCols = N >= 32 ? N / 2 : N;
-                for (int c0 = half * kHalfCols; c0 < (half + 1) * kHalfCols && c0 < N; c0 += 16) {
-                    float v[16];
-                    ptx::tmem_ld16(acc + (uint32_t)(r * N + c0), v);
-                    if (!(p.dbg & 1)) {   // warp-uniform: the stores are warp-cooperative
-                        float4* stage = stage_all + warp * 128;
-                        if (p.stems_per_tile > 1 || p.stem0 > 0) {   // down1: the column selects the stem (its own output image)
-                            const int se = p.stem0 + c0 / p.ep.cout;
-                            epilogue16(p.ep, se, se * p.ep.B + tl.n, Y, X, 0, c0 % p.ep.cout, v, stage, valid);
-                        } else if (p.ep.mode == 2) epilogue16(p.ep, tl.s, tl.n, Y, X, c0 / p.ep.cout, c0 % p.ep.cout, v, stage, valid);
-                        else epilogue16(p.ep, tl.s, tl.n, Y, X, 0, c0, v, stage, valid);
-                    }
+                float v[16];
+                ptx::tmem_ld16(acc + (uint32_t)(r * N + c0), v);
+                if (!(p.dbg & 1)) {   // warp-uniform: the stores are warp-cooperative
+                    if (p.stems_per_tile > 1 || p.stem0 > 0) {   // down1: the column selects the stem (its own output image)
+                        const int se = p.stem0 + c0 / p.ep.cout;
+                        epilogue16(p.ep, se, se * p.ep.B + tl.n, Y, X, 0, c0 % p.ep.cout, v, stage, valid);
+                    } else if (p.ep.mode == 2) epilogue16(p.ep, tl.s, tl.n, Y, X, c0 / p.ep.cout, c0 % p.ep.cout, v, stage, valid);
+                    else epilogue16(p.ep, tl.s, tl.n, Y, X, 0, c0, v, stage, valid);
                 }
             }
             ptx::tc_fence_before();
@@ -229,35 +244,40 @@ __global__ void __launch_bounds__(kRpThreads, 1) conv_rp_kernel(const __grid_con
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 10) {
+    if (warp == kWarpMma) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<kTmemCols>(tmem_d);
     }
 }
 
-template <int N, int R, int WS, int KB>
+template <int N, int R, int WS, int KB, int EPW = 8>
 static void launch_rp(const RowConvParams& p, cudaStream_t st)
 {
-    constexpr size_t smem = rp_smem_bytes<N, R, WS, KB>();
+    constexpr size_t smem = rp_smem_bytes<N, R, WS, KB, EPW>();
     static_assert(smem <= 232448, "must fit the 227 KB per-CTA limit");
     static int sms = 0;
     if (!sms) {
-        cudaFuncSetAttribute(conv_rp_kernel<N, R, WS, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(conv_rp_kernel<N, R, WS, KB, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int n_tiles = p.tiles_x * p.tiles_y * p.ep.Bv * p.ep.S;
     dim3 grid(n_tiles < sms ? n_tiles : sms, 1, 1);
-    conv_rp_kernel<N, R, WS, KB><<<grid, kRpThreads, smem, st>>>(p);
+    conv_rp_kernel<N, R, WS, KB, EPW><<<grid, (EPW + 3) * 32, smem, st>>>(p);
 }
 
 void launch_conv_rp(const RowConvParams& p, cudaStream_t st)
 {
-    if (p.kb_width == 8) {   // down1: 8-channel k-blocks, up to 4 stems fused into N
-        if (p.N == 64 && p.R == 4) launch_rp<64, 4, 9, 8>(p, st);
-        else if (p.N == 32 && p.R == 4) launch_rp<32, 4, 9, 8>(p, st);
-        else if (p.N == 16 && p.R == 4) launch_rp<16, 4, 9, 8>(p, st);
+    if (p.kb_width == 8) {   // down1: 8-channel k-blocks, up to 4 stems fused into N; small patches leave room for 16 epilogue warps
+        const bool wide = !(p.dbg & 64);   // SRT_RP_DBG bit 6: the 8-warp epilogue (timing experiments)
+        if (p.N == 64 && p.R == 4) { if (wide) launch_rp<64, 4, 9, 8, 16>(p, st); else launch_rp<64, 4, 9, 8>(p, st); }
+        else if (p.N == 32 && p.R == 4) { if (wide) launch_rp<32, 4, 9, 8, 16>(p, st); else launch_rp<32, 4, 9, 8>(p, st); }
+        else if (p.N == 16 && p.R == 4) { if (wide) launch_rp<16, 4, 9, 8, 16>(p, st); else launch_rp<16, 4, 9, 8>(p, st); }
+    } else if (p.dbg & 128) {   // experiment: 16 epilogue warps paid for with a shallower weight ring
+        if (p.N == 32 && p.R == 3) launch_rp<32, 3, 4, 32, 16>(p, st);
+        else if (p.N == 64 && p.R == 3) launch_rp<64, 3, 2, 32, 16>(p, st);
+        else if (p.N == 128 && p.R == 2) launch_rp<128, 2, 3, 32, 16>(p, st);
     } else if (p.N == 32 && p.R == 3) launch_rp<32, 3, 8, 32>(p, st);
     else if (p.N == 64 && p.R == 3) launch_rp<64, 3, 4, 32>(p, st);
     else if (p.N == 128 && p.R == 2) launch_rp<128, 2, 4, 32>(p, st);

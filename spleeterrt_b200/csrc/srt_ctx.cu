@@ -64,7 +64,7 @@ static PFN_encodeTiled get_encode()
 // activation tensor [n][H][W][C] fp32 -> 4-D map, box {32, tw, th, nb}, 128B swizzle, zero OOB fill
 static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int N, int tw, int th, int nb, int kbw = kKB)
 {
-    // box = {kbw channels (32 -> SWIZZLE_128B, 8 -> SWIZZLE_32B), tw pixels, th rows, nb images}; may overhang the tensor (zero fill)
+    // box = {kbw channels (32 -> SWIZZLE_128B, 16 -> SWIZZLE_64B, 8 -> SWIZZLE_32B), tw pixels, th rows, nb images}; may overhang the tensor (zero fill)
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -72,7 +72,7 @@ static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int
     cuuint32_t box[4] = {(cuuint32_t)kbw, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     kbw == kKB ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     kbw == kKB ? CU_TENSOR_MAP_SWIZZLE_128B : kbw == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) C=%d W=%d H=%d N=%d box=%d,%d,%d", (int)r, C, W, H, N, tw, th, nb);
     return 0;
@@ -378,7 +378,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             q.dbg = dbe ? atoi(dbe) : 0;
             const char* ste = getenv("SRT_UP6_STAGES");
             const char* ace = getenv("SRT_UP6_ACC");
-            q.stages = ste ? std::max(2, std::min(4, atoi(ste))) : 4;
+            q.stages = ste ? std::max(2, std::min(5, atoi(ste))) : 5;
             q.acc_slots = ace ? std::max(2, std::min(8, atoi(ace))) : 4;
             const int W = F / 2;
             q.blocks_x = (W + 125) / 126;
@@ -387,8 +387,8 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
                 q.bias[s] = b6[s]; q.bn_scale[s] = s6[s]; q.bn_offset[s] = o6[s];
                 q.act[s] = c->act_dec[s];
             }
-            if ((r = make_tmap(&q.tmap[0], c->E[1], 16, W, T / 2, S * c->B, 128, 1, 1, 8))) return r;
-            if ((r = make_tmap(&q.tmap[1], c->U[5], 16, W, T / 2, S * c->B, 128, 1, 1, 8))) return r;
+            if ((r = make_tmap(&q.tmap[0], c->E[1], 16, W, T / 2, S * c->B, 128, 1, 1, 16))) return r;
+            if ((r = make_tmap(&q.tmap[1], c->U[5], 16, W, T / 2, S * c->B, 128, 1, 1, 16))) return r;
             c->use_up6tc = true;
         }
     }

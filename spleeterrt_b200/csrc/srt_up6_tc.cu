@@ -12,15 +12,20 @@
 //
 // A persistent CTA walks "units" = (stem, image, column block, row chunk).  Inside a unit it walks
 // input rows top to bottom; per row:
-//   warp 12      TMA: 4 boxes {8 ch, 128 px} (2 sources x 2 channel halves, SWIZZLE_32B, OOB = zero)
-//   warps 8-11   split: a -> hi = tf32_rn(a) (in place), lo = a - hi (second tile).  The two inputs are
-//                fp32 and this layer feeds the mask almost directly, so plain TF32 operands would double
-//                the stem error of small nets (oracle emulation); hi + lo keeps fp32 accuracy.
+//   warp 12      TMA: 2 boxes {16 ch, 128 px} (one per source, SWIZZLE_64B, OOB = zero).  One box per 8-channel K step
+//                (4 boxes of 32-byte rows) was fetch-bound: with everything but the TMA switched off the kernel
+//                still took 0.77 of its 0.85 ms (profiles/r1m_up6_stage_sweep.txt) - the copy engine works per
+//                contiguous fragment, and 64-byte fragments halve their number.
+//   warps 8-11   split: hi = the tile as loaded (the MMA sees a truncated to TF32), lo = a - trunc_tf32(a)
+//                (second tile).  The two inputs are fp32 and this layer feeds the mask almost directly, so
+//                plain TF32 operands would double the stem error of small nets (oracle emulation,
+//                DESIGN.md); hi + lo keeps fp32 accuracy.
 //   warp 13      MMA: G_row = A_hi*W_hi + A_lo*W_hi (+ A_hi*W_lo for weights that are not TF32-exact),
 //                N = 32, two rows interleaved on two TMEM accumulators
 //   warps 0-7    TMEM -> G ring in shared memory ([4 rows][25 taps][128 px]), then the gather for the
 //                previous input row (needs rows y-1, y, y+1), bias + act + BN, float2 stores.
 // Column blocks overlap by one pixel on each side (the tile starts at x0 - 1), rows chunks by one row.
+#include "srt_epilogue.cuh"
 #include "srt_kernels.cuh"
 #include "srt_plan.h"
 #include "srt_ptx.cuh"
@@ -28,20 +33,24 @@
 namespace srt {
 
 constexpr int kU6Threads = 448;            // 8 epilogue + 4 split + TMA + MMA warps
-constexpr int kU6Stages = 4;               // input rows in flight
+constexpr int kU6Stages = 5;               // input rows in flight (the kernel is bound by the TMA -> split -> MMA -> release
+                                           // latency chain per ring slot: 2 / 3 / 4 stages ran 1.40 / 1.16 / 0.85 ms, profiles/r1m_up6_stage_sweep.txt)
 constexpr int kU6AccSlots = 8;             // TMEM accumulators (32 columns each)
-constexpr int kU6RowBytes = 4 * 128 * 32;  // 4 boxes x 128 pixels x 8 channels fp32 = 16 KB
+constexpr int kU6RowBytes = 2 * 128 * 64;  // 2 boxes x 128 pixels x 16 channels fp32 = 16 KB
+constexpr int kU6BoxBytes = 128 * 64;
 constexpr int kU6GSlot = 25 * 128;         // floats per G row
 
 struct U6Header {
     uint64_t a_full[kU6Stages], a_ready[kU6Stages], a_empty[kU6Stages];
     uint64_t acc_full[kU6AccSlots], acc_empty[kU6AccSlots];
+    uint64_t w_full, w_idle;       // weights of the current stem landed / every MMA that read the previous stem's weights retired
     uint32_t tmem_base, pad;
 };
 
 static size_t up6_tc_smem_bytes(int S)
 {
-    return sizeof(U6Header) + 1024 + (size_t)2 * kU6Stages * kU6RowBytes + (size_t)S * kUp6TcWFloatsPerStem * 4 + (size_t)4 * kU6GSlot * 4;
+    (void)S;   // only the current stem's weights are resident (8 KB): the space of the other stems buys the fifth ring stage
+    return sizeof(U6Header) + 1024 + (size_t)2 * kU6Stages * kU6RowBytes + (size_t)kUp6TcWFloatsPerStem * 4 + (size_t)4 * kU6GSlot * 4;
 }
 
 struct U6Unit {
@@ -68,19 +77,17 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     U6Header* hdr = reinterpret_cast<U6Header*>(smem_raw);
     const uint32_t a_base = (ptx::smem_u32(smem_raw) + (uint32_t)sizeof(U6Header) + 1023u) & ~1023u;
-    uint8_t* a_raw = smem_raw + (a_base - ptx::smem_u32(smem_raw));   // [stage][box][128][8] fp32, hi after the split
+    uint8_t* a_raw = smem_raw + (a_base - ptx::smem_u32(smem_raw));   // [stage][source][128][16] fp32, hi after the split
     uint8_t* a_lo = a_raw + kU6Stages * kU6RowBytes;                  // same layout, residuals
     const uint32_t lo_base = a_base + kU6Stages * kU6RowBytes;
-    float* wsm = reinterpret_cast<float*>(a_lo + kU6Stages * kU6RowBytes);   // [S][box][term][32][8] pre-swizzled
+    float* wsm = reinterpret_cast<float*>(a_lo + kU6Stages * kU6RowBytes);   // [box][term][32][8] pre-swizzled, current stem
     const uint32_t w_base = lo_base + kU6Stages * kU6RowBytes;
-    float* G = wsm + (size_t)p.S * kUp6TcWFloatsPerStem;                     // [4][25][128]
+    float* G = wsm + (size_t)kUp6TcWFloatsPerStem;                           // [4][25][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.T / 2, W = p.F / 2;
     const int n_units = p.blocks_x * p.chunks * p.Bv * p.S;
 
-    for (int i = threadIdx.x; i < p.S * kUp6TcWFloatsPerStem; i += kU6Threads) wsm[i] = p.w[i];
-    ptx::fence_proxy_async();   // the weights are read by the tensor core (async proxy)
     if (warp == 12 && lane == 0) {
         ptx::tma_prefetch_desc(&p.tmap[0]);
         ptx::tma_prefetch_desc(&p.tmap[1]);
@@ -93,6 +100,8 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
             ptx::mbar_init(&hdr->acc_full[i], 1);
             ptx::mbar_init(&hdr->acc_empty[i], 8);  // one arrival per epilogue warp
         }
+        ptx::mbar_init(&hdr->w_full, 1);
+        ptx::mbar_init(&hdr->w_idle, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 13) ptx::tmem_alloc<kU6AccSlots * 32>(&hdr->tmem_base);
@@ -113,7 +122,7 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                     // pull the rows further ahead into L2 first
                     if (p.prefetch_rows > 0 && y + p.prefetch_rows <= t.r1) {
 #pragma unroll
-                        for (int b = 0; b < 4; b++) ptx::tma_prefetch_4d(&p.tmap[b >> 1], (b & 1) * 8, t.x0 - 1, y + p.prefetch_rows, t.n);
+                        for (int b = 0; b < 2; b++) ptx::tma_prefetch_4d(&p.tmap[b], 0, t.x0 - 1, y + p.prefetch_rows, t.n);
                     }
                     ptx::mbar_wait(&hdr->a_empty[st], ph ^ 1);
                     if (p.dbg & 4) ptx::mbar_arrive(&hdr->a_full[st]);
@@ -121,8 +130,8 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                         ptx::mbar_arrive_expect_tx(&hdr->a_full[st], kU6RowBytes);
                         uint8_t* dst = a_raw + (size_t)st * kU6RowBytes;
 #pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            ptx::tma_load_4d(dst + b * 4096, &p.tmap[b >> 1], &hdr->a_full[st], (b & 1) * 8, t.x0 - 1, y, t.n);
+                        for (int b = 0; b < 2; b++)
+                            ptx::tma_load_4d(dst + b * kU6BoxBytes, &p.tmap[b], &hdr->a_full[st], 0, t.x0 - 1, y, t.n);
                     }
                     if (++st == p.stages) { st = 0; ph ^= 1; }
                 }
@@ -140,13 +149,24 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                 else ptx::mbar_wait(&hdr->a_full[st], ph);
                 float4* raw = reinterpret_cast<float4*>(a_raw + (size_t)st * kU6RowBytes);
                 float4* lo = reinterpret_cast<float4*>(a_lo + (size_t)st * kU6RowBytes);
-                if (!(p.dbg & 8))
+                if (p.dbg & 32) {   // A/B switch: round-to-nearest hi, rewritten in place
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float4 a = raw[ts + 128 * i];
+                        const float4 h = make_float4(ptx::rna_tf32(a.x), ptx::rna_tf32(a.y), ptx::rna_tf32(a.z), ptx::rna_tf32(a.w));
+                        raw[ts + 128 * i] = h;
+                        lo[ts + 128 * i] = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
+                    }
+                } else if (!(p.dbg & 8))
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
+                    // hi = the raw tile itself: the tensor core reads only the TF32 bits of an fp32 operand (sign, exponent,
+                    // 10 mantissa bits), i.e. a truncated to TF32.  lo = a - trunc(a) is exact in fp32 and < 2^-10 |a|, so
+                    // hi + tf32(lo) carries >= 20 mantissa bits.  Not rewriting hi saves a third of this warp group's
+                    // shared-memory traffic (the kernel's bound).
                     const float4 a = raw[ts + 128 * i];
-                    const float4 h = make_float4(ptx::rna_tf32(a.x), ptx::rna_tf32(a.y), ptx::rna_tf32(a.z), ptx::rna_tf32(a.w));
-                    raw[ts + 128 * i] = h;
-                    lo[ts + 128 * i] = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
+                    lo[ts + 128 * i] = make_float4(a.x - ptx::trunc_tf32(a.x), a.y - ptx::trunc_tf32(a.y), a.z - ptx::trunc_tf32(a.z),
+                                                   a.w - ptx::trunc_tf32(a.w));
                 }
                 ptx::fence_proxy_async();
                 __syncwarp();
@@ -158,11 +178,25 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
         // ===== MMA issuer: rows in pairs, so consecutive MMAs hit different accumulators ============
         if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
             constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, 32);
-            int st = 0, as = 0;
-            uint32_t ph = 0, aph = 0;
+            int st = 0, as = 0, cur_s = -1;
+            uint32_t ph = 0, aph = 0, wph = 0, iph = 0;
+            const uint32_t w_lo = ptx::umma_desc_lo(w_base);
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const U6Unit t = u6_unit(p, u);
-                const uint32_t w_lo = ptx::umma_desc_lo(w_base + (uint32_t)t.s * kUp6TcWFloatsPerStem * 4);
+                if (t.s != cur_s) {
+                    // units are stem-major, so a CTA changes stem at most S - 1 times: drain the MMAs that read the old
+                    // weights, then bulk-copy the new stem's 8 KB (async proxy -> async proxy, completes on w_full)
+                    if (cur_s >= 0) {
+                        ptx::mma_commit(&hdr->w_idle);
+                        ptx::mbar_wait(&hdr->w_idle, iph);
+                        iph ^= 1;
+                    }
+                    ptx::mbar_arrive_expect_tx(&hdr->w_full, kUp6TcWFloatsPerStem * 4);
+                    ptx::bulk_load_1d(wsm, p.w + (size_t)t.s * kUp6TcWFloatsPerStem, kUp6TcWFloatsPerStem * 4, &hdr->w_full);
+                    ptx::mbar_wait(&hdr->w_full, wph);
+                    wph ^= 1;
+                    cur_s = t.s;
+                }
                 for (int y = t.r0 - 1; y <= t.r1; y += 2) {   // the row count r1 - r0 + 2 is even
                     int stj[2], asj[2];
                     for (int j = 0; j < 2; j++) {
@@ -182,8 +216,9 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                             const uint32_t b_lo = w_lo + (uint32_t)(((b * 2 + wterm) * 1024) >> 4);
 #pragma unroll
                             for (int j = 0; j < 2; j++) {
-                                const uint32_t a_lo_d = ptx::umma_desc_lo(abase + (uint32_t)stj[j] * kU6RowBytes + (uint32_t)b * 4096);
-                                ptx::mma_tf32_ss_lo(tmem_d + (uint32_t)(asj[j] * 32), a_lo_d, b_lo, idesc, (term | b) ? 1u : 0u, ptx::kDescHiSw32);
+                                // K step b: source b >> 1, channels 8 (b & 1) .. +7 = bytes 32 (b & 1) of the 64-byte swizzled rows
+                                const uint32_t a_lo_d = ptx::umma_desc_lo(abase + (uint32_t)stj[j] * kU6RowBytes + (uint32_t)(b >> 1) * kU6BoxBytes) + (uint32_t)(b & 1) * 2;
+                                ptx::mma_tf32_ss_ab(tmem_d + (uint32_t)(asj[j] * 32), a_lo_d, ptx::kDescHiSw64, b_lo, ptx::kDescHiSw32, idesc, (term | b) ? 1u : 0u);
                             }
                         }
                     }
@@ -196,6 +231,10 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
         }
     } else {
         // ===== epilogue warps 0..7 =================================================================
+        // Software-pipelined per input row y:  issue the TMEM load of row y  |  gather + store the output rows of
+        // input row y - 2 from G rows y-3, y-2, y-1 (complete and published by the previous barrier) while that load
+        // is in flight  |  wait for the load, write G[y]  |  barrier.  The gather reads three ring slots and the
+        // store goes to the fourth, so one 256-thread barrier per row is enough.
         const int q = warp & 3, half = warp >> 2;
         const int m = q * 32 + lane;              // TMEM lane = pixel of the tile
         const int gm = threadIdx.x & 127;         // gather: pixel
@@ -208,13 +247,38 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
             const float bias = p.bias[t.s], sc = p.bn_scale[t.s], of = p.bn_offset[t.s];
             const int act = p.act[t.s];
             const int X = t.x0 - 1 + gm;
-            const bool col_ok = gm >= 1 && gm <= p.bw && X < W;
+            const bool col_ok = gm >= 1 && gm <= p.bw && X < W && !(p.dbg & 1);
+            // out(2 yo + po, 2 X + qo) = sum_{dy, dx} G[yo + dy][(po + 1 - 2 dy) * 5 + (qo + 1 - 2 dx)][X + dx];
+            // `c` = ring index of input row yo
+            auto gather = [&](int yo, int c) {
+                float o0 = 0.0f, o1 = 0.0f;
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++) {
+                    if (po == 0 && dy == 1) continue;      // kh = -1
+                    const int kh = po + 1 - 2 * dy;
+                    const float* gr = G + (size_t)((c + dy) & 3) * kU6GSlot + (kh * 5) * 128 + gm;
+                    o0 += gr[1 * 128] + gr[3 * 128 - 1];                       // qo = 0: kw = 1 (dx 0), 3 (dx -1)
+                    o1 += gr[0 * 128 + 1] + gr[2 * 128] + gr[4 * 128 - 1];     // qo = 1: kw = 0 (dx +1), 2 (dx 0), 4 (dx -1)
+                }
+                o0 += bias;
+                o1 += bias;
+                float2 r;
+                if (act == ACT_ELU_CLAMP) { r.x = act_fast<ACT_ELU_CLAMP>(o0); r.y = act_fast<ACT_ELU_CLAMP>(o1); }
+                else if (act == ACT_RELU) { r.x = act_fast<ACT_RELU>(o0); r.y = act_fast<ACT_RELU>(o1); }
+                else if (act == ACT_ELU) { r.x = act_fast<ACT_ELU>(o0); r.y = act_fast<ACT_ELU>(o1); }
+                else { r.x = apply_act(act, o0); r.y = apply_act(act, o1); }
+                r.x = sc * r.x + of;
+                r.y = sc * r.y + of;
+                *reinterpret_cast<float2*>(p.out + ((size_t)t.n * p.T + 2 * yo + po) * p.F + 2 * X) = r;
+            };
             for (int y = t.r0 - 1; y <= t.r1; y++, grow++) {
                 if (p.dbg & 16) ptx::mbar_wait_warp(&hdr->acc_full[as], aph);
                 else ptx::mbar_wait(&hdr->acc_full[as], aph);
                 ptx::tc_fence_after();
-                float v[16];
-                ptx::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 32 + half * 16), v);
+                uint32_t v[16];
+                ptx::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 32 + half * 16), v);
+                if (y - 2 >= t.r0 && col_ok) gather(y - 2, grow - 2);
+                ptx::tmem_ld16_wait(v);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&hdr->acc_empty[as]);
@@ -222,26 +286,10 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                 float* gs = G + (size_t)(grow & 3) * kU6GSlot;
 #pragma unroll
                 for (int i = 0; i < 16; i++)
-                    if (half * 16 + i < 25) gs[(half * 16 + i) * 128 + m] = v[i];
+                    if (half * 16 + i < 25) gs[(half * 16 + i) * 128 + m] = __uint_as_float(v[i]);
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
-                const int yo = y - 1;             // rows yo-1, yo, yo+1 are now in the ring
-                if (yo >= t.r0 && col_ok && !(p.dbg & 1)) {
-                    // out(2 yo + po, 2 X + qo) = sum_{dy, dx} G[yo + dy][(po + 1 - 2 dy) * 5 + (qo + 1 - 2 dx)][X + dx]
-                    float o0 = 0.0f, o1 = 0.0f;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; dy++) {
-                        if (po == 0 && dy == 1) continue;      // kh = -1
-                        const int kh = po + 1 - 2 * dy;
-                        const float* gr = G + (size_t)((grow - 1 + dy) & 3) * kU6GSlot + (kh * 5) * 128 + gm;
-                        o0 += gr[1 * 128] + gr[3 * 128 - 1];                       // qo = 0: kw = 1 (dx 0), 3 (dx -1)
-                        o1 += gr[0 * 128 + 1] + gr[2 * 128] + gr[4 * 128 - 1];     // qo = 1: kw = 0 (dx +1), 2 (dx 0), 4 (dx -1)
-                    }
-                    float2 r;
-                    r.x = sc * apply_act(act, o0 + bias) + of;
-                    r.y = sc * apply_act(act, o1 + bias) + of;
-                    *reinterpret_cast<float2*>(p.out + ((size_t)t.n * p.T + 2 * yo + po) * p.F + 2 * X) = r;
-                }
             }
+            if (col_ok) gather(t.r1 - 1, grow - 2);   // flush: the last output rows of the unit (G rows r1-2, r1-1, r1)
         }
     }
     ptx::tc_fence_before();

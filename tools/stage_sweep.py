@@ -7,6 +7,11 @@ SETS = {
            ("only_epi", {"SRT_RP_DBG": "14"})],
     "up6": [("base", {}), ("lane0_poll", {"SRT_UP6_DBG": "16"}), ("all_off", {"SRT_UP6_DBG": "15"}), ("no_mma", {"SRT_UP6_DBG": "2"}),
             ("no_gather", {"SRT_UP6_DBG": "1"}), ("simt", {"SRT_UP6_TC": "0"})],
+    "up6b": [("base", {}), ("stages4", {"SRT_UP6_STAGES": "4"}), ("stages3", {"SRT_UP6_STAGES": "3"}), ("acc8", {"SRT_UP6_ACC": "8"}),
+             ("pf24", {"SRT_UP6_PREFETCH": "24"}), ("pf6", {"SRT_UP6_PREFETCH": "6"}), ("no_gather", {"SRT_UP6_DBG": "1"}), ("all_off", {"SRT_UP6_DBG": "15"})],
+    "up6c": [("base", {}), ("rna_split", {"SRT_UP6_DBG": "32"}), ("no_gather", {"SRT_UP6_DBG": "1"}), ("no_split", {"SRT_UP6_DBG": "8"})],
+    "epw": [("base", {}), ("down1_8warps", {"SRT_RP_DBG": "64"}), ("rp_16warps", {"SRT_RP_DBG": "128"}),
+            ("only_epi", {"SRT_RP_DBG": "14"}), ("only_epi_d1_8w", {"SRT_RP_DBG": "78"}), ("only_epi_rp16", {"SRT_RP_DBG": "142"})],
     "istft": [("auto", {}), ("hops16", {"SRT_ISTFT_HOPS": "16"}), ("hops28", {"SRT_ISTFT_HOPS": "28"}), ("hops40", {"SRT_ISTFT_HOPS": "40"}),
               ("hops55", {"SRT_ISTFT_HOPS": "55"})],
 }
