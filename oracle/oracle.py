@@ -242,6 +242,26 @@ def separate(nets, pcmL, pcmR, T, F, unaffected=0.1, flavour=0, want_masks=False
     return (out, masks) if want_masks else out
 
 
+def separate_cli(nets, pcmL, pcmR, T, F, n_out, unaffected=0.1):
+    """The CLI's output modes (main.c:776-970).  n_out = 2: nets = [vocal net] -> float32[2][2][n]
+    (vocal, accompaniment); n_out = 3: nets = [drum net, vocal net] -> float32[3][2][n] (drum, vocal, accompaniment)."""
+    lib = port()
+    pcmL = np.ascontiguousarray(pcmL, np.float32)
+    pcmR = np.ascontiguousarray(pcmR, np.float32)
+    n, ns = pcmL.size, len(nets)
+    assert ns == n_out - 1
+    coeffs = [np.ascontiguousarray(c, np.float32) for c, _ in nets]
+    cp = (C.c_void_p * ns)(*[c.ctypes.data for c in coeffs])
+    modes = (C.c_int * ns)(*[m for _, m in nets])
+    out = np.zeros((n_out, 2, n), np.float32)
+    op = (C.c_void_p * (2 * n_out))(*[out[s, c].ctypes.data for s in range(n_out) for c in range(2)])
+    lib.srt_oracle_separate_cli.argtypes = [C.c_void_p, C.c_void_p, C.c_int, _f32p, _f32p, C.c_size_t,
+                                            C.c_int, C.c_int, C.c_float, C.c_void_p]
+    rc = lib.srt_oracle_separate_cli(cp, modes, n_out, pcmL, pcmR, n, T, F, unaffected, op)
+    assert rc == 0
+    return out
+
+
 # ----------------------------------------------------------------------------- reference API
 class RefExec:
     """The reference's Executable flavour, compiled as is (oracle/_ref/libref_exec.so)."""
@@ -354,6 +374,50 @@ class RefExec:
                         ms[q][f0:f0 + nt, F:BINS] *= np.float32(unaffected)
             oL, oR = self.istft(*ms)
             out[s, 0], out[s, 1] = oL[FFT:FFT + n], oR[FFT:FFT + n]
+        return out
+
+
+    def _net_over_spectrum(self, coeff, mode, planes, T, F, unaffected):
+        """processMT's single-thread branch (main.c:447-541) on the reference's own processSpleeter, in place."""
+        run = self.unet_instance(coeff, T, F, mode)
+        frames = planes[0].shape[0]
+        for f0 in range(0, frames, T):
+            nt = min(T, frames - f0)
+            mag = np.zeros((2, T, F), np.float32)
+            for c in range(2):
+                mag[c, :nt] = np.hypot(planes[2 * c][f0:f0 + nt, :F], planes[2 * c + 1][f0:f0 + nt, :F]) * np.float32(FFT)
+            mask = run(mag)
+            for c in range(2):
+                for q in (2 * c, 2 * c + 1):
+                    planes[q][f0:f0 + nt, :F] *= mask[c, :nt]
+                    planes[q][f0:f0 + nt, F:BINS] *= np.float32(unaffected)
+
+    def separate_cli(self, nets, pcmL, pcmR, T, F, n_out, unaffected=0.1):
+        """The CLI's 2- and 3-output flows (main.c:776-970) on the reference's own stft / processSpleeter / istft."""
+        n = len(pcmL)
+        padded = FFT * ((n + FFT - 1) // FFT) + 2 * FFT
+        pl, pr = np.zeros(padded, np.float32), np.zeros(padded, np.float32)
+        pl[FFT:FFT + n] = pcmL
+        pr[FFT:FFT + n] = pcmR
+        spec = self.stft(pl, pr)
+        cut = slice(FFT, FFT + n)
+        out = np.zeros((n_out, 2, n), np.float32)
+        if n_out == 2:
+            self._net_over_spectrum(nets[0][0], nets[0][1], spec, T, F, unaffected)
+            oL, oR = self.istft(*spec)
+            out[0, 0], out[0, 1] = oL[cut], oR[cut]
+            out[1, 0], out[1, 1] = pl[cut] - oL[cut], pr[cut] - oR[cut]
+            return out
+        orig = [p.copy() for p in spec]
+        self._net_over_spectrum(nets[0][0], nets[0][1], spec, T, F, unaffected)
+        resid = [o - d for o, d in zip(orig, spec)]
+        dL, dR = self.istft(*spec)
+        avL, avR = self.istft(*resid)
+        self._net_over_spectrum(nets[1][0], nets[1][1], resid, T, F, unaffected)
+        vL, vR = self.istft(*resid)
+        out[0, 0], out[0, 1] = dL[cut], dR[cut]
+        out[1, 0], out[1, 1] = vL[cut], vR[cut]
+        out[2, 0], out[2, 1] = (avL - vL)[cut], (avR - vR)[cut]
         return out
 
 

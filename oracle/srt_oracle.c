@@ -506,6 +506,101 @@ int srt_oracle_separate(const float *const *coeffs, const int *stemModes, int nS
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------
+ * One net over a whole spectrum, in place = processMT's single-thread branch (main.c:447-541):
+ * per T-frame tile magnitude (:459-471), U-Net, mask multiply below binLimit (:476-485),
+ * unaffectedWeight above (:486-493); tail tile zero-padded (:507-514).
+ * ---------------------------------------------------------------------------------- */
+static void net_over_spectrum(const float *coeff, int stemMode, int flavour, float *const sp[4], size_t frames,
+                              int T, int F, float unaffectedWeight)
+{
+    const size_t P = (size_t)T * F;
+    const size_t tiles = (frames + T - 1) / T;
+    float *mag = (float *)malloc(sizeof(float) * 2 * P);
+    float *mask = (float *)malloc(sizeof(float) * 2 * P);
+    for (size_t j = 0; j < tiles; j++) {
+        const size_t f0 = j * T;
+        for (int t = 0; t < T; t++)
+            for (int i = 0; i < F; i++) {
+                const size_t idx = (f0 + t) * SRT_FFT + i;
+                const int live = f0 + t < frames;
+                mag[0 * P + (size_t)t * F + i] = live ? hypotf(sp[0][idx], sp[1][idx]) * (float)SRT_FFT : 0.0f;
+                mag[1 * P + (size_t)t * F + i] = live ? hypotf(sp[2][idx], sp[3][idx]) * (float)SRT_FFT : 0.0f;
+            }
+        srt_oracle_unet(coeff, F, T, stemMode, flavour, mag, mask, NULL);
+        for (int t = 0; t < T && f0 + t < frames; t++) {
+            const size_t off = (f0 + t) * SRT_FFT;
+            for (int i = 0; i < F; i++) {
+                const float mL = mask[0 * P + (size_t)t * F + i], mR = mask[1 * P + (size_t)t * F + i];
+                sp[0][off + i] *= mL; sp[1][off + i] *= mL;
+                sp[2][off + i] *= mR; sp[3][off + i] *= mR;
+            }
+            for (int i = F; i < SRT_BINS; i++)
+                for (int q = 0; q < 4; q++) sp[q][off + i] *= unaffectedWeight;
+        }
+    }
+    free(mag); free(mask);
+}
+
+/* ------------------------------------------------------------------------------------
+ * The CLI's two output modes around the tile driver (main.c:776-970), with its host framing.
+ *   nOut == 2 (main.c:777-796): vocal = istft(mask * spec) with coeffs[0]; accompaniment = input - vocal
+ *             in the time domain.  stems = {vocal L, R, accompaniment L, R}.
+ *   nOut == 3 (main.c:845-936): drum net (coeffs[0]) masks the mixture; the residual spectrum
+ *             orig - drum (:859-865) is inverse-transformed (accompaniment + vocal, :879) and also
+ *             fed to the vocal net (coeffs[1], :911); accompaniment = that sum - vocal in the time
+ *             domain (:923-927).  stems = {drum L, R, vocal L, R, accompaniment L, R}.
+ * ---------------------------------------------------------------------------------- */
+int srt_oracle_separate_cli(const float *const *coeffs, const int *stemModes, int nOut,
+                            const float *pcmL, const float *pcmR, size_t n, int T, int F,
+                            float unaffectedWeight, float *const *stems)
+{
+    if (nOut != 2 && nOut != 3) return -1;
+    const size_t padded = srt_oracle_padded_len(n);
+    const size_t frames = padded / SRT_HOP;
+    const size_t plane = frames * SRT_FFT;
+    float *pl = (float *)calloc(padded, sizeof(float)), *pr = (float *)calloc(padded, sizeof(float));
+    memcpy(pl + SRT_FFT, pcmL, n * sizeof(float));
+    memcpy(pr + SRT_FFT, pcmR, n * sizeof(float));
+    float *a[4], *b[4];
+    for (int i = 0; i < 4; i++) { a[i] = (float *)calloc(plane, sizeof(float)); b[i] = (float *)calloc(plane, sizeof(float)); }
+    srt_oracle_stft(pl, pr, padded, a[0], a[1], a[2], a[3]);
+    const size_t outLen = frames * SRT_HOP + (SRT_FFT - SRT_HOP);
+    float *o[3][2];
+    for (int k = 0; k < 3; k++)
+        for (int c = 0; c < 2; c++) o[k][c] = (float *)calloc(outLen, sizeof(float));
+    if (nOut == 2) {
+        net_over_spectrum(coeffs[0], stemModes[0], 0, a, frames, T, F, unaffectedWeight);
+        srt_oracle_istft(a[0], a[1], a[2], a[3], frames, o[0][0], o[0][1]);
+        for (size_t i = 0; i < n; i++) {                         /* main.c:790-794 then channel_joinFloat's preshift */
+            stems[0][i] = o[0][0][SRT_FFT + i];
+            stems[1][i] = o[0][1][SRT_FFT + i];
+            stems[2][i] = pl[SRT_FFT + i] - o[0][0][SRT_FFT + i];
+            stems[3][i] = pr[SRT_FFT + i] - o[0][1][SRT_FFT + i];
+        }
+    } else {
+        for (int q = 0; q < 4; q++) memcpy(b[q], a[q], sizeof(float) * plane);   /* orig_* (:849-856) */
+        net_over_spectrum(coeffs[0], stemModes[0], 0, a, frames, T, F, unaffectedWeight);   /* drum (:858) */
+        for (int q = 0; q < 4; q++)
+            for (size_t i = 0; i < plane; i++) b[q][i] = b[q][i] - a[q][i];       /* residual (:860-865) */
+        srt_oracle_istft(a[0], a[1], a[2], a[3], frames, o[0][0], o[0][1]);       /* drum (:867) */
+        srt_oracle_istft(b[0], b[1], b[2], b[3], frames, o[2][0], o[2][1]);       /* accompaniment + vocal (:881) */
+        net_over_spectrum(coeffs[1], stemModes[1], 0, b, frames, T, F, unaffectedWeight);   /* vocal (:911) */
+        srt_oracle_istft(b[0], b[1], b[2], b[3], frames, o[1][0], o[1][1]);       /* (:914) */
+        for (size_t i = 0; i < n; i++)
+            for (int c = 0; c < 2; c++) {
+                stems[0 + c][i] = o[0][c][SRT_FFT + i];
+                stems[2 + c][i] = o[1][c][SRT_FFT + i];
+                stems[4 + c][i] = o[2][c][SRT_FFT + i] - o[1][c][SRT_FFT + i];    /* (:923-927) */
+            }
+    }
+    for (int i = 0; i < 4; i++) { free(a[i]); free(b[i]); }
+    for (int k = 0; k < 3; k++)
+        for (int c = 0; c < 2; c++) free(o[k][c]);
+    free(pl); free(pr);
+    return 0;
+}
+
 /* half -> float with denormals flushed to zero (f32Decompress, main.c:423-434). */
 void srt_oracle_half_to_float(const uint16_t *in, float *out, size_t n)
 {

@@ -5,7 +5,7 @@ oracle/build_ref.py from /root/reference).  Run in the build container:
     python oracle/build_ref.py && python tests/golden/make_golden.py
 
 Fixtures are small on purpose (they are committed): a T=64 x F=64 U-Net call with seeded
-synthetic fp16-representable weights (both activation modes) and a 20-frame STFT/iSTFT."""
+synthetic fp16-representable weights (both activation modes), a 20-frame STFT/iSTFT and a T=64 x F=64 run of the CLI's 3-output cascade."""
 import os
 import sys
 
@@ -32,4 +32,12 @@ planes = r.stft(L, R)
 oL, oR = r.istft(*planes)
 np.savez_compressed(os.path.join(HERE, "stft_small.npz"), L=L, R=R, reL=planes[0][:, :2049], imL=planes[1][:, :2049],
                     reR=planes[2][:, :2049], imR=planes[3][:, :2049], outL=oL, outR=oR)
+# 3-output cascade of the CLI (main.c:845-936): drum net (ELU) -> residual spectrum -> vocal net (LeakyReLU/ReLU)
+n = 9000
+L = (rng.standard_normal(n) * 0.2).astype(np.float32)
+R = (rng.standard_normal(n) * 0.2).astype(np.float32)
+sd, sv = 5151, 5252
+nets = [(O.synthetic_weights(sd), 1), (O.synthetic_weights(sv), 0)]
+stems = r.separate_cli(nets, L, R, 64, 64, 3)
+np.savez_compressed(os.path.join(HERE, "cascade_T64_F64.npz"), seed_drum=sd, seed_vocal=sv, L=L, R=R, stems=stems)
 print("golden fixtures written")

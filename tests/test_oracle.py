@@ -91,6 +91,33 @@ def test_separate_port_vs_reference(oracle, small_nets):
     assert np.abs(a).max() > 1e-3
 
 
+@pytest.mark.parametrize("n_out", [2, 3])
+def test_cli_output_modes_port_vs_reference(oracle, small_nets, n_out):
+    """The CLI's 2-output (vocal, accompaniment = input - vocal) and 3-output cascade (drum net -> residual
+    spectrum -> vocal net -> time-domain subtraction), main.c:776-970."""
+    r = _ref(oracle)
+    L, R = oracle.synth_pcm(1, n=21000)
+    nets = small_nets if n_out == 3 else small_nets[1:]
+    a = r.separate_cli(nets, L, R, 64, 256, n_out)
+    b = oracle.separate_cli(nets, L, R, 64, 256, n_out)
+    assert np.sqrt(((a - b) ** 2).mean()) < 1e-6
+    assert np.abs(a).max() > 1e-3
+    # the outputs of either mode add up to the inverse transform of the analysed input (linearity of the iSTFT)
+    if n_out == 2:
+        assert np.abs(a[0] + a[1] - np.stack([L, R])).max() < 1e-6
+
+
+def test_golden_cli_cascade(oracle):
+    """Committed fixture of the 3-output cascade, generated from the reference build (tests/golden/make_golden.py)."""
+    p = os.path.join(GOLD, "cascade_T64_F64.npz")
+    if not os.path.exists(p):
+        pytest.skip("golden not generated")
+    g = np.load(p)
+    nets = [(oracle.synthetic_weights(int(g["seed_drum"])), 1), (oracle.synthetic_weights(int(g["seed_vocal"])), 0)]
+    y = oracle.separate_cli(nets, g["L"], g["R"], 64, 64, 3)
+    assert np.sqrt(((y - g["stems"]) ** 2).mean()) < 1e-6
+
+
 def test_golden_unet(oracle):
     """Committed fixture generated from the reference build (tests/golden/make_golden.py)."""
     p = os.path.join(GOLD, "unet_T64_F64.npz")
