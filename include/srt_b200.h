@@ -59,6 +59,19 @@ typedef struct {
  * stem_modes[s]: 0 = LeakyReLU(0.2)/ReLU, !=0 = ELU/ELU (spleeter.c:130-139).
  * The blobs are copied; they need not outlive the call. */
 int srt_create(const srt_config* cfg, const float* const* coeffs, const int* stem_modes, srt_ctx** out);
+/* The CLI's output modes as one device-resident call (Executable/main.c:776-970; the reference runs them as
+ * stft -> processMT -> [residual -> processMT] -> istft x n -> time-domain subtraction on the host).
+ *   n_outputs = 2: coeffs = {vocal net}.        Output pairs per stream: [vocal, accompaniment = input - vocal]
+ *                  (main.c:782-794; vocal net = coeffProvPtr1, stemMode 0).
+ *   n_outputs = 3: coeffs = {drum net, vocal net}.  Output pairs: [drum, vocal, accompaniment]: the drum net
+ *                  (coeffProvPtr2, stemMode 1) masks the spectrum, the vocal net runs on the magnitudes of
+ *                  residual = spectrum - drum spectrum, accompaniment = istft(residual) - vocal (main.c:845-927).
+ * cfg->n_stems is ignored.  The returned context is used with srt_separate_batch / _batch_async / _device exactly
+ * like one from srt_create: stems_out holds n_outputs (L, R) pairs per stream and unaffected[0] (NULL = 0.1) is
+ * the single unaffectedWeight of main.c:773. */
+int srt_create_cli(const srt_config* cfg, int n_outputs, const float* const* coeffs, srt_ctx** out);
+/* (L, R) output pairs per stream of srt_separate_*: n_stems, or n_outputs for a context from srt_create_cli */
+int srt_output_pairs(const srt_ctx* ctx);
 void srt_destroy(srt_ctx* ctx);
 const char* srt_last_error(void);
 
@@ -77,7 +90,7 @@ int srt_unet_device(srt_ctx* ctx, const float* d_mag, int n_img, float* d_mask);
 /* ---- full path --------------------------------------------------------------------------
  * n_streams stereo streams; stream i has n_samples[i] samples per channel (planar).
  * stems_out[i * n_stems * 2 + s * 2 + c] receives stem s, channel c of stream i
- * (n_samples[i] floats).  unaffected[s] scales the bins >= F (main.c:486-493; the VST uses
+ * (n_samples[i] floats; for a srt_create_cli context read n_outputs for n_stems).  unaffected[s] scales the bins >= F (main.c:486-493; the VST uses
  * 0.25 / 0.0, Spleeter4Stems.c:73,281); NULL = 0.1 for every stem (main.c:773).
  * *_batch takes host pointers (copies inside), *_device takes device pointers. */
 int srt_separate_batch(srt_ctx* ctx, const float* const* pcmL, const float* const* pcmR,

@@ -5,5 +5,5 @@ reference's own operator interface (``processSpleeter`` / ``stft`` / ``istft``, 
 compute happens in ``libspleeterrt_b200.so`` (hand-written sm_100a CUDA); there is no CPU or
 PyTorch fallback — if the library or a B200 is missing, calls raise.
 """
-from .api import (COEFF_FLOATS, FFTSIZE, HOPSIZE, BINS, Separator, Streamer, SrtError, half_to_float,  # noqa: F401
+from .api import (COEFF_FLOATS, FFTSIZE, HOPSIZE, BINS, Separator, CliSeparator, Streamer, SrtError, half_to_float,  # noqa: F401
                   lib_path, load_library, exported_symbols, HEADER_SYMBOLS)

@@ -15,7 +15,7 @@ COEFF_FLOATS = 9822725
 
 # every symbol include/*.h declares (checked by the CPU test-suite against the built library)
 HEADER_SYMBOLS = {
-    "srt_b200.h": ["srt_create", "srt_destroy", "srt_last_error", "srt_half_to_float", "srt_unet_host",
+    "srt_b200.h": ["srt_create", "srt_create_cli", "srt_output_pairs", "srt_destroy", "srt_last_error", "srt_half_to_float", "srt_unet_host",
                    "srt_unet_device", "srt_separate_batch", "srt_separate_batch_async", "srt_batch_wait",
                    "srt_separate_device", "srt_stft_rows",
                    "srt_stft_host", "srt_istft_host", "srt_launch_count", "srt_last_timing", "srt_set_timing",
@@ -58,6 +58,8 @@ def load_library():
     lib.srt_last_error.restype = C.c_char_p
     lib.srt_create.argtypes = [C.POINTER(_Config), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.srt_destroy.argtypes = [C.c_void_p]
+    lib.srt_create_cli.argtypes = [C.POINTER(_Config), C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.srt_output_pairs.argtypes = [C.c_void_p]
     lib.srt_unet_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.srt_unet_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.srt_separate_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -257,6 +259,39 @@ class Separator:
 
     def synchronize(self):
         self._check(self.lib.srt_synchronize(self.h))
+
+
+class CliSeparator(Separator):
+    """The CLI's output modes (Executable/main.c:776-970) as one device call (srt_create_cli).
+
+    n_outputs = 2: nets = [vocal coeff]            -> separate() returns [vocal, accompaniment = input - vocal]
+    n_outputs = 3: nets = [drum coeff, vocal coeff] -> [drum, vocal, accompaniment] (drum net, then the vocal net on
+    the residual spectrum).  The activations are the ones main.c picks (drum: ELU, vocal: LeakyReLU/ReLU).
+    separate(streams, unaffected=[w]) takes the single unaffectedWeight of main.c:773.
+    """
+
+    def __init__(self, coeffs, n_outputs, time_step, bin_limit, max_images=1, max_batch_images=0, device=0,
+                 conv_impl=None, cuda_stream=None):
+        self.lib = load_library()
+        if conv_impl is None:
+            conv_impl = 1 if os.environ.get("SRT_CONV_IMPL", "") == "simt" else 0
+        if len(coeffs) != n_outputs - 1:
+            raise SrtError("n_outputs = 2 takes one net (vocal), n_outputs = 3 two (drum, vocal)")
+        cfg = _Config(device, 1, time_step, bin_limit, max_images, max_batch_images, 0, conv_impl, cuda_stream)
+        self.T, self.F = time_step, bin_limit
+        self.max_images = max_images
+        blobs = [np.ascontiguousarray(c, np.float32) for c in coeffs]
+        for c in blobs:
+            if c.size != COEFF_FLOATS:
+                raise SrtError("each net must be one spleeterCoeff blob of 9822725 floats")
+        cp = (C.c_void_p * len(blobs))(*[c.ctypes.data for c in blobs])
+        h = C.c_void_p()
+        self._check(self.lib.srt_create_cli(C.byref(cfg), int(n_outputs), cp, C.byref(h)))
+        self.h = h
+        self.S = self.lib.srt_output_pairs(self.h)   # output pairs per stream
+
+    def process_spleeter(self, x):
+        raise SrtError("a CLI-mode context only offers the full path")
 
 
 class Streamer:

@@ -155,6 +155,11 @@ struct srt_ctx {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     int last_Bv = 0;
+    // CLI output modes (srt_create_cli): 0 = one output pair per net; 2 = [vocal, input - vocal] (main.c:776-844);
+    // 3 = [drum, vocal, accompaniment] cascade (main.c:845-970) whose second net lives in `next`
+    int cli_mode = 0;
+    srt_ctx* next = nullptr;      // owned; enqueues on this context's stream
+    int pairs() const { return cli_mode ? cli_mode : S; }
 };
 
 template <class Tp>
@@ -227,6 +232,7 @@ extern "C" void srt_destroy(srt_ctx* c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->next) { srt_destroy(c->next); c->next = nullptr; }
     for (void* p : c->allocs) cudaFree(p);
     if (c->d_meta_base) cudaFree(c->d_meta_base);
     if (c->h_meta_base) cudaFreeHost(c->h_meta_base);
@@ -593,6 +599,34 @@ extern "C" int srt_create(const srt_config* cfg, const float* const* coeffs, con
     return 0;
 }
 
+// The CLI's output modes (Executable/main.c:776-970) as device-resident contexts: one single-net context per cascade
+// stage, the second stage enqueuing on the first one's stream.  Net roles and activations as main.c: the drum net is
+// coeffProvPtr2 with stemMode 1 (:858), the vocal net coeffProvPtr1 with stemMode 0 (:782, :911).
+extern "C" int srt_create_cli(const srt_config* cfg, int n_outputs, const float* const* coeffs, srt_ctx** out)
+{
+    if (!cfg || !out || !coeffs) return fail(SRT_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (n_outputs != 2 && n_outputs != 3) return fail(SRT_ERR_ARG, "n_outputs must be 2 or 3 (main.c:776, 845), got %d", n_outputs);
+    srt_config c1 = *cfg;
+    c1.n_stems = 1;
+    const int mode_first = n_outputs == 3 ? 1 : 0;
+    srt_ctx* a = nullptr;
+    int r = srt_create(&c1, coeffs, &mode_first, &a);
+    if (r) return r;
+    a->cli_mode = n_outputs;
+    if (n_outputs == 3) {
+        srt_config c2 = c1;
+        c2.cuda_stream = (void*)a->stream;
+        const int mode_second = 0;
+        if ((r = srt_create(&c2, coeffs + 1, &mode_second, &a->next))) {
+            std::string keep = g_err; srt_destroy(a); g_err = keep;
+            return r;
+        }
+    }
+    *out = a;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // U-Net on Bv images whose magnitudes sit at d_mag (layout [Bv][T][F][2]); masks go to
 // mask_base[s][mask_img0 + b] with `mask_stride` images between stems.
@@ -804,7 +838,7 @@ static int commit_meta(srt_ctx* c, size_t bytes)
 static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* const* d_pcmR, const size_t* n_samples,
                          int n_streams, const float* unaffected, float* const* d_out, int front_pad)
 {
-    const int T = c->T, S = c->S;
+    const int T = c->T, S = c->S, P = c->pairs();
     BatchMeta m;
     for (int i = 0; i < n_streams; i++) {
         if (n_samples[i] == 0 || n_samples[i] > (size_t)1 << 30) return fail(SRT_ERR_ARG, "stream %d: bad length", i);
@@ -821,13 +855,13 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     if (m.total > c->NB) return fail(SRT_ERR_CAPACITY, "batch needs %d tiles > max_batch_images %d", m.total, c->NB);
     // ---- metadata block: [pcmL ptrs][pcmR ptrs][out ptrs][n][nfr][img0][imgs]
     const size_t o_pl = 0, o_pr = o_pl + 8 * (size_t)n_streams, o_out = o_pr + 8 * (size_t)n_streams;
-    const size_t o_n = o_out + 8 * (size_t)n_streams * S * 2, o_nfr = o_n + 4 * (size_t)n_streams, o_i0 = o_nfr + 4 * (size_t)n_streams;
+    const size_t o_n = o_out + 8 * (size_t)n_streams * P * 2, o_nfr = o_n + 4 * (size_t)n_streams, o_i0 = o_nfr + 4 * (size_t)n_streams;
     const size_t o_img = (o_i0 + 4 * (size_t)n_streams + 7) & ~(size_t)7, total_b = o_img + sizeof(ImgDesc) * m.imgs.size();
     int r = ensure_meta(c, total_b);
     if (r) return r;
     std::memcpy(c->h_meta + o_pl, d_pcmL, 8 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_pr, d_pcmR, 8 * (size_t)n_streams);
-    std::memcpy(c->h_meta + o_out, d_out, 8 * (size_t)n_streams * S * 2);
+    std::memcpy(c->h_meta + o_out, d_out, 8 * (size_t)n_streams * P * 2);
     std::memcpy(c->h_meta + o_n, m.n.data(), 4 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_nfr, m.nfr.data(), 4 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_i0, m.img0.data(), 4 * (size_t)n_streams);
@@ -857,36 +891,81 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     // ---- mask * spectrum -> inverse FFT -> window -> overlap-add -> un-framing, one fused kernel
     // (SRT_FUSED_OLA=0 selects the two-kernel path through the scratch frames, kept for the tier-A istft())
     const char* fo = getenv("SRT_FUSED_OLA");
-    if (!(fo && atoi(fo) == 0)) {
+    const bool fused = !(fo && atoi(fo) == 0);
+    if (c->cli_mode && !fused) return fail(SRT_ERR_STATE, "the CLI output modes need the fused iSTFT+OLA kernel (unset SRT_FUSED_OLA)");
+    int max_fr = 0;
+    for (int i = 0; i < n_streams; i++) max_fr = std::max(max_fr, m.nfr[i]);
+    // Hops per CTA: a CTA spends h + 3 transforms on h hops (3 warm-up frames of overlap), and the grid runs
+    // in waves of 2 CTAs per SM (128 registers x 256 threads).  Pick the h that minimises waves x (h + 3):
+    // small h for a single stream (fill the SMs), large h for a full batch (amortise the warm-up) while
+    // keeping the last wave full.  SRT_ISTFT_HOPS overrides.
+    auto hops_per_cta = [&](int transforms) {
+        const long long slots = 2LL * c->sm_count;
+        long long best_cost = -1;
+        int best_h = 16;
+        for (int h = 4; h <= 64; h++) {
+            long long ctas = 0;
+            for (int i = 0; i < n_streams; i++) ctas += (m.nfr[i] + h - 1) / h;
+            ctas *= transforms;
+            const long long cost = ((ctas + slots - 1) / slots) * (h + 3);
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_h = h; }
+        }
+        const char* he = getenv("SRT_ISTFT_HOPS");
+        return he ? std::max(1, atoi(he)) : best_h;
+    };
+    // one fused synthesis launch: `transforms` inverse transforms per frame, the first `masked` of them through
+    // the masks of `src`'s nets, writing output pairs pair_first...
+    auto synthesis = [&](srt_ctx* src, int transforms, int masked, int pair_first) {
         Timed t(c, 14);
         IstftOlaParams p{};
-        p.spec = c->d_spec; p.mask = c->d_mask;
+        p.spec = src->d_spec; p.mask = src->d_mask;
         p.stream_img0 = (const int*)(c->d_meta + o_i0); p.n_frames = d_nfr; p.n_samples = d_n;
         p.postwin = c->d_postwin; p.twiddle = c->d_twiddle; p.out = (float* const*)(c->d_meta + o_out);
-        for (int s = 0; s < S; s++) p.unaffected[s] = unaffected ? unaffected[s] : 0.1f;
-        p.T = T; p.F = c->F; p.S = S; p.mask_stem_stride = c->NB; p.stream_first = 0; p.front_pad = front_pad;
-        int max_fr = 0;
-        for (int i = 0; i < n_streams; i++) max_fr = std::max(max_fr, m.nfr[i]);
-        // Hops per CTA: a CTA spends h + 3 transforms on h hops (3 warm-up frames of overlap), and the grid runs
-        // in waves of 2 CTAs per SM (128 registers x 256 threads).  Pick the h that minimises waves x (h + 3):
-        // small h for a single stream (fill the SMs), large h for a full batch (amortise the warm-up) while
-        // keeping the last wave full.  SRT_ISTFT_HOPS overrides.
-        {
-            const long long slots = 2LL * c->sm_count;
-            long long best_cost = -1;
-            int best_h = 16;
-            for (int h = 4; h <= 64; h++) {
-                long long ctas = 0;
-                for (int i = 0; i < n_streams; i++) ctas += (m.nfr[i] + h - 1) / h;
-                ctas *= S;
-                const long long cost = ((ctas + slots - 1) / slots) * (h + 3);
-                if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best_h = h; }
-            }
-            const char* he = getenv("SRT_ISTFT_HOPS");
-            p.hops_per_cta = he ? std::max(1, atoi(he)) : best_h;
-        }
+        for (int s = 0; s < masked; s++) p.unaffected[s] = c->cli_mode ? (unaffected ? unaffected[0] : 0.1f) : (unaffected ? unaffected[s] : 0.1f);
+        p.T = T; p.F = c->F; p.S = transforms; p.S_masked = masked; p.out_pairs = P; p.pair_first = pair_first;
+        p.mask_stem_stride = c->NB; p.stream_first = 0; p.front_pad = front_pad;
+        p.hops_per_cta = hops_per_cta(transforms);
         launch_istft_ola(p, n_streams, max_fr, c->stream);
         c->launches++;
+    };
+    auto difference = [&](bool from_pcm, int dst_pair, int sub_pair) {
+        Timed t(c, 15);
+        DiffParams p{};
+        p.pcmL = from_pcm ? (const float* const*)(c->d_meta + o_pl) : nullptr;
+        p.pcmR = from_pcm ? (const float* const*)(c->d_meta + o_pr) : nullptr;
+        p.out = (float* const*)(c->d_meta + o_out);
+        p.n_samples = d_n;
+        p.out_pairs = P; p.dst_pair = dst_pair; p.sub_pair = sub_pair;
+        p.n_streams = n_streams; p.max_samples = (int)m.max_n;
+        launch_diff(p, c->stream);
+        c->launches++;
+    };
+    if (c->cli_mode == 2) {
+        // vocal, then accompaniment = input - vocal in the time domain (main.c:782-794)
+        synthesis(c, 1, 1, 0);
+        difference(true, 1, 0);
+    } else if (c->cli_mode == 3) {
+        // drum net -> residual spectrum -> vocal net on the residual -> accompaniment = residual - vocal (main.c:845-927)
+        srt_ctx* n = c->next;
+        synthesis(c, 1, 1, 0);
+        {
+            Timed t(c, 13);
+            ResidualParams p{};
+            p.spec_in = c->d_spec; p.mask_in = c->d_mask; p.imgs = d_imgs; p.n_frames = d_nfr;
+            p.spec_out = n->d_spec; p.mag = n->d_mag; p.mag_lo_off = (size_t)n->NB * T * c->F * 2;
+            p.unaffected = unaffected ? unaffected[0] : 0.1f;
+            p.T = T; p.F = c->F; p.n_img = m.total;
+            launch_residual(p, c->stream);
+            c->launches++;
+        }
+        for (int i0 = 0; i0 < m.total; i0 += n->B) {
+            const int Bv = std::min(n->B, m.total - i0);
+            if ((r = run_unet(n, i0, Bv, n->d_mask, n->NB, i0))) return r;
+        }
+        synthesis(n, 2, 1, 1);      // pair 1 = vocal (masked), pair 2 = the residual itself (main.c:881)
+        difference(false, 2, 1);
+    } else if (fused) {
+        synthesis(c, S, S, 0);
     } else {
     int s0 = 0;
     while (s0 < n_streams) {
@@ -951,6 +1030,7 @@ static int batch_wait_slot(srt_ctx* c, int slot);
 static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
                          int n_streams, const float* unaffected, float* const* stems_out)
 {
+    const int P = c->pairs();
     if (!c->s_in) {
         CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
@@ -965,7 +1045,7 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
     }
     size_t tot = 0;
     for (int i = 0; i < n_streams; i++) tot += (n_samples[i] + 3) & ~(size_t)3;
-    if (tot * 2 > c->bpcm_cap[slot] || tot * 2 * c->S > c->bout_cap[slot]) {
+    if (tot * 2 > c->bpcm_cap[slot] || tot * 2 * P > c->bout_cap[slot]) {
         // grow every slot at once, so only the first call of a new size pays for allocation
         for (int i = 0; i < kBatchSlots; i++) {
             int r = batch_wait_slot(c, i);
@@ -981,24 +1061,24 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
                 CK(cudaMalloc((void**)&c->d_bpcm[i], tot * 2 * 4));
                 c->bpcm_cap[i] = tot * 2;
             }
-            if (tot * 2 * c->S > c->bout_cap[i]) {
+            if (tot * 2 * P > c->bout_cap[i]) {
                 if (c->d_bout[i]) cudaFree(c->d_bout[i]);
                 c->d_bout[i] = nullptr; c->bout_cap[i] = 0;
-                CK(cudaMalloc((void**)&c->d_bout[i], tot * 2 * c->S * 4));
-                c->bout_cap[i] = tot * 2 * c->S;
+                CK(cudaMalloc((void**)&c->d_bout[i], tot * 2 * P * 4));
+                c->bout_cap[i] = tot * 2 * P;
             }
         }
     }
     float* const d_pcm = c->d_bpcm[slot];
     float* const d_out = c->d_bout[slot];
     std::vector<const float*> dl(n_streams), dr(n_streams);
-    std::vector<float*> dout((size_t)n_streams * c->S * 2);
+    std::vector<float*> dout((size_t)n_streams * P * 2);
     size_t off = 0;
     for (int i = 0; i < n_streams; i++) {
         const size_t np = (n_samples[i] + 3) & ~(size_t)3;
         dl[i] = d_pcm + off * 2;
         dr[i] = d_pcm + off * 2 + np;
-        for (int q = 0; q < c->S * 2; q++) dout[(size_t)i * c->S * 2 + q] = d_out + off * 2 * c->S + (size_t)q * np;
+        for (int q = 0; q < P * 2; q++) dout[(size_t)i * P * 2 + q] = d_out + off * 2 * P + (size_t)q * np;
         off += np;
     }
     // Groups shorten the latency of a lone call (the first download starts after 1/groups of the kernels) but
@@ -1049,13 +1129,13 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
         const int i0 = g * per, i1 = std::min(n_streams, i0 + per);
         if (i0 >= i1) break;
         CK(cudaStreamWaitEvent(c->stream, c->ev_in[g], 0));
-        int r = separate_core(c, dl.data() + i0, dr.data() + i0, n_samples + i0, i1 - i0, unaffected, dout.data() + (size_t)i0 * c->S * 2, kFFT);
+        int r = separate_core(c, dl.data() + i0, dr.data() + i0, n_samples + i0, i1 - i0, unaffected, dout.data() + (size_t)i0 * P * 2, kFFT);
         if (r) return r;
         CK(cudaEventRecord(c->ev_c[g], c->stream));
         CK(cudaStreamWaitEvent(c->s_out, c->ev_c[g], 0));
         for (int i = i0; i < i1; i++)
-            for (int q = 0; q < c->S * 2; q++)
-                add(runs, stems_out[(size_t)i * c->S * 2 + q], dout[(size_t)i * c->S * 2 + q], n_samples[i] * 4);
+            for (int q = 0; q < P * 2; q++)
+                add(runs, stems_out[(size_t)i * P * 2 + q], dout[(size_t)i * P * 2 + q], n_samples[i] * 4);
         CK(flush(runs, cudaMemcpyDeviceToHost, c->s_out));
     }
     CK(cudaEventRecord(c->ev_cdone[slot], c->stream));
@@ -1230,7 +1310,8 @@ extern "C" int srt_istft_host(srt_ctx* c, const float* reL, const float* imL, co
 // ------------------------------------------------------------------------------------------
 // introspection
 // ------------------------------------------------------------------------------------------
-extern "C" long long srt_launch_count(const srt_ctx* c) { return c ? c->launches : 0; }
+extern "C" long long srt_launch_count(const srt_ctx* c) { return c ? c->launches + (c->next ? c->next->launches : 0) : 0; }
+extern "C" int srt_output_pairs(const srt_ctx* c) { return c ? c->pairs() : 0; }
 extern "C" int srt_set_timing(srt_ctx* c, int enable)
 {
     if (!c) return SRT_ERR_STATE;
@@ -1238,6 +1319,7 @@ extern "C" int srt_set_timing(srt_ctx* c, int enable)
     c->timing = false;
     reset_spans(c);
     c->timing = enable != 0;
+    if (c->next) srt_set_timing(c->next, enable);
     return 0;
 }
 extern "C" int srt_last_timing(const srt_ctx* c, int which, float* ms_out)
@@ -1250,6 +1332,11 @@ extern "C" int srt_last_timing(const srt_ctx* c, int which, float* ms_out)
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) tot += ms;
         }
+    if (c->next) {   // second stage of the cascade
+        float more = 0.f;
+        srt_last_timing(c->next, which, &more);
+        tot += more;
+    }
     *ms_out = tot;
     return 0;
 }

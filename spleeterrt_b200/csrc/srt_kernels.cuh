@@ -190,13 +190,44 @@ struct IstftOlaParams {
     const float2* twiddle;
     float* const* out;            // [stream][S*2] planar outputs
     float unaffected[8];
-    int T, F, S;
+    int T, F, S;                  // S = inverse transforms per frame (grid.y)
+    int S_masked;                 // transforms s < S_masked apply stem s's mask; the others are the plain inverse transform (main.c:881)
+    int out_pairs;                // (L, R) pointer pairs per stream in `out` (>= S; the CLI modes keep extra pairs)
+    int pair_first;               // transform s writes pair pair_first + s
     int mask_stem_stride;
     int stream_first;
     int front_pad;
     int hops_per_cta;
 };
 void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cudaStream_t st);
+
+// Second stage of the CLI's 3-output cascade (main.c:849-865, 911): residual spectrum = spec - mask*spec of the first
+// net (bins >= F: spec - unaffected*spec), and the magnitudes of that residual for the second net.
+struct ResidualParams {
+    const float4* spec_in;        // first stage: [n_img][T][2049]
+    const float* mask_in;         // first stage, stem 0: [n_img][T][F][2]
+    const ImgDesc* imgs;
+    const int* n_frames;          // per stream
+    float4* spec_out;             // [n_img][T][2049]
+    float* mag;                   // space-to-depth hi part, lo at + mag_lo_off (as StftParams)
+    size_t mag_lo_off;
+    float unaffected;
+    int T, F, n_img;
+};
+void launch_residual(const ResidualParams& p, cudaStream_t st);
+
+// Time-domain differences of the CLI's output modes: pair `dst_pair` of every stream becomes a - (pair `sub_pair`),
+// with a = the stream's input PCM (2 outputs: accompaniment = input - vocal, main.c:790-794) or pair `dst_pair`
+// itself (3 outputs: accompaniment = (accompaniment + vocal) - vocal, main.c:923-927).
+struct DiffParams {
+    const float* const* pcmL;     // per stream, or nullptr: a = the destination pair
+    const float* const* pcmR;
+    float* const* out;            // [stream][out_pairs * 2]
+    const int* n_samples;
+    int out_pairs, dst_pair, sub_pair;
+    int n_streams, max_samples;
+};
+void launch_diff(const DiffParams& p, cudaStream_t st);
 
 // launchers (defined in the .cu files)
 void launch_conv_tc(const ConvParams& p, cudaStream_t st);

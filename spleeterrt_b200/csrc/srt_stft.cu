@@ -9,6 +9,8 @@
 //
 // Conventions kept from the reference: re = Re FFT(x*hann)/4096,
 // im = -Im FFT(x*hann)/4096 (conjugate), magnitude = hypot(re, im) * 4096.
+#include <algorithm>
+
 #include "srt_fft.cuh"
 #include "srt_kernels.cuh"
 #include "srt_ptx.cuh"
@@ -164,9 +166,10 @@ __global__ void __launch_bounds__(kFftThreads, 2) istft_ola_kernel(const IstftOl
     const int h1 = min(h0 + p.hops_per_cta, nfr);
     const int j = threadIdx.x;
     const int n = p.n_samples[st], img0 = p.stream_img0[st];
-    float* outL = p.out[(size_t)st * p.S * 2 + s * 2];
-    float* outR = p.out[(size_t)st * p.S * 2 + s * 2 + 1];
-    const float uw = p.unaffected[s];
+    float* outL = p.out[((size_t)st * p.out_pairs + p.pair_first + s) * 2];
+    float* outR = p.out[((size_t)st * p.out_pairs + p.pair_first + s) * 2 + 1];
+    const bool masked = s < p.S_masked;   // else: the plain inverse transform of the spectrum (main.c:881)
+    const float uw = masked ? p.unaffected[s] : 1.0f;
     float w[16];
     float2 acc[16];
 #pragma unroll
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(kFftThreads, 2) istft_ola_kernel(const IstftOl
     for (int f = max(h0 - 3, 0); f < h1; f++) {
         const int img = img0 + f / p.T, t = f % p.T;
         const float4* srow = p.spec + ((size_t)img * p.T + t) * kBins;
-        const float2* mrow = reinterpret_cast<const float2*>(p.mask) + (((size_t)s * p.mask_stem_stride + img) * p.T + t) * p.F;
+        const float2* mrow = reinterpret_cast<const float2*>(p.mask) + (((size_t)(masked ? s : 0) * p.mask_stem_stride + img) * p.T + t) * p.F;
         float2 v[16];
 #pragma unroll
         for (int r = 0; r < 16; r++) {
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kFftThreads, 2) istft_ola_kernel(const IstftOl
             const int kk = k <= kFFT / 2 ? k : kFFT - k;
             const float4 sp = srow[kk];
             float mL = uw, mR = uw;
-            if (kk < p.F) { const float2 m = mrow[kk]; mL = m.x; mR = m.y; }
+            if (masked && kk < p.F) { const float2 m = mrow[kk]; mL = m.x; mR = m.y; }
             const float xlr = sp.x * mL, xli = -(sp.y * mL), xrr = sp.z * mR, xri = -(sp.w * mR);
             float2 z;
             if (k <= kFFT / 2) z = make_float2(xlr - xri, xli + xrr);
@@ -219,6 +222,64 @@ void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cu
     if (n_streams == 0 || max_frames == 0) return;
     dim3 grid((max_frames + p.hops_per_cta - 1) / p.hops_per_cta, p.S, n_streams);
     istft_ola_kernel<<<grid, kFftThreads, 0, st>>>(p);
+}
+
+// =========================================================================================
+// Cascade stage 2 (main.c:849-865, 911): residual = spec - mask * spec, and its magnitudes.  One CTA per
+// (tile image, frame), like stft_kernel; the subtraction is done on the products the reference forms
+// (orig - re*mask), not on (1 - mask).
+// =========================================================================================
+__global__ void __launch_bounds__(256) residual_kernel(const ResidualParams p)
+{
+    const int img = blockIdx.x / p.T, t = blockIdx.x % p.T;
+    const ImgDesc d = p.imgs[img];
+    const bool live = d.f0 + t < p.n_frames[d.stream];
+    const float4* in = p.spec_in + ((size_t)img * p.T + t) * kBins;
+    const float2* mrow = reinterpret_cast<const float2*>(p.mask_in) + ((size_t)img * p.T + t) * p.F;
+    float4* out = p.spec_out + ((size_t)img * p.T + t) * kBins;
+    float2* mimg = reinterpret_cast<float2*>(p.mag) + (size_t)img * p.T * p.F;
+    for (int k = threadIdx.x; k < kBins; k += 256) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+            const float4 sp = in[k];
+            float mL = p.unaffected, mR = p.unaffected;
+            if (k < p.F) { const float2 m = mrow[k]; mL = m.x; mR = m.y; }
+            // two roundings like the reference (product stored, then subtracted), not one FMA
+            o = make_float4(__fsub_rn(sp.x, __fmul_rn(sp.x, mL)), __fsub_rn(sp.y, __fmul_rn(sp.y, mL)), __fsub_rn(sp.z, __fmul_rn(sp.z, mR)),
+                            __fsub_rn(sp.w, __fmul_rn(sp.w, mR)));
+        }
+        out[k] = o;
+        if (k < p.F) {
+            const float mL = hypotf(o.x, o.y) * (float)kFFT, mR = hypotf(o.z, o.w) * (float)kFFT;
+            const float hL = ptx::rna_tf32(mL), hR = ptx::rna_tf32(mR);
+            const size_t mi = mag_s2d_index(p.T, p.F, t, k);
+            mimg[mi] = make_float2(hL, hR);
+            mimg[mi + p.mag_lo_off / 2] = make_float2(mL - hL, mR - hR);
+        }
+    }
+}
+
+void launch_residual(const ResidualParams& p, cudaStream_t st)
+{
+    if (p.n_img == 0) return;
+    residual_kernel<<<p.n_img * p.T, 256, 0, st>>>(p);
+}
+
+__global__ void __launch_bounds__(256) diff_kernel(const DiffParams p)
+{
+    const int st = blockIdx.z, c = blockIdx.y;
+    const int n = p.n_samples[st];
+    float* dst = p.out[((size_t)st * p.out_pairs + p.dst_pair) * 2 + c];
+    const float* b = p.out[((size_t)st * p.out_pairs + p.sub_pair) * 2 + c];
+    const float* a = p.pcmL ? (c ? p.pcmR[st] : p.pcmL[st]) : dst;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] = a[i] - b[i];
+}
+
+void launch_diff(const DiffParams& p, cudaStream_t st)
+{
+    if (p.n_streams == 0 || p.max_samples == 0) return;
+    dim3 grid(std::min((p.max_samples + 255) / 256, 1024), 2, p.n_streams);
+    diff_kernel<<<grid, 256, 0, st>>>(p);
 }
 
 // =========================================================================================
