@@ -79,6 +79,22 @@ const char* srt_last_error(void);
  * denormals flushed to zero (f32Decompress, main.c:423-434).  Host side, exact. */
 void srt_half_to_float(const uint16_t* in, float* out, size_t n);
 
+/* ---- weight files (host side, exact) ----------------------------------------------------------
+ * srt_load_coeff_dat: one fp32 spleeterCoeff dump of exactly 39 290 900 bytes, the files the VST reads with one
+ *   fread (VST/Source/PluginProcessor.cpp:48-80: drum4stems.dat ...).  Unlike the reference a missing or short
+ *   file is an error (SRT_ERR_ARG), not uninitialised weights.  srt_save_coeff_dat writes the same format.
+ * srt_model_fp16_nets / srt_load_model_fp16: the fp16 model blob (spleeterQuantized, Executable/spleeter.h:32-62:
+ *   consecutive nets of 9 822 725 halves); net `net` is expanded like f32Decompress (main.c:423-443).  In the
+ *   reference's model net 0 is the drum net (stemMode 1) and net 1 the vocal net (stemMode 0), main.c:759-760.
+ * srt_pack_layer: one net's weights of a tensor-core layer (0..4 = down2..down6, 5..9 = up1..up5) in the K-major,
+ *   128-byte-swizzled B-operand layout the tcgen05 kernels stream (form 0: generic kernel, form 1: row-patch kernel;
+ *   weights that are not TF32-exact get the two-term split).  out == NULL returns the size in floats. */
+int srt_load_coeff_dat(const char* path, float* coeff_out /* SRT_COEFF_FLOATS */);
+int srt_save_coeff_dat(const char* path, const float* coeff);
+int srt_model_fp16_nets(const char* path);
+int srt_load_model_fp16(const char* path, int net, float* coeff_out /* SRT_COEFF_FLOATS */);
+long long srt_pack_layer(int layer, int form, int time_step, int bin_limit, const float* coeff, float* out, size_t cap_floats);
+
 /* ---- U-Net only -------------------------------------------------------------------------
  * x: n_img images, each planar [2][T][F] like processSpleeter's input (host memory).
  * y: [n_stems][n_img][2][T][F] masks (host memory).  n_img <= max_images. */
@@ -111,6 +127,24 @@ int srt_batch_wait(srt_ctx* ctx, int ticket);
 int srt_separate_device(srt_ctx* ctx, const float* const* d_pcmL, const float* const* d_pcmR,
                         const size_t* n_samples, int n_streams, const float* unaffected,
                         float* const* d_stems_out);
+
+/* ---- interleaved frames either side of the path ------------------------------------------------
+ * The reference CLI decodes to interleaved frames and splits them on the host (channel_splitFloat, main.c:53-76,
+ * 767), duplicates a mono channel (main.c:768-769), and joins each result back into interleaved frames for the
+ * float32 WAV writer (channel_joinFloat, main.c:806, 815-824).  These entry points take and return those buffers
+ * directly: the split is the stride of the STFT framer's loads, the join the stride of the overlap-add stores.
+ *   pcm[i]       n_samples[i] frames of channels[i] (1 or 2) interleaved floats
+ *   out[i * pairs + q]   n_samples[i] interleaved stereo frames (2 * n_samples[i] floats) of output pair q,
+ *                pairs = srt_output_pairs(ctx)
+ * Results are bit-identical to the planar entry points.  Device pointers must be 4-byte aligned. */
+int srt_separate_batch_interleaved(srt_ctx* ctx, const float* const* pcm, const int* channels, const size_t* n_samples,
+                                   int n_streams, const float* unaffected, float* const* out);
+int srt_separate_batch_interleaved_async(srt_ctx* ctx, const float* const* pcm, const int* channels,
+                                         const size_t* n_samples, int n_streams, const float* unaffected,
+                                         float* const* out, int* ticket_out);
+int srt_separate_device_interleaved(srt_ctx* ctx, const float* const* d_pcm, const int* channels,
+                                    const size_t* n_samples, int n_streams, const float* unaffected,
+                                    float* const* d_out);
 
 /* ---- transforms (Executable/stftFix.c) --------------------------------------------------
  * srt_stft_host: rows = ceil(n/1024); planes are [rows][4096] host buffers supplied by the

@@ -15,9 +15,11 @@ COEFF_FLOATS = 9822725
 
 # every symbol include/*.h declares (checked by the CPU test-suite against the built library)
 HEADER_SYMBOLS = {
-    "srt_b200.h": ["srt_create", "srt_create_cli", "srt_output_pairs", "srt_destroy", "srt_last_error", "srt_half_to_float", "srt_unet_host",
+    "srt_b200.h": ["srt_create", "srt_create_cli", "srt_output_pairs", "srt_destroy", "srt_last_error", "srt_half_to_float",
+                   "srt_load_coeff_dat", "srt_save_coeff_dat", "srt_model_fp16_nets", "srt_load_model_fp16", "srt_pack_layer", "srt_unet_host",
                    "srt_unet_device", "srt_separate_batch", "srt_separate_batch_async", "srt_batch_wait",
-                   "srt_separate_device", "srt_stft_rows",
+                   "srt_separate_device", "srt_separate_batch_interleaved", "srt_separate_batch_interleaved_async",
+                   "srt_separate_device_interleaved", "srt_stft_rows",
                    "srt_stft_host", "srt_istft_host", "srt_launch_count", "srt_last_timing", "srt_set_timing",
                    "srt_debug_tensor", "srt_host_alloc", "srt_host_free", "srt_synchronize",
                    "srt_stream_create", "srt_stream_process", "srt_stream_destroy", "srt_stream_launch_count"],
@@ -66,6 +68,9 @@ def load_library():
     lib.srt_separate_device.argtypes = lib.srt_separate_batch.argtypes
     lib.srt_separate_batch_async.argtypes = lib.srt_separate_batch.argtypes + [C.POINTER(C.c_int)]
     lib.srt_batch_wait.argtypes = [C.c_void_p, C.c_int]
+    lib.srt_separate_batch_interleaved.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.srt_separate_device_interleaved.argtypes = lib.srt_separate_batch_interleaved.argtypes
+    lib.srt_separate_batch_interleaved_async.argtypes = lib.srt_separate_batch_interleaved.argtypes + [C.POINTER(C.c_int)]
     lib.srt_stft_rows.restype = C.c_size_t
     lib.srt_stft_rows.argtypes = [C.c_size_t]
     lib.srt_stft_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
@@ -81,6 +86,12 @@ def load_library():
     lib.srt_host_free.argtypes = [C.c_void_p]
     lib.srt_synchronize.argtypes = [C.c_void_p]
     lib.srt_half_to_float.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.srt_load_coeff_dat.argtypes = [C.c_char_p, C.c_void_p]
+    lib.srt_save_coeff_dat.argtypes = [C.c_char_p, C.c_void_p]
+    lib.srt_model_fp16_nets.argtypes = [C.c_char_p]
+    lib.srt_load_model_fp16.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    lib.srt_pack_layer.restype = C.c_longlong
+    lib.srt_pack_layer.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
     lib.srt_stream_create.argtypes = [C.POINTER(_Config), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.srt_stream_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.srt_stream_destroy.argtypes = [C.c_void_p]
@@ -108,6 +119,50 @@ def half_to_float(halves):
 TIMING_CATEGORIES = {"down2": 0, "down3": 1, "down4": 2, "down5": 3, "down6": 4, "up1": 5, "up2": 6, "up3": 7,
                      "up4": 8, "up5": 9, "down1": 10, "up6": 11, "up7": 12, "stft": 13, "istft": 14, "ola": 15,
                      "h2d": 16, "d2h": 17}
+
+
+def _host_check(lib, rc):
+    if rc < 0:
+        raise SrtError(f"srt error {rc}: {lib.srt_last_error().decode()}")
+    return rc
+
+
+def load_coeff_dat(path):
+    """One fp32 spleeterCoeff dump (the VST's *.dat, PluginProcessor.cpp:48-80) -> float32[9822725]."""
+    lib = load_library()
+    out = np.empty(COEFF_FLOATS, np.float32)
+    _host_check(lib, lib.srt_load_coeff_dat(os.fsencode(path), out.ctypes.data))
+    return out
+
+
+def save_coeff_dat(path, coeff):
+    lib = load_library()
+    coeff = np.ascontiguousarray(coeff, np.float32)
+    if coeff.size != COEFF_FLOATS:
+        raise SrtError("a net is one spleeterCoeff blob of 9822725 floats")
+    _host_check(lib, lib.srt_save_coeff_dat(os.fsencode(path), coeff.ctypes.data))
+
+
+def load_model_fp16(path):
+    """The fp16 model blob (spleeterQuantized) -> list of float32[9822725], one per net (main.c:435-443)."""
+    lib = load_library()
+    nets = _host_check(lib, lib.srt_model_fp16_nets(os.fsencode(path)))
+    out = []
+    for k in range(nets):
+        w = np.empty(COEFF_FLOATS, np.float32)
+        _host_check(lib, lib.srt_load_model_fp16(os.fsencode(path), k, w.ctypes.data))
+        out.append(w)
+    return out
+
+
+def pack_layer(coeff, layer, time_step, bin_limit, form=0):
+    """Packed tcgen05 B-operand blob of one tensor-core layer (srt_pack_layer)."""
+    lib = load_library()
+    coeff = np.ascontiguousarray(coeff, np.float32)
+    n = _host_check(lib, lib.srt_pack_layer(layer, form, time_step, bin_limit, coeff.ctypes.data, None, 0))
+    out = np.empty(n, np.float32)
+    _host_check(lib, lib.srt_pack_layer(layer, form, time_step, bin_limit, coeff.ctypes.data, out.ctypes.data, out.size))
+    return out
 
 
 class Separator:
@@ -194,6 +249,21 @@ class Separator:
         if unaffected is not None:
             uw = (C.c_float * self.S)(*[float(u) for u in unaffected])
         self._check(self.lib.srt_separate_batch(self.h, pl, pr, n, ns, uw, po))
+        return outs
+
+    def separate_interleaved(self, frames, unaffected=None):
+        """frames: list of float32[n][channels] (channels 1 or 2) or float32[n] (mono): interleaved frames as a WAV
+        decoder yields them (main.c:767-769).  Returns a list of float32[pairs][n][2]: interleaved stereo frames per
+        output pair, ready for a float32 WAV writer (main.c:806)."""
+        ns = len(frames)
+        X = [np.ascontiguousarray(x, np.float32).reshape(len(x), -1) for x in frames]
+        ch = (C.c_int * ns)(*[x.shape[1] for x in X])
+        n = (C.c_size_t * ns)(*[x.shape[0] for x in X])
+        pp = (C.c_void_p * ns)(*[x.ctypes.data for x in X])
+        outs = [np.empty((self.S, x.shape[0], 2), np.float32) for x in X]
+        po = (C.c_void_p * (ns * self.S))(*[o[q].ctypes.data for o in outs for q in range(self.S)])
+        uw = (C.c_float * self.S)(*[float(u) for u in unaffected]) if unaffected is not None else None
+        self._check(self.lib.srt_separate_batch_interleaved(self.h, pp, ch, n, ns, uw, po))
         return outs
 
     def separate_async(self, streams, unaffected=None):

@@ -11,7 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libspleeterrt_b200.so")
-SOURCES = ["srt_plan.cpp", "srt_ctx.cu", "srt_conv_tc.cu", "srt_conv_rp.cu", "srt_up6_tc.cu", "srt_unet_simt.cu", "srt_stft.cu", "srt_stream.cu", "srt_tier_a.cu"]
+SOURCES = ["srt_plan.cpp", "srt_weights.cpp", "srt_ctx.cu", "srt_conv_tc.cu", "srt_conv_rp.cu", "srt_up6_tc.cu", "srt_unet_simt.cu", "srt_stft.cu", "srt_stream.cu", "srt_tier_a.cu"]
 HEADERS = ["srt_plan.h", "srt_kernels.cuh", "srt_ptx.cuh", "srt_epilogue.cuh", "srt_fft.cuh", "srt_internal.h",
            "../../include/srt_b200.h", "../../include/spleeter.h", "../../include/stftFix.h", "../../include/Spleeter4Stems.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -56,5 +56,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_examples():
+    """The C hosts under examples/ (plain gcc against include/ and the in-tree library) -> examples/_build/."""
+    root = os.path.dirname(PKG)
+    out = os.path.join(root, "examples", "_build")
+    os.makedirs(out, exist_ok=True)
+    built = []
+    for name in ("main_b200", "spleeter_cli_b200"):
+        src = os.path.join(root, "examples", name + ".c")
+        exe = os.path.join(out, name)
+        if _stale(exe, [src, LIB, os.path.join(root, "include", "srt_b200.h")]):
+            subprocess.check_call(["gcc", "-O2", "-Wall", "-I", os.path.join(root, "include"), src, "-L", PKG, "-lspleeterrt_b200",
+                                   "-Wl,-rpath," + PKG, "-Wl,-rpath,$ORIGIN/../../spleeterrt_b200", "-lm", "-o", exe])
+        built.append(exe)
+    return built
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_examples())

@@ -835,8 +835,11 @@ static int commit_meta(srt_ctx* c, size_t bytes)
     return 0;
 }
 
+// pcm_stride (nullable = planar): per-stream distance in floats between consecutive samples of a channel; out_stride:
+// 1 = planar outputs, 2 = interleaved stereo frames (d_out still lists an L and an R pointer per pair, R = L + 1).
 static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* const* d_pcmR, const size_t* n_samples,
-                         int n_streams, const float* unaffected, float* const* d_out, int front_pad)
+                         int n_streams, const float* unaffected, float* const* d_out, int front_pad,
+                         const int* pcm_stride = nullptr, int out_stride = 1)
 {
     const int T = c->T, S = c->S, P = c->pairs();
     BatchMeta m;
@@ -856,7 +859,8 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     // ---- metadata block: [pcmL ptrs][pcmR ptrs][out ptrs][n][nfr][img0][imgs]
     const size_t o_pl = 0, o_pr = o_pl + 8 * (size_t)n_streams, o_out = o_pr + 8 * (size_t)n_streams;
     const size_t o_n = o_out + 8 * (size_t)n_streams * P * 2, o_nfr = o_n + 4 * (size_t)n_streams, o_i0 = o_nfr + 4 * (size_t)n_streams;
-    const size_t o_img = (o_i0 + 4 * (size_t)n_streams + 7) & ~(size_t)7, total_b = o_img + sizeof(ImgDesc) * m.imgs.size();
+    const size_t o_ps = o_i0 + 4 * (size_t)n_streams;
+    const size_t o_img = (o_ps + 4 * (size_t)n_streams + 7) & ~(size_t)7, total_b = o_img + sizeof(ImgDesc) * m.imgs.size();
     int r = ensure_meta(c, total_b);
     if (r) return r;
     std::memcpy(c->h_meta + o_pl, d_pcmL, 8 * (size_t)n_streams);
@@ -865,6 +869,7 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     std::memcpy(c->h_meta + o_n, m.n.data(), 4 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_nfr, m.nfr.data(), 4 * (size_t)n_streams);
     std::memcpy(c->h_meta + o_i0, m.img0.data(), 4 * (size_t)n_streams);
+    for (int i = 0; i < n_streams; i++) ((int*)(c->h_meta + o_ps))[i] = pcm_stride ? pcm_stride[i] : 1;
     std::memcpy(c->h_meta + o_img, m.imgs.data(), sizeof(ImgDesc) * m.imgs.size());
     if ((r = commit_meta(c, total_b))) return r;
     const ImgDesc* d_imgs = (const ImgDesc*)(c->d_meta + o_img);
@@ -877,6 +882,7 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
         p.pcmL = (const float* const*)(c->d_meta + o_pl);
         p.pcmR = (const float* const*)(c->d_meta + o_pr);
         p.n_samples = d_n; p.n_frames = d_nfr; p.imgs = d_imgs;
+        p.pcm_stride = pcm_stride ? (const int*)(c->d_meta + o_ps) : nullptr;
         p.window = c->d_window; p.twiddle = c->d_twiddle;
         p.spec = c->d_spec; p.mag = c->d_mag; p.mag_lo_off = (size_t)c->NB * T * c->F * 2;
         p.T = T; p.F = c->F; p.n_img = m.total; p.front_pad = front_pad;
@@ -892,7 +898,8 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     // (SRT_FUSED_OLA=0 selects the two-kernel path through the scratch frames, kept for the tier-A istft())
     const char* fo = getenv("SRT_FUSED_OLA");
     const bool fused = !(fo && atoi(fo) == 0);
-    if (c->cli_mode && !fused) return fail(SRT_ERR_STATE, "the CLI output modes need the fused iSTFT+OLA kernel (unset SRT_FUSED_OLA)");
+    if ((c->cli_mode || out_stride != 1) && !fused)
+        return fail(SRT_ERR_STATE, "the CLI output modes and interleaved outputs need the fused iSTFT+OLA kernel (unset SRT_FUSED_OLA)");
     int max_fr = 0;
     for (int i = 0; i < n_streams; i++) max_fr = std::max(max_fr, m.nfr[i]);
     // Hops per CTA: a CTA spends h + 3 transforms on h hops (3 warm-up frames of overlap), and the grid runs
@@ -922,7 +929,7 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
         p.stream_img0 = (const int*)(c->d_meta + o_i0); p.n_frames = d_nfr; p.n_samples = d_n;
         p.postwin = c->d_postwin; p.twiddle = c->d_twiddle; p.out = (float* const*)(c->d_meta + o_out);
         for (int s = 0; s < masked; s++) p.unaffected[s] = c->cli_mode ? (unaffected ? unaffected[0] : 0.1f) : (unaffected ? unaffected[s] : 0.1f);
-        p.T = T; p.F = c->F; p.S = transforms; p.S_masked = masked; p.out_pairs = P; p.pair_first = pair_first;
+        p.T = T; p.F = c->F; p.S = transforms; p.S_masked = masked; p.out_pairs = P; p.pair_first = pair_first; p.out_stride = out_stride;
         p.mask_stem_stride = c->NB; p.stream_first = 0; p.front_pad = front_pad;
         p.hops_per_cta = hops_per_cta(transforms);
         launch_istft_ola(p, n_streams, max_fr, c->stream);
@@ -935,6 +942,8 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
         p.pcmR = from_pcm ? (const float* const*)(c->d_meta + o_pr) : nullptr;
         p.out = (float* const*)(c->d_meta + o_out);
         p.n_samples = d_n;
+        p.pcm_stride = pcm_stride ? (const int*)(c->d_meta + o_ps) : nullptr;
+        p.out_stride = out_stride;
         p.out_pairs = P; p.dst_pair = dst_pair; p.sub_pair = sub_pair;
         p.n_streams = n_streams; p.max_samples = (int)m.max_n;
         launch_diff(p, c->stream);
@@ -1018,6 +1027,40 @@ extern "C" int srt_separate_device(srt_ctx* c, const float* const* d_pcmL, const
     return separate_core(c, d_pcmL, d_pcmR, n_samples, n_streams, unaffected, d_stems_out, kFFT);
 }
 
+// Interleaved frames either side of the path (the decoder's buffer before channel_splitFloat, main.c:767; the WAV
+// writer's buffer after channel_joinFloat, main.c:806): the split and the join are strided accesses of the STFT loads
+// and the overlap-add stores instead of host loops.
+static int check_channels(const int* channels, int n_streams)
+{
+    if (!channels) return fail(SRT_ERR_ARG, "channels is NULL");
+    for (int i = 0; i < n_streams; i++)
+        if (channels[i] != 1 && channels[i] != 2) return fail(SRT_ERR_ARG, "stream %d: %d channels (1 or 2 supported, main.c:764-769)", i, channels[i]);
+    return 0;
+}
+
+extern "C" int srt_separate_device_interleaved(srt_ctx* c, const float* const* d_pcm, const int* channels, const size_t* n_samples,
+                                               int n_streams, const float* unaffected, float* const* d_out)
+{
+    if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
+    if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
+    int r = check_channels(channels, n_streams);
+    if (r) return r;
+    CK(cudaSetDevice(c->cfg.device));
+    reset_spans(c);
+    const int P = c->pairs();
+    std::vector<const float*> L(n_streams), R(n_streams);
+    std::vector<float*> out((size_t)n_streams * P * 2);
+    for (int i = 0; i < n_streams; i++) {
+        L[i] = d_pcm[i];
+        R[i] = d_pcm[i] + (channels[i] == 2 ? 1 : 0);       // mono: both channels read the same samples (main.c:768-769)
+        for (int q = 0; q < P; q++) {
+            out[((size_t)i * P + q) * 2] = d_out[(size_t)i * P + q];
+            out[((size_t)i * P + q) * 2 + 1] = d_out[(size_t)i * P + q] + 1;
+        }
+    }
+    return separate_core(c, L.data(), R.data(), n_samples, n_streams, unaffected, out.data(), kFFT, channels, 2);
+}
+
 static int batch_wait_slot(srt_ctx* c, int slot);
 
 // Enqueues one host-pointer batch into staging slot `slot`: H2D on s_in, compute on the context's stream,
@@ -1027,8 +1070,11 @@ static int batch_wait_slot(srt_ctx* c, int slot);
 //   H2D into d_bpcm[slot]  waits for the compute that last read it        (ev_cdone[slot])
 //   compute into d_bout[slot] waits for the D2H that last read it         (ev_d2h[slot])
 // everything else (spectra, activations, masks) lives on the context's stream and is ordered by it.
+// channels != nullptr selects the interleaved formats: pcmL[i] = n_samples[i] frames of channels[i] interleaved floats
+// (pcmR unused), stems_out[i * pairs + q] = n_samples[i] interleaved stereo frames.  The staging layout is the same
+// (2 * np floats of PCM and 2 * np floats per output pair and stream), so each stream is one DMA per direction and pair.
 static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
-                         int n_streams, const float* unaffected, float* const* stems_out)
+                         int n_streams, const float* unaffected, float* const* stems_out, const int* channels = nullptr)
 {
     const int P = c->pairs();
     if (!c->s_in) {
@@ -1077,8 +1123,9 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
     for (int i = 0; i < n_streams; i++) {
         const size_t np = (n_samples[i] + 3) & ~(size_t)3;
         dl[i] = d_pcm + off * 2;
-        dr[i] = d_pcm + off * 2 + np;
-        for (int q = 0; q < P * 2; q++) dout[(size_t)i * P * 2 + q] = d_out + off * 2 * P + (size_t)q * np;
+        dr[i] = channels ? dl[i] + (channels[i] == 2 ? 1 : 0) : d_pcm + off * 2 + np;
+        for (int q = 0; q < P * 2; q++)
+            dout[(size_t)i * P * 2 + q] = channels ? d_out + off * 2 * P + (size_t)(q >> 1) * 2 * np + (q & 1) : d_out + off * 2 * P + (size_t)q * np;
         off += np;
     }
     // Groups shorten the latency of a lone call (the first download starts after 1/groups of the kernels) but
@@ -1119,8 +1166,12 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
     for (int g = 0; g < groups; g++) {
         const int i0 = g * per, i1 = std::min(n_streams, i0 + per);
         for (int i = i0; i < i1; i++) {
-            add(runs, (void*)dl[i], pcmL[i], n_samples[i] * 4);
-            add(runs, (void*)dr[i], pcmR[i], n_samples[i] * 4);
+            if (channels) {
+                add(runs, (void*)dl[i], pcmL[i], n_samples[i] * 4 * (size_t)channels[i]);
+            } else {
+                add(runs, (void*)dl[i], pcmL[i], n_samples[i] * 4);
+                add(runs, (void*)dr[i], pcmR[i], n_samples[i] * 4);
+            }
         }
         CK(flush(runs, cudaMemcpyHostToDevice, c->s_in));
         CK(cudaEventRecord(c->ev_in[g], c->s_in));
@@ -1129,13 +1180,18 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
         const int i0 = g * per, i1 = std::min(n_streams, i0 + per);
         if (i0 >= i1) break;
         CK(cudaStreamWaitEvent(c->stream, c->ev_in[g], 0));
-        int r = separate_core(c, dl.data() + i0, dr.data() + i0, n_samples + i0, i1 - i0, unaffected, dout.data() + (size_t)i0 * P * 2, kFFT);
+        int r = separate_core(c, dl.data() + i0, dr.data() + i0, n_samples + i0, i1 - i0, unaffected, dout.data() + (size_t)i0 * P * 2, kFFT,
+                              channels ? channels + i0 : nullptr, channels ? 2 : 1);
         if (r) return r;
         CK(cudaEventRecord(c->ev_c[g], c->stream));
         CK(cudaStreamWaitEvent(c->s_out, c->ev_c[g], 0));
-        for (int i = i0; i < i1; i++)
-            for (int q = 0; q < P * 2; q++)
-                add(runs, stems_out[(size_t)i * P * 2 + q], dout[(size_t)i * P * 2 + q], n_samples[i] * 4);
+        for (int i = i0; i < i1; i++) {
+            if (channels) {
+                for (int q = 0; q < P; q++) add(runs, stems_out[(size_t)i * P + q], dout[((size_t)i * P + q) * 2], n_samples[i] * 8);
+            } else {
+                for (int q = 0; q < P * 2; q++) add(runs, stems_out[(size_t)i * P * 2 + q], dout[(size_t)i * P * 2 + q], n_samples[i] * 4);
+            }
+        }
         CK(flush(runs, cudaMemcpyDeviceToHost, c->s_out));
     }
     CK(cudaEventRecord(c->ev_cdone[slot], c->stream));
@@ -1152,8 +1208,8 @@ static int batch_wait_slot(srt_ctx* c, int slot)
     return 0;
 }
 
-extern "C" int srt_separate_batch_async(srt_ctx* c, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
-                                        int n_streams, const float* unaffected, float* const* stems_out, int* ticket_out)
+static int batch_submit(srt_ctx* c, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples, int n_streams,
+                        const float* unaffected, float* const* stems_out, int* ticket_out, const int* channels)
 {
     if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
     if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
@@ -1163,7 +1219,7 @@ extern "C" int srt_separate_batch_async(srt_ctx* c, const float* const* pcmL, co
     const int slot = (int)(c->batch_seq % kBatchSlots);
     int r = batch_wait_slot(c, slot);   // one batch too many in flight: the slot's previous owner must have drained
     if (r) return r;
-    if ((r = batch_enqueue(c, slot, pcmL, pcmR, n_samples, n_streams, unaffected, stems_out))) {
+    if ((r = batch_enqueue(c, slot, pcmL, pcmR, n_samples, n_streams, unaffected, stems_out, channels))) {
         // leave nothing half-enqueued behind an error return
         cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out);
         return r;
@@ -1173,6 +1229,20 @@ extern "C" int srt_separate_batch_async(srt_ctx* c, const float* const* pcmL, co
     c->batch_seq++;
     *ticket_out = ticket;
     return 0;
+}
+
+extern "C" int srt_separate_batch_async(srt_ctx* c, const float* const* pcmL, const float* const* pcmR, const size_t* n_samples,
+                                        int n_streams, const float* unaffected, float* const* stems_out, int* ticket_out)
+{
+    return batch_submit(c, pcmL, pcmR, n_samples, n_streams, unaffected, stems_out, ticket_out, nullptr);
+}
+
+extern "C" int srt_separate_batch_interleaved_async(srt_ctx* c, const float* const* pcm, const int* channels, const size_t* n_samples,
+                                                    int n_streams, const float* unaffected, float* const* out, int* ticket_out)
+{
+    int r = check_channels(channels, n_streams < 0 ? 0 : n_streams);
+    if (r) return r;
+    return batch_submit(c, pcm, nullptr, n_samples, n_streams, unaffected, out, ticket_out, channels);
 }
 
 extern "C" int srt_batch_wait(srt_ctx* c, int ticket)
@@ -1191,6 +1261,17 @@ extern "C" int srt_separate_batch(srt_ctx* c, const float* const* pcmL, const fl
 {
     int ticket = -1;
     int r = srt_separate_batch_async(c, pcmL, pcmR, n_samples, n_streams, unaffected, stems_out, &ticket);
+    if (r) return r;
+    if ((r = srt_batch_wait(c, ticket))) return r;
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int srt_separate_batch_interleaved(srt_ctx* c, const float* const* pcm, const int* channels, const size_t* n_samples,
+                                              int n_streams, const float* unaffected, float* const* out)
+{
+    int ticket = -1;
+    int r = srt_separate_batch_interleaved_async(c, pcm, channels, n_samples, n_streams, unaffected, out, &ticket);
     if (r) return r;
     if ((r = srt_batch_wait(c, ticket))) return r;
     CK(cudaStreamSynchronize(c->stream));

@@ -138,6 +138,8 @@ struct ImgDesc {                  // one T-frame tile of one stream
 struct StftParams {
     const float* const* pcmL;     // per stream device pointers (unpadded samples)
     const float* const* pcmR;
+    const int* pcm_stride;        // per stream: floats between consecutive samples of a channel (1 planar, 2 interleaved stereo,
+                                  // 1 with pcmR == pcmL for mono, main.c:767-769), or nullptr = 1
     const int* n_samples;         // per stream
     const int* n_frames;          // per stream: padded_len / 1024 (stftFix.c:367)
     const ImgDesc* imgs;          // [n_img]
@@ -194,6 +196,7 @@ struct IstftOlaParams {
     int S_masked;                 // transforms s < S_masked apply stem s's mask; the others are the plain inverse transform (main.c:881)
     int out_pairs;                // (L, R) pointer pairs per stream in `out` (>= S; the CLI modes keep extra pairs)
     int pair_first;               // transform s writes pair pair_first + s
+    int out_stride;               // 1 = planar outputs, 2 = interleaved stereo frames (R pointer = L pointer + 1), main.c:806
     int mask_stem_stride;
     int stream_first;
     int front_pad;
@@ -223,7 +226,9 @@ struct DiffParams {
     const float* const* pcmL;     // per stream, or nullptr: a = the destination pair
     const float* const* pcmR;
     float* const* out;            // [stream][out_pairs * 2]
+    const int* pcm_stride;        // as StftParams
     const int* n_samples;
+    int out_stride;               // as IstftOlaParams
     int out_pairs, dst_pair, sub_pair;
     int n_streams, max_samples;
 };

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
     const int n = p.n_samples[d.stream];
     const float* L = p.pcmL[d.stream];
     const float* R = p.pcmR[d.stream];
+    const int ps = p.pcm_stride ? p.pcm_stride[d.stream] : 1;
     const long base = (long)f * kHop - p.front_pad;
     float2 v[16];
 #pragma unroll
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(kFftThreads) stft_kernel(const StftParams p)
         float2 x = make_float2(0.f, 0.f);
         if (si >= 0 && si < n) {
             const float w = __ldg(&p.window[i]);
-            x = make_float2(L[si] * w, R[si] * w);
+            x = make_float2(L[si * ps] * w, R[si * ps] * w);
         }
         v[r] = x;
     }
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(kFftThreads, 2) istft_ola_kernel(const IstftOl
     float* outR = p.out[((size_t)st * p.out_pairs + p.pair_first + s) * 2 + 1];
     const bool masked = s < p.S_masked;   // else: the plain inverse transform of the spectrum (main.c:881)
     const float uw = masked ? p.unaffected[s] : 1.0f;
+    const int os = p.out_stride;
     float w[16];
     float2 acc[16];
 #pragma unroll
@@ -207,7 +209,101 @@ __global__ void __launch_bounds__(kFftThreads, 2) istft_ola_kernel(const IstftOl
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const long io = (long)f * kHop + j + 256 * k - p.front_pad;
-                if (io >= 0 && io < n) { outL[io] = acc[k].x; outR[io] = acc[k].y; }
+                if (io >= 0 && io < n) { outL[io * os] = acc[k].x; outR[io * os] = acc[k].y; }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 12; r++) acc[r] = acc[r + 4];
+#pragma unroll
+        for (int r = 12; r < 16; r++) acc[r] = make_float2(0.f, 0.f);
+    }
+}
+
+// Same walk, with the next frame's rows staged by the copy engine while the current frame is transformed.
+// The register kernel above exposes one global-load round trip per frame (16 LDG.128 + 16 LDG.64 per thread in
+// front of the first butterfly; two 8-warp CTAs per SM cannot hide it: ncu r1o issue slots 56 % busy, DRAM 21 %).
+// Here one thread issues two 1-D bulk copies (spectrum row 32 784 B, mask row 8 F B) for frame f+1 right after the
+// CTA has finished reading frame f's rows, an mbarrier publishes them, and the gather of the Hermitian extension
+// reads shared memory (each bin is needed twice, for k and N-k).
+constexpr uint32_t kSpecRowBytes = kBins * sizeof(float4);
+static size_t istft_pf_smem(int F) { return sizeof(FftSmem) + kSpecRowBytes + (size_t)F * sizeof(float2) + 16; }
+
+__global__ void __launch_bounds__(kFftThreads, 2) istft_ola_pf_kernel(const IstftOlaParams p)
+{
+    extern __shared__ __align__(128) uint8_t dsm[];
+    FftSmem& sm = *reinterpret_cast<FftSmem*>(dsm);
+    const float4* sspec = reinterpret_cast<const float4*>(dsm + sizeof(FftSmem));
+    const float2* smask = reinterpret_cast<const float2*>(dsm + sizeof(FftSmem) + kSpecRowBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm + sizeof(FftSmem) + kSpecRowBytes + (size_t)p.F * sizeof(float2));
+    const int st = p.stream_first + blockIdx.z, s = blockIdx.y;
+    const int nfr = p.n_frames[st];
+    const int h0 = blockIdx.x * p.hops_per_cta;
+    if (h0 >= nfr) return;
+    const int h1 = min(h0 + p.hops_per_cta, nfr);
+    const int j = threadIdx.x;
+    const int n = p.n_samples[st], img0 = p.stream_img0[st];
+    float* outL = p.out[((size_t)st * p.out_pairs + p.pair_first + s) * 2];
+    float* outR = p.out[((size_t)st * p.out_pairs + p.pair_first + s) * 2 + 1];
+    const bool masked = s < p.S_masked;   // else: the plain inverse transform of the spectrum (main.c:881)
+    const float uw = masked ? p.unaffected[s] : 1.0f;
+    const int os = p.out_stride;
+    const int Fm = masked ? p.F : 0;      // bins below Fm take the staged mask
+    auto stage = [&](int f) {             // one thread: rows of frame f -> shared memory
+        const int img = img0 + f / p.T, t = f % p.T;
+        const float4* srow = p.spec + ((size_t)img * p.T + t) * kBins;
+        ptx::mbar_arrive_expect_tx(bar, kSpecRowBytes + (uint32_t)Fm * (uint32_t)sizeof(float2));
+        ptx::bulk_load_1d((void*)sspec, srow, kSpecRowBytes, bar);
+        if (masked) {
+            const float2* mrow = reinterpret_cast<const float2*>(p.mask) + (((size_t)s * p.mask_stem_stride + img) * p.T + t) * p.F;
+            ptx::bulk_load_1d((void*)smask, mrow, (uint32_t)p.F * (uint32_t)sizeof(float2), bar);
+        }
+    };
+    const int f_first = max(h0 - 3, 0);
+    if (j == 0) {
+        ptx::mbar_init(bar, 1);
+        ptx::fence_barrier_init();
+        stage(f_first);
+    }
+    float w[16];
+    float2 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        w[r] = __ldg(&p.postwin[j + 256 * r]);
+        acc[r] = make_float2(0.f, 0.f);
+    }
+    fft_smem_init(sm, p.twiddle, j);
+    __syncthreads();                      // barrier initialised before anyone polls it
+    uint32_t phase = 0;
+    for (int f = f_first; f < h1; f++) {
+        ptx::mbar_wait(bar, phase);
+        phase ^= 1;
+        float2 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const int k = j + 256 * r;
+            const int kk = k <= kFFT / 2 ? k : kFFT - k;
+            const float4 sp = sspec[kk];
+            float mL = uw, mR = uw;
+            if (kk < Fm) { const float2 m = smask[kk]; mL = m.x; mR = m.y; }
+            const float xlr = sp.x * mL, xli = -(sp.y * mL), xrr = sp.z * mR, xri = -(sp.w * mR);
+            float2 z;
+            if (k <= kFFT / 2) z = make_float2(xlr - xri, xli + xrr);
+            else z = make_float2(xlr + xri, -xli + xrr);
+            v[r] = make_float2(z.x, -z.y);
+        }
+        __syncthreads();   // staged rows consumed; the previous frame's pass-3 reads of the exchange buffer are done
+        if (j == 0 && f + 1 < h1) stage(f + 1);
+        fft4096(v, sm, p.twiddle, j);
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            acc[r].x += v[r].x * w[r];
+            acc[r].y += -v[r].y * w[r];
+        }
+        if (f >= h0) {   // segment f is complete: frames f-3 .. f have been added
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const long io = (long)f * kHop + j + 256 * k - p.front_pad;
+                if (io >= 0 && io < n) { outL[io * os] = acc[k].x; outR[io * os] = acc[k].y; }
             }
         }
 #pragma unroll
@@ -221,7 +317,18 @@ void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cu
 {
     if (n_streams == 0 || max_frames == 0) return;
     dim3 grid((max_frames + p.hops_per_cta - 1) / p.hops_per_cta, p.S, n_streams);
-    istft_ola_kernel<<<grid, kFftThreads, 0, st>>>(p);
+    static const int prefetch = [] { const char* e = getenv("SRT_ISTFT_PREFETCH"); return e ? atoi(e) : 1; }();
+    if (prefetch) {
+        static bool attr_set = false;
+        const size_t smem = istft_pf_smem(p.F);
+        if (!attr_set) {
+            cudaFuncSetAttribute(istft_ola_pf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)istft_pf_smem(2048));
+            attr_set = true;
+        }
+        istft_ola_pf_kernel<<<grid, kFftThreads, smem, st>>>(p);
+    } else {
+        istft_ola_kernel<<<grid, kFftThreads, 0, st>>>(p);
+    }
 }
 
 // =========================================================================================
@@ -272,7 +379,8 @@ __global__ void __launch_bounds__(256) diff_kernel(const DiffParams p)
     float* dst = p.out[((size_t)st * p.out_pairs + p.dst_pair) * 2 + c];
     const float* b = p.out[((size_t)st * p.out_pairs + p.sub_pair) * 2 + c];
     const float* a = p.pcmL ? (c ? p.pcmR[st] : p.pcmL[st]) : dst;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i] = a[i] - b[i];
+    const long os = p.out_stride, as = p.pcmL ? (p.pcm_stride ? p.pcm_stride[st] : 1) : os;
+    for (long i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) dst[i * os] = a[i * as] - b[i * os];
 }
 
 void launch_diff(const DiffParams& p, cudaStream_t st)

@@ -103,3 +103,34 @@ def test_unmodified_cli_on_b200_matches_reference_cli(oracle, tmp_path, T, F, st
             err = float(np.sqrt(np.mean((ref[nm][:, c].astype(np.float64) - got[nm][:, c]) ** 2)))
             assert err < TOL_RMS, (nm, c, err)
         assert float(np.sqrt(np.mean(ref[nm].astype(np.float64) ** 2))) > 1e-3, f"{nm}: silent reference output"
+
+
+EXAMPLE_CLI = os.path.join(ROOT, "examples", "_build", "spleeter_cli_b200")
+MODEL_FP16 = os.path.join(ROOT, "spleeterrt_b200", "weights", "model_fp16.bin")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(EXAMPLE_CLI) and os.path.exists(MODEL_FP16)),
+                    reason="reference CLI / examples/_build / model blob not built (python __graft_entry__.py in the build container)")
+@pytest.mark.parametrize("T,F,stems,seconds,mono", [(128, 512, 3, 6.0, False), (64, 1024, 2, 3.0, True), (256, 1024, 2, 8.0, False)])
+def test_device_level_cli_host_matches_reference_cli(oracle, tmp_path, T, F, stems, seconds, mono):
+    """examples/spleeter_cli_b200.c: same command line and output files as main.c, but decode -> ONE device call
+    (srt_create_cli + srt_separate_batch_interleaved: split, cascade, subtraction and join on the GPU) -> WAV writer.
+    Its WAVs match the reference CLI's within the north star's 1e-4 RMS (stereo and mono inputs)."""
+    n = int(seconds * 44100)
+    L, R = oracle.synth_pcm(9, n=n)
+    wav = str(tmp_path / "in.wav")
+    write_wav_f32(wav, L if mono else np.stack([L, R], axis=1))
+    ref = run_cli(REF_CLI, str(tmp_path / "ref"), wav, T, F, stems)
+    os.makedirs(tmp_path / "dev", exist_ok=True)
+    r = subprocess.run([EXAMPLE_CLI, "1", str(T), str(F), str(stems), wav, MODEL_FP16], cwd=str(tmp_path / "dev"),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-500:])
+    names = ["Vocal", "Accompaniment"] if stems <= 2 else ["Accompaniment", "Drum", "Vocal"]
+    assert sorted(ref) == sorted(names)
+    for nm in names:
+        got = read_wav_f32(str(tmp_path / "dev" / f"in.wav_{nm}.wav"))
+        assert got.shape == ref[nm].shape == (n, 2)
+        for c in range(2):
+            err = float(np.sqrt(np.mean((ref[nm][:, c].astype(np.float64) - got[:, c]) ** 2)))
+            assert err < TOL_RMS, (nm, c, err)

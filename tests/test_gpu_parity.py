@@ -259,6 +259,37 @@ def test_cli_mode_argument_errors(srt, oracle):
         srt.CliSeparator([coeff], 3, 64, 64)
 
 
+def test_interleaved_frames_in_and_out(srt, oracle, small_nets):
+    """srt_separate_batch_interleaved: the decoder's interleaved frames in (stereo and mono, main.c:767-769), the WAV
+    writer's interleaved frames out (main.c:806): bit-identical to the planar entry point, and the mono stream equals
+    the oracle run with R = L."""
+    T, F = 64, 256
+    (L0, R0), (L1, _) = oracle.synth_pcm(30, n=33000), oracle.synth_pcm(31, n=9001)
+    sep = srt.Separator(small_nets, T, F, max_images=2, max_batch_images=3)
+    planar = sep.separate([(L0, R0), (L1, L1)], unaffected=[0.1, 0.1])
+    inter = sep.separate_interleaved([np.stack([L0, R0], 1), L1], unaffected=[0.1, 0.1])
+    for pl, it in zip(planar, inter):
+        assert it.shape == (2, pl.shape[2], 2)
+        assert np.array_equal(it.transpose(0, 2, 1), pl)
+    ref = oracle.separate(small_nets, L1, L1, T, F)
+    assert rms(inter[1].transpose(0, 2, 1) - ref) < 1e-4
+    sep.close()
+    # CLI 2-output mode through the same formats: accompaniment = input - vocal reads the interleaved input
+    cli = srt.CliSeparator([small_nets[1][0]], 2, T, F, max_images=2)
+    a = cli.separate([(L0, R0)])[0]
+    b = cli.separate_interleaved([np.stack([L0, R0], 1)])[0]
+    assert np.array_equal(b.transpose(0, 2, 1), a)
+    m = cli.separate_interleaved([L1])[0]
+    assert np.abs(m[0] + m[1] - np.stack([L1, L1], 1)).max() < 1e-6
+    cli.close()
+    with pytest.raises(srt.SrtError):
+        sep2 = srt.Separator(small_nets[:1], T, F)
+        try:
+            sep2.separate_interleaved([np.zeros((5000, 3), np.float32)])
+        finally:
+            sep2.close()
+
+
 def test_unity_mask_is_identity_full_size(srt, oracle):
     """Size-independent property at benchmark shape (T=512, F=1024, 10 s): all-zero weights with
     a +100 head bias give mask == 1, so every stem reproduces the input (SURVEY §4 'VST stream' pin)."""

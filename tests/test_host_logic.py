@@ -168,3 +168,63 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle/", "ORACLE_DOC/") or "import" not in txt.split("oracle")[0][-40:], f
                 assert "from oracle" not in txt and "import oracle" not in txt and "srt_oracle" not in txt, f
+
+
+# ----------------------------------------------------------------------------- weight file formats
+def test_coeff_dat_round_trip_and_errors(oracle, tmp_path):
+    """fp32 `.dat` dumps (PluginProcessor.cpp:48-80): exact round trip; a short or missing file is an error, not
+    uninitialised weights."""
+    import spleeterrt_b200 as srt
+    w = oracle.synthetic_weights(21) * np.float32(1.0001)       # not fp16-representable any more
+    p = tmp_path / "drum4stems.dat"
+    srt.save_coeff_dat(p, w)
+    assert os.path.getsize(p) == 39290900
+    assert np.array_equal(np.fromfile(p, np.float32), w)         # the format is the raw struct
+    assert np.array_equal(srt.load_coeff_dat(p), w)
+    short = tmp_path / "short.dat"
+    short.write_bytes(b"\0" * 1000)
+    with pytest.raises(srt.SrtError):
+        srt.load_coeff_dat(short)
+    with pytest.raises(srt.SrtError):
+        srt.load_coeff_dat(tmp_path / "missing.dat")
+
+
+def test_model_fp16_blob_matches_reference_expansion(oracle, tmp_path):
+    """spleeterQuantized blob -> nets, expanded like f32Decompress (main.c:423-443): denormal halves flush to zero."""
+    import spleeterrt_b200 as srt
+    rng = np.random.default_rng(5)
+    halves = rng.integers(0, 1 << 16, size=2 * srt.COEFF_FLOATS, dtype=np.uint16)
+    halves[(halves & 0x7c00) == 0x7c00] &= 0xbfff                # no inf/nan: the model has none
+    halves[:8] = [0x0001, 0x03ff, 0x8001, 0x83ff, 0x0400, 0x8400, 0x0000, 0x8000]   # denormals, smallest normals, zeros
+    p = tmp_path / "model_fp16.bin"
+    halves.tofile(p)
+    nets = srt.load_model_fp16(p)
+    assert len(nets) == 2
+    want = oracle.half_to_float(halves).reshape(2, -1)           # the oracle's restatement of f32Decompress
+    assert np.array_equal(nets[0].view(np.uint32), want[0].view(np.uint32))
+    assert np.array_equal(nets[1].view(np.uint32), want[1].view(np.uint32))
+    assert np.all(nets[0][:4] == 0) and nets[0][4] == np.float32(2.0 ** -14)
+    bad = tmp_path / "odd.bin"
+    halves[:1000].tofile(bad)
+    with pytest.raises(srt.SrtError):
+        srt.load_model_fp16(bad)
+
+
+@pytest.mark.parametrize("layer,name,form", [(0, "down2", 0), (0, "down2", 1), (3, "down5", 0), (5, "up1", 0), (9, "up5", 0), (9, "up5", 1)])
+def test_pack_layer_is_a_zero_padded_permutation(oracle, layer, name, form):
+    """srt_pack_layer: every weight of the layer lands exactly once in the K-major swizzled blob (the rest is the
+    zero padding of unused taps / parities); non-TF32-exact weights double into hi + lo terms that sum back."""
+    import spleeterrt_b200 as srt
+    coeff = oracle.synthetic_weights(33)
+    w = np.sort(oracle.coeff_views(coeff)[name + ".w"].ravel())
+    blob = srt.pack_layer(coeff, layer, 64, 128, form)
+    nz = np.sort(blob[blob != 0])
+    assert np.array_equal(nz, w[w != 0])
+    # fp32 weights that TF32 cannot hold: two terms per weight, hi + lo == w to fp32 rounding of the lo term
+    coeff32 = coeff * np.float32(1.00013)
+    blob2 = srt.pack_layer(coeff32, layer, 64, 128, form)
+    assert blob2.size == 2 * blob.size
+    w32 = oracle.coeff_views(coeff32)[name + ".w"].ravel().astype(np.float64)
+    assert abs(blob2.astype(np.float64).sum() - w32.sum()) < 1e-6 * np.abs(w32).sum()
+    with pytest.raises(srt.SrtError):
+        srt.pack_layer(coeff, 11, 64, 128)
