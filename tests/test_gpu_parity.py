@@ -302,6 +302,50 @@ def test_unity_mask_is_identity_full_size(srt, oracle):
     sep.close()
 
 
+def test_batch_invariance_full_size(srt, oracle, small_nets):
+    """Size-independent property at the benchmark shape (T=512, F=1024): a stream's stems do not depend on what else
+    is in the batch, on its position in it, or on how the tiles are split into U-Net passes (units = (stream, tile,
+    stem) share no state) - bit for bit.  One stream spans two tiles (15 s)."""
+    a = tuple(oracle.synth_pcm(40, n=441000))
+    b = tuple(x[:300000] for x in oracle.synth_pcm(41, n=300000))
+    c = tuple(oracle.synth_pcm(42, n=15 * 44100))
+    sep = srt.Separator(small_nets, 512, 1024, max_images=4, max_batch_images=4)
+    alone = sep.separate([a])[0]
+    mixed = sep.separate([b, c, a])
+    assert np.array_equal(mixed[2], alone)
+    sep.close()
+    sep1 = srt.Separator(small_nets, 512, 1024, max_images=2, max_batch_images=3)     # two U-Net passes
+    again = sep1.separate([c, a])
+    assert np.array_equal(again[1], alone) and np.array_equal(again[0], mixed[1])
+    sep1.close()
+    assert rms(alone) > 1e-3
+    # and the masks are soft masks: the two stems of net (drum, vocal) never exceed the input's energy by much
+    assert rms(alone[0]) < 2 * rms(np.stack(a)) and rms(alone[1]) < 2 * rms(np.stack(a))
+
+
+@pytest.mark.parametrize("n", [1, 1023, 4096, 4097, 12288])
+def test_boundary_lengths_vs_oracle(srt, oracle, small_nets, n):
+    """Framing edge cases of main.c:762-767: a single sample, less than a hop, exactly one / just over one FFT block,
+    a whole number of blocks."""
+    L, R = (x[:n] for x in oracle.synth_pcm(50, n=16384))
+    sep = srt.Separator(small_nets[:1], 64, 128, max_images=1)
+    got = sep.separate([(L, R)])[0]
+    sep.close()
+    ref = oracle.separate(small_nets[:1], L, R, 64, 128)
+    assert got.shape == ref.shape == (1, 2, n)
+    assert rms(got - ref) < 1e-4 and np.abs(got - ref).max() < 1e-3
+
+
+def test_empty_inputs_are_errors(srt, oracle, small_nets):
+    sep = srt.Separator(small_nets[:1], 64, 128, max_images=1)
+    with pytest.raises(srt.SrtError):
+        sep.separate([(np.zeros(0, np.float32), np.zeros(0, np.float32))])      # a stream without samples
+    import ctypes as C
+    with pytest.raises(srt.SrtError):
+        sep.separate_raw(None, None, None, 0, None, None)                          # a batch without streams
+    sep.close()
+
+
 def test_capacity_errors_are_loud(srt, oracle):
     coeff = oracle.synthetic_weights(5)
     sep = srt.Separator([(coeff, 1)], 64, 64, max_images=1)
