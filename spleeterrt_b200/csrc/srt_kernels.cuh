@@ -245,7 +245,7 @@ void launch_istft(const IstftParams& p, cudaStream_t st);
 void launch_ola(const OlaParams& p, cudaStream_t st);
 // [n][T][F][2] (API layout) -> space-to-depth, TF32-rounded
 void launch_mag_to_s2d(const float* in, float* out_hi, float* out_lo, int T, int F, int n_img, cudaStream_t st);
-size_t conv_tc_smem_bytes(int n_tile, int* stages_out);
+size_t conv_tc_smem_bytes(int n_tile, int mt, int* stages_out);
 
 __device__ __forceinline__ float apply_act(int act, float x)
 {

@@ -12,6 +12,7 @@ SETS = {
     "up6c": [("base", {}), ("rna_split", {"SRT_UP6_DBG": "32"}), ("no_gather", {"SRT_UP6_DBG": "1"}), ("no_split", {"SRT_UP6_DBG": "8"})],
     "epw": [("base", {}), ("down1_8warps", {"SRT_RP_DBG": "64"}), ("rp_16warps", {"SRT_RP_DBG": "128"}),
             ("only_epi", {"SRT_RP_DBG": "14"}), ("only_epi_d1_8w", {"SRT_RP_DBG": "78"}), ("only_epi_rp16", {"SRT_RP_DBG": "142"})],
+    "mt": [("mt_off", {"SRT_TC_MT": "0"}), ("mt_256", {"SRT_TC_MT": "256"}), ("mt_128", {"SRT_TC_MT": "128"}), ("mt_64", {"SRT_TC_MT": "64"})],
     "istft": [("auto", {}), ("hops16", {"SRT_ISTFT_HOPS": "16"}), ("hops28", {"SRT_ISTFT_HOPS": "28"}), ("hops40", {"SRT_ISTFT_HOPS": "40"}),
               ("hops55", {"SRT_ISTFT_HOPS": "55"})],
 }
