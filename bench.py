@@ -89,6 +89,23 @@ def host_threads():
     return os.cpu_count() or 1
 
 
+def set_host_threads(cores):
+    """Make the OpenMP runtime(s) of this process use `cores` threads.  The environment variable is only read when a
+    libgomp is loaded, and torchrun exports OMP_NUM_THREADS=1 to its workers, so set it through the API as well: on the
+    system libgomp the reference build links against and on torch's own copy."""
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(cores))
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(int(cores))
+    except Exception:
+        pass
+
+
 def reference_arm(args, rank):
     """The reference's own CPU implementation of the path (oracle/_ref build of the reference's C
     sources, naive CPU_GEMM backend), all host threads, bounded sample per step."""
@@ -99,7 +116,9 @@ def reference_arm(args, rank):
     nets = O.four_stem_weights()
     L, R = O.synth_pcm(0, n=N_SAMPLES)
     cores = host_threads()
-    os.environ["OMP_NUM_THREADS"] = str(cores)
+    if have_ref:
+        O.ref_exec()                  # load the reference build (and its libgomp) before setting the thread count
+    set_host_threads(cores)
 
     def step():
         if have_ref:
@@ -132,13 +151,10 @@ def cpu_baseline_sample():
     nets = O.four_stem_weights()
     L, R = O.synth_pcm(0, n=N_SAMPLES)
     cores = host_threads()
-    os.environ["OMP_NUM_THREADS"] = str(cores)
-    try:   # torch shares libgomp with the reference build: pin its thread count too
-        import torch
-        torch.set_num_threads(cores)
-    except Exception:
-        pass
     have_ref = O.have_ref()
+    if have_ref:
+        O.ref_exec()
+    set_host_threads(cores)
     t0 = time.perf_counter()
     if have_ref:
         O.ref_exec().separate(nets, L, R, T, F, unaffected=0.1)

@@ -255,13 +255,8 @@ static void launch_rp(const RowConvParams& p, cudaStream_t st)
 {
     constexpr size_t smem = rp_smem_bytes<N, R, WS, KB, EPW>();
     static_assert(smem <= 232448, "must fit the 227 KB per-CTA limit");
-    static int sms = 0;
-    if (!sms) {
-        cudaFuncSetAttribute(conv_rp_kernel<N, R, WS, KB, EPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    static LaunchState state;
+    const int sms = state.prepare(conv_rp_kernel<N, R, WS, KB, EPW>, smem);
     const int n_tiles = p.tiles_x * p.tiles_y * p.ep.Bv * p.ep.S;
     dim3 grid(n_tiles < sms ? n_tiles : sms, 1, 1);
     conv_rp_kernel<N, R, WS, KB, EPW><<<grid, (EPW + 3) * 32, smem, st>>>(p);

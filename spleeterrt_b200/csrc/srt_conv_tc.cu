@@ -180,11 +180,8 @@ static void launch_one(const ConvParams& p, int pair_mode, cudaStream_t st)
 {
     int stages;
     const size_t smem = conv_tc_smem_bytes(N_TILE, MT, &stages);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(conv_tc_kernel<N_TILE, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static LaunchState state;
+    state.prepare(conv_tc_kernel<N_TILE, MT>, smem);
     const int txy = p.tiles_x * p.tiles_y;
     dim3 grid(txy, p.n_tiles * p.phases, p.S * p.tiles_n);
     if (MT > 1) {

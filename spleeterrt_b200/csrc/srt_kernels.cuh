@@ -6,7 +6,37 @@
 
 #include "srt_plan.h"
 
+#include <atomic>
+
 namespace srt {
+
+// Per-device launch state of one kernel: the opt-in dynamic shared-memory size (an attribute of the function ON A
+// DEVICE, so a process that holds contexts on several GPUs must set it on each) and the SM count for persistent grids.
+// One static instance per launcher; safe for concurrent host threads (tier A runs several instances from several
+// threads, main.c:330, 592): the worst case is two threads setting the same attribute.
+struct LaunchState {
+    static constexpr int kMaxDevices = 64;
+    std::atomic<int> smem[kMaxDevices];
+    std::atomic<int> sms[kMaxDevices];
+    // makes `bytes` of dynamic shared memory launchable for `kernel` on the current device; returns its SM count
+    template <class K>
+    int prepare(K kernel, size_t bytes)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const int d = (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+        if (smem[d].load(std::memory_order_acquire) < (int)bytes || d != dev) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            smem[d].store((int)bytes, std::memory_order_release);
+        }
+        int n = sms[d].load(std::memory_order_acquire);
+        if (n == 0 || d != dev) {
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            sms[d].store(n, std::memory_order_release);
+        }
+        return n;
+    }
+};
 
 // ---------------------------------------------------------------------------------------
 // Gather-GEMM layer launch parameters (tcgen05 kernel and SIMT verification kernel).

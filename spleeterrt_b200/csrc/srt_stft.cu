@@ -319,12 +319,9 @@ void launch_istft_ola(const IstftOlaParams& p, int n_streams, int max_frames, cu
     dim3 grid((max_frames + p.hops_per_cta - 1) / p.hops_per_cta, p.S, n_streams);
     static const int prefetch = [] { const char* e = getenv("SRT_ISTFT_PREFETCH"); return e ? atoi(e) : 1; }();
     if (prefetch) {
-        static bool attr_set = false;
+        static LaunchState state;
         const size_t smem = istft_pf_smem(p.F);
-        if (!attr_set) {
-            cudaFuncSetAttribute(istft_ola_pf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)istft_pf_smem(2048));
-            attr_set = true;
-        }
+        state.prepare(istft_ola_pf_kernel, istft_pf_smem(2048));
         istft_ola_pf_kernel<<<grid, kFftThreads, smem, st>>>(p);
     } else {
         istft_ola_kernel<<<grid, kFftThreads, 0, st>>>(p);

@@ -303,17 +303,8 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
 void launch_up6_tc(const Up6TcParams& p, cudaStream_t st)
 {
     const size_t smem = up6_tc_smem_bytes(p.S);
-    static int sms = 0;
-    static size_t configured = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    if (smem > configured) {
-        cudaFuncSetAttribute(up6_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    static LaunchState state;
+    const int sms = state.prepare(up6_tc_kernel, smem);
     const int n_units = p.blocks_x * p.chunks * p.Bv * p.S;
     up6_tc_kernel<<<n_units < sms ? n_units : sms, kU6Threads, smem, st>>>(p);
 }

@@ -346,6 +346,22 @@ def test_empty_inputs_are_errors(srt, oracle, small_nets):
     sep.close()
 
 
+def test_two_devices_in_one_process(srt, oracle, small_nets):
+    """srt_config.device: contexts on two GPUs of one process give identical stems (the opt-in shared-memory sizes of
+    the kernels are per-device attributes and must be set on each)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    L, R = oracle.synth_pcm(60, n=40000)
+    outs = []
+    for dev in (0, 1):
+        sep = srt.Separator(small_nets, 64, 1024, max_images=1, device=dev)
+        outs.append(sep.separate([(L, R)])[0])
+        sep.close()
+    assert np.array_equal(outs[0], outs[1])
+    assert rms(outs[0] - oracle.separate(small_nets, L, R, 64, 1024)) < 1e-4
+
+
 def test_capacity_errors_are_loud(srt, oracle):
     coeff = oracle.synthetic_weights(5)
     sep = srt.Separator([(coeff, 1)], 64, 64, max_images=1)
