@@ -146,6 +146,24 @@ int srt_separate_device_interleaved(srt_ctx* ctx, const float* const* d_pcm, con
                                     const size_t* n_samples, int n_streams, const float* unaffected,
                                     float* const* d_out);
 
+/* ---- sample-rate conversion in front of the path ----------------------------------------------
+ * JamesDSPOfflineResampling (main.c:209-224, called at main.c:264-270 when the file is not at 44.1 kHz) = libsamplerate
+ * src_simple() on the sinc interpolator of Executable/libsamplerate/src_sinc.c.  The coefficient table is the host's
+ * (`decompressedCoefficients`, main.c:277, 693-694): coeff_count = 22438 floats and index_inc = 491 in the reference
+ * (src_sinc.c:141-143).  in: n_in frames of `channels` (1 or 2) interleaved floats; out: n_out frames, normally
+ * srt_resample_frames(n_in, ratio) = ceil(n_in * ratio) (main.c:265); *n_generated = frames the converter produced
+ * (it may stop one frame short, src_sinc.c:323-326), the rest of `out` is zero like the reference's buffer.
+ * Bit-identical to the reference build.  ratio = 44100 / file rate. */
+size_t srt_resample_frames(size_t n_in, double ratio);
+int srt_resample_host(srt_ctx* ctx, const float* in, size_t n_in, int channels, double ratio, const float* coeffs,
+                      int coeff_count, int index_inc, float* out, size_t n_out, size_t* n_generated);
+int srt_resample_device(srt_ctx* ctx, const float* d_in, size_t n_in, int channels, double ratio, const float* d_coeffs,
+                        int coeff_count, int index_inc, float* d_out, size_t n_out, size_t* n_generated);
+/* host-only: the converter's bookkeeping (input frame and 12-bit fixed-point table offset per output frame);
+ * returns the number of frames generated, frames / starts may be NULL */
+long long srt_resample_plan(size_t n_in, int channels, double ratio, int coeff_count, int index_inc, size_t n_out,
+                            int32_t* frames, int32_t* starts);
+
 /* ---- transforms (Executable/stftFix.c) --------------------------------------------------
  * srt_stft_host: rows = ceil(n/1024); planes are [rows][4096] host buffers supplied by the
  * caller, zero-filled on return outside bins 0..2048 of the computed rows (stftFix.c:367-371).

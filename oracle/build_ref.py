@@ -88,7 +88,36 @@ def build(force=False):
            + [os.path.join(ex, "gemm.c")], extra=["-I" + vst])
     wbin = decode_weights(force)
     build_cli(wbin, force)
+    build_resampler(force)
     return True
+
+
+def build_resampler(force=False):
+    """oracle/_ref/libref_resample.so: the reference's resampling front end (main.c:132-224 + libsamplerate) behind the
+    two entry points of oracle/ref_resample_shim.c, and the sinc coefficient table it decompresses, dumped next to the
+    model blob (spleeterrt_b200/weights/resampler_mq.f32: reference DATA, git-ignored like the weights)."""
+    ex = os.path.join(REF, "Executable")
+    so = os.path.join(OUT, "libref_resample.so")
+    shim = os.path.join(HERE, "ref_resample_shim.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(shim):
+        sdir = os.path.join(OUT, "model_stub")
+        os.makedirs(sdir, exist_ok=True)
+        with open(os.path.join(sdir, "model.c"), "w") as f:      # main.c only takes the blob's address (main.c:759)
+            f.write("#include <stdint.h>\nstatic const int32_t coeffQuantized[1] = {0};\n")
+        with open(os.path.join(sdir, "stub.c"), "w") as f:
+            f.write("void openblas_set_num_threads(int n) { (void)n; }\n")
+        subprocess.check_call(["gcc", "-O2", "-w", "-fPIC", "-shared", "-I", sdir, "-I", ex, shim, os.path.join(sdir, "stub.c"),
+                               os.path.join(ex, "libsamplerate", "samplerate.c"), os.path.join(ex, "libsamplerate", "src_sinc.c"),
+                               "-L", OUT, "-lref_exec", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread", "-o", so])
+    table = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights", "resampler_mq.f32")
+    if force or not os.path.exists(table):
+        import ctypes
+        import numpy as np
+        lib = ctypes.CDLL(so)
+        t = np.zeros(22438, np.float32)
+        lib.ref_resampler_table(t.ctypes.data_as(ctypes.c_void_p))
+        os.makedirs(os.path.dirname(table), exist_ok=True)
+        t.tofile(table)
 
 
 def build_cli(wbin, force=False):

@@ -262,6 +262,67 @@ def separate_cli(nets, pcmL, pcmR, T, F, n_out, unaffected=0.1):
     return out
 
 
+# ----------------------------------------------------------------------------- resampler
+RESAMPLER_TABLE = os.path.join(os.path.dirname(HERE), "spleeterrt_b200", "weights", "resampler_mq.f32")
+RS_HALF_LEN, RS_INDEX_INC = 22436, 491     # src_sinc.c:141-143
+
+
+def resampler_table():
+    """The sinc coefficient table the reference host decompresses at start-up (main.c:693-694), dumped from the
+    reference build by oracle/build_ref.py (reference data, not committed)."""
+    return np.fromfile(RESAMPLER_TABLE, np.float32)
+
+
+def have_resampler_table():
+    return os.path.exists(RESAMPLER_TABLE)
+
+
+def synthetic_resampler_table(seed=3):
+    """A windowed-sinc table of the same geometry for runs without the reference's data."""
+    i = np.arange(RS_HALF_LEN + 2, dtype=np.float64)
+    t = i / RS_INDEX_INC
+    w = 0.5 * (1 + np.cos(np.pi * i / (RS_HALF_LEN + 2)))
+    return (0.92 * np.sinc(0.92 * t) * w).astype(np.float32)
+
+
+def resample(x, ratio, table=None):
+    """x: float32[n] (mono) or [n][2] interleaved frames -> (float32[ceil(n*ratio)][ch] zero-filled, frames generated),
+    JamesDSPOfflineResampling (main.c:209-224, 264-270)."""
+    lib = port()
+    x = np.ascontiguousarray(x, np.float32)
+    ch = 1 if x.ndim == 1 else x.shape[1]
+    n = x.shape[0]
+    table = np.ascontiguousarray(resampler_table() if table is None else table, np.float32)
+    n_out = int(np.ceil(n * ratio))
+    out = np.zeros((n_out, ch), np.float32)
+    lib.srt_oracle_resample.restype = C.c_long
+    lib.srt_oracle_resample.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_long]
+    gen = lib.srt_oracle_resample(x.ctypes.data, n, ch, float(ratio), table.ctypes.data, RS_HALF_LEN, RS_INDEX_INC,
+                                  out.ctypes.data, n_out)
+    return out, int(gen)
+
+
+def ref_resample(x, ratio, table=None):
+    """The reference's own resampler (oracle/_ref/libref_resample.so)."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libref_resample.so"))
+    x = np.ascontiguousarray(x, np.float32)
+    ch = 1 if x.ndim == 1 else x.shape[1]
+    n = x.shape[0]
+    if table is None:
+        table = np.zeros(RS_HALF_LEN + 2, np.float32)
+        lib.ref_resampler_table(table.ctypes.data_as(C.c_void_p))
+    table = np.ascontiguousarray(table, np.float32)
+    n_out = int(np.ceil(n * ratio))
+    out = np.zeros((n_out, ch), np.float32)
+    lib.ref_resample.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_double, C.c_void_p]
+    lib.ref_resample(x.ctypes.data, out.ctypes.data, n, n_out, ch, float(ratio), table.ctypes.data)
+    return out
+
+
+def have_ref_resampler():
+    return os.path.exists(os.path.join(REF_DIR, "libref_resample.so"))
+
+
 # ----------------------------------------------------------------------------- reference API
 class RefExec:
     """The reference's Executable flavour, compiled as is (oracle/_ref/libref_exec.so)."""

@@ -777,3 +777,149 @@ void srt_oracle_vst_process(void *h, const float *inL, const float *inR, int n, 
         }
     }
 }
+
+/* =========================================================================================
+ * Sample-rate conversion in front of the path.
+ *
+ * main.c:264-274 resamples the decoded file to 44.1 kHz with JamesDSPOfflineResampling (main.c:209-224) =
+ * libsamplerate's src_simple() (samplerate.c:427-441, end_of_input = 1) on the sinc interpolator of
+ * Executable/libsamplerate/src_sinc.c with the coefficient table the host supplies (`decompressedCoefficients`,
+ * src_sinc.c:141-143: 22438 floats, half length 22436, 491 table steps per input sample).
+ *
+ * Restated without the streaming ring buffer: samples are addressed by absolute index (zero outside the input),
+ * and only the INTEGER bookkeeping of the buffer (b_current / b_end / b_real_end, prepare_data src_sinc.c:1102-1172)
+ * is carried along, because it decides at which output frame the converter stops (src_sinc.c:312-328, 467-482:
+ * mono stops on `>`, stereo on `>=`, both comparing against the end of the data in BUFFER coordinates).
+ * Per output frame (src_sinc.c:330-347 / 484-500, calc_output_single :218-271, calc_output_stereo :366-420):
+ *     inc   = lrint(index_inc * min(ratio, 1) * 4096)                    12-bit fixed point
+ *     start = lrint(frac * index_inc * min(ratio, 1) * 4096)             frac = fractional input position
+ *     left  = sum over the taps at table positions start + j*inc (far -> near) of x[b - j]
+ *     right = sum over the taps at table positions inc - start + j*inc (far -> near) of x[b + 1 + j]
+ *     y = (float)(min(ratio, 1) * (left + right))       taps interpolated linearly between table entries, sums in double
+ * then frac += 1/ratio, carried into b with fmod_one (common.h:137-145).
+ * ========================================================================================= */
+typedef struct {
+    const float *x;
+    long n_floats;      /* n_in * ch */
+    int ch;
+} rs_src;
+
+static inline double rs_sample(const rs_src *s, long i)
+{
+    return (i >= 0 && i < s->n_floats) ? (double)s->x[i] : 0.0;
+}
+
+static inline double rs_tap(const float *coeffs, int32_t fidx)
+{
+    const double fraction = (double)(fidx & 4095) * (1.0 / 4096.0);
+    const int k = fidx >> 12;
+    return coeffs[k] + fraction * (coeffs[k + 1] - coeffs[k]);     /* float difference, double interpolation */
+}
+
+static double rs_fmod_one(double v)
+{
+    const double r = v - (double)lrint(v);
+    return r < 0.0 ? r + 1.0 : r;
+}
+
+/* Returns the number of output frames written (<= n_out); frames beyond stay untouched (the caller's buffer is
+ * zero-filled in main.c:267-268).  Returns -1 for a ratio libsamplerate rejects (samplerate.c:144). */
+long srt_oracle_resample(const float *in, long n_in, int ch, double ratio, const float *coeffs, int half_len, int index_inc,
+                         float *out, long n_out)
+{
+    if (ratio < 1.0 / 256.0 || ratio > 256.0 || (ch != 1 && ch != 2)) return -1;
+    const rs_src src = {in, n_in * ch, ch};
+    /* buffer geometry (sinc_set_converter, src_sinc.c:150-153) */
+    long b_len = 3 * lrint((half_len + 2.0) / index_inc * 256.0 + 1);
+    if (b_len < 4096) b_len = 4096;
+    b_len = b_len * ch + 1;
+    double count = (half_len + 2.0) / index_inc;
+    if (ratio < 1.0) count /= ratio;
+    const long half = ch * (lrint(count) + 1);
+    long b_cur = 0, b_end = 0, b_real_end = -1, in_used = 0;
+    const long in_count = n_in * ch;
+    long abs_cur = 0;                      /* absolute float index of the sample at b_cur */
+    double frac = 0.0;
+    const double terminate = 1.0 / ratio + 1e-20;
+    const double scale_inc = index_inc * (ratio < 1.0 ? ratio : 1.0);
+    const int32_t inc = (int32_t)lrint(scale_inc * 4096.0);
+    const int32_t max_idx = (int32_t)half_len << 12;
+    long gen = 0;
+    while (gen < n_out) {
+        long in_hand = (b_end - b_cur + b_len) % b_len;
+        if (in_hand <= half) {
+            /* ---- prepare_data, indices only (src_sinc.c:1102-1172) */
+            if (b_real_end < 0 && in != NULL) {
+                long len;
+                if (b_cur == 0) {
+                    len = b_len - 2 * half;
+                    b_cur = b_end = half;
+                } else if (b_end + half + ch < b_len) {
+                    len = b_len - b_cur - half;
+                    if (len < 0) len = 0;
+                } else {
+                    len = b_end - b_cur;
+                    b_cur = half;
+                    b_end = b_cur + len;
+                    len = b_len - b_cur - half;
+                    if (len < 0) len = 0;
+                }
+                if (len > in_count - in_used) len = in_count - in_used;
+                len -= len % ch;
+                b_end += len;
+                in_used += len;
+                if (in_used == in_count && b_end - b_cur < 2 * half) {      /* end_of_input is always set by src_simple */
+                    if (b_len - b_end < half + 5) {
+                        len = b_end - b_cur;
+                        b_cur = half;
+                        b_end = b_cur + len;
+                    }
+                    b_real_end = b_end;
+                    len = half + 5;
+                    if (b_end + len > b_len) len = b_len - b_end;
+                    b_end += len;
+                }
+            }
+            in_hand = (b_end - b_cur + b_len) % b_len;
+            if (in_hand <= half) break;
+        }
+        if (b_real_end >= 0) {
+            const double pos = (double)b_cur + frac + terminate;
+            if (ch == 1 ? pos > (double)b_real_end : pos >= (double)b_real_end) break;
+        }
+        const int32_t start = (int32_t)lrint(frac * scale_inc * 4096.0);
+        for (int c = 0; c < ch; c++) {
+            /* left half: far tap first */
+            int32_t fidx = start;
+            int32_t n = (max_idx - fidx) / inc;
+            fidx += n * inc;
+            long di = abs_cur - (long)ch * n + c;
+            double left = 0.0;
+            do {
+                left += rs_tap(coeffs, fidx) * rs_sample(&src, di);
+                fidx -= inc;
+                di += ch;
+            } while (fidx >= 0);
+            /* right half */
+            fidx = inc - start;
+            n = (max_idx - fidx) / inc;
+            fidx += n * inc;
+            di = abs_cur + (long)ch * (1 + n) + c;
+            double right = 0.0;
+            do {
+                right += rs_tap(coeffs, fidx) * rs_sample(&src, di);
+                fidx -= inc;
+                di -= ch;
+            } while (fidx > 0);
+            out[gen * ch + c] = (float)((scale_inc / index_inc) * (left + right));
+        }
+        gen++;
+        frac += 1.0 / ratio;
+        const double rem = rs_fmod_one(frac);
+        const long step = lrint(frac - rem);
+        b_cur = (b_cur + ch * step) % b_len;
+        abs_cur += ch * step;
+        frac = rem;
+    }
+    return gen;
+}

@@ -6,5 +6,5 @@ compute happens in ``libspleeterrt_b200.so`` (hand-written sm_100a CUDA); there 
 PyTorch fallback — if the library or a B200 is missing, calls raise.
 """
 from .api import (COEFF_FLOATS, FFTSIZE, HOPSIZE, BINS, Separator, CliSeparator, Streamer, SrtError, half_to_float,  # noqa: F401
-                  load_coeff_dat, save_coeff_dat, load_model_fp16, pack_layer,
+                  load_coeff_dat, save_coeff_dat, load_model_fp16, pack_layer, resample_plan,
                   lib_path, load_library, exported_symbols, HEADER_SYMBOLS)

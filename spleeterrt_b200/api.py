@@ -19,7 +19,8 @@ HEADER_SYMBOLS = {
                    "srt_load_coeff_dat", "srt_save_coeff_dat", "srt_model_fp16_nets", "srt_load_model_fp16", "srt_pack_layer", "srt_unet_host",
                    "srt_unet_device", "srt_separate_batch", "srt_separate_batch_async", "srt_batch_wait",
                    "srt_separate_device", "srt_separate_batch_interleaved", "srt_separate_batch_interleaved_async",
-                   "srt_separate_device_interleaved", "srt_stft_rows",
+                   "srt_separate_device_interleaved", "srt_resample_frames", "srt_resample_host", "srt_resample_device",
+                   "srt_resample_plan", "srt_stft_rows",
                    "srt_stft_host", "srt_istft_host", "srt_launch_count", "srt_last_timing", "srt_set_timing",
                    "srt_debug_tensor", "srt_host_alloc", "srt_host_free", "srt_synchronize",
                    "srt_stream_create", "srt_stream_process", "srt_stream_destroy", "srt_stream_launch_count"],
@@ -86,6 +87,13 @@ def load_library():
     lib.srt_host_free.argtypes = [C.c_void_p]
     lib.srt_synchronize.argtypes = [C.c_void_p]
     lib.srt_half_to_float.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.srt_resample_frames.restype = C.c_size_t
+    lib.srt_resample_frames.argtypes = [C.c_size_t, C.c_double]
+    lib.srt_resample_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.srt_resample_device.argtypes = lib.srt_resample_host.argtypes
+    lib.srt_resample_plan.restype = C.c_longlong
+    lib.srt_resample_plan.argtypes = [C.c_size_t, C.c_int, C.c_double, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
     lib.srt_load_coeff_dat.argtypes = [C.c_char_p, C.c_void_p]
     lib.srt_save_coeff_dat.argtypes = [C.c_char_p, C.c_void_p]
     lib.srt_model_fp16_nets.argtypes = [C.c_char_p]
@@ -163,6 +171,18 @@ def pack_layer(coeff, layer, time_step, bin_limit, form=0):
     out = np.empty(n, np.float32)
     _host_check(lib, lib.srt_pack_layer(layer, form, time_step, bin_limit, coeff.ctypes.data, out.ctypes.data, out.size))
     return out
+
+
+RESAMPLER_INDEX_INC = 491      # Executable/libsamplerate/src_sinc.c:143
+
+
+def resample_plan(n_in, channels, ratio, coeff_count=22438, index_inc=RESAMPLER_INDEX_INC):
+    """(input frame, table offset) per output frame of the reference's one-shot converter; host only."""
+    lib = load_library()
+    n_out = lib.srt_resample_frames(n_in, float(ratio))
+    fr, st = np.zeros(max(n_out, 1), np.int32), np.zeros(max(n_out, 1), np.int32)
+    gen = _host_check(lib, lib.srt_resample_plan(n_in, channels, float(ratio), coeff_count, index_inc, n_out, fr.ctypes.data, st.ctypes.data))
+    return fr[:gen], st[:gen], n_out
 
 
 class Separator:
@@ -297,6 +317,20 @@ class Separator:
 
     def wait(self, ticket):
         self._check(self.lib.srt_batch_wait(self.h, ticket))
+
+    # ---- sample-rate conversion --------------------------------------------------------------
+    def resample(self, x, ratio, table, index_inc=RESAMPLER_INDEX_INC):
+        """x: float32[n] or [n][ch] interleaved frames -> (float32[ceil(n*ratio)][ch], frames generated): the
+        reference's JamesDSPOfflineResampling (main.c:209-224) with the host's sinc table."""
+        x = np.ascontiguousarray(x, np.float32)
+        ch = 1 if x.ndim == 1 else x.shape[1]
+        table = np.ascontiguousarray(table, np.float32)
+        n_out = self.lib.srt_resample_frames(x.shape[0], float(ratio))
+        out = np.empty((n_out, ch), np.float32)
+        gen = C.c_size_t(0)
+        self._check(self.lib.srt_resample_host(self.h, x.ctypes.data, x.shape[0], ch, float(ratio), table.ctypes.data, table.size,
+                                               index_inc, out.ctypes.data, n_out, C.byref(gen)))
+        return out, gen.value
 
     # ---- transforms -----------------------------------------------------------------------
     def stft(self, L, R):

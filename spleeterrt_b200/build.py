@@ -11,12 +11,12 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libspleeterrt_b200.so")
-SOURCES = ["srt_plan.cpp", "srt_weights.cpp", "srt_ctx.cu", "srt_conv_tc.cu", "srt_conv_rp.cu", "srt_up6_tc.cu", "srt_unet_simt.cu", "srt_stft.cu", "srt_stream.cu", "srt_tier_a.cu"]
+SOURCES = ["srt_plan.cpp", "srt_weights.cpp", "srt_ctx.cu", "srt_conv_tc.cu", "srt_conv_rp.cu", "srt_up6_tc.cu", "srt_unet_simt.cu", "srt_stft.cu", "srt_stream.cu", "srt_tier_a.cu", "srt_resample.cu"]
 HEADERS = ["srt_plan.h", "srt_kernels.cuh", "srt_ptx.cuh", "srt_epilogue.cuh", "srt_fft.cuh", "srt_internal.h",
            "../../include/srt_b200.h", "../../include/spleeter.h", "../../include/stftFix.h", "../../include/Spleeter4Stems.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-fno-strict-aliasing"]
+         "-Xcompiler", "-fPIC,-fno-strict-aliasing,-ffp-contract=off"]
 
 
 def _stale(target, deps):

@@ -726,6 +726,7 @@ int ctx_run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask_st
 }
 float* ctx_mag(srt_ctx* c) { return c->d_mag; }
 cudaStream_t ctx_stream(srt_ctx* c) { return c->stream; }
+int ctx_device(srt_ctx* c) { return c->cfg.device; }
 const float2* ctx_twiddle(srt_ctx* c) { return c->d_twiddle; }
 void ctx_count_launch(srt_ctx* c, int n) { c->launches += n; }
 int set_error(int code, const char* msg) { return fail(code, "%s", msg); }

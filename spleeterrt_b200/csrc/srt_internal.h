@@ -10,6 +10,7 @@ namespace internal {
 int ctx_run_unet(srt_ctx* ctx, int mag_img0, int Bv, float* mask_base, int mask_stride, int mask_img0);
 float* ctx_mag(srt_ctx* ctx);   // the context's space-to-depth magnitude buffer: [max_batch_images] hi images, then as many lo images
 cudaStream_t ctx_stream(srt_ctx* ctx);
+int ctx_device(srt_ctx* ctx);
 const float2* ctx_twiddle(srt_ctx* ctx);
 void ctx_count_launch(srt_ctx* ctx, int n);
 int set_error(int code, const char* msg);

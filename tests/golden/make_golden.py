@@ -5,7 +5,7 @@ oracle/build_ref.py from /root/reference).  Run in the build container:
     python oracle/build_ref.py && python tests/golden/make_golden.py
 
 Fixtures are small on purpose (they are committed): a T=64 x F=64 U-Net call with seeded
-synthetic fp16-representable weights (both activation modes), a 20-frame STFT/iSTFT and a T=64 x F=64 run of the CLI's 3-output cascade."""
+synthetic fp16-representable weights (both activation modes), a 20-frame STFT/iSTFT, a T=64 x F=64 run of the CLI's 3-output cascade and four short sample-rate conversions."""
 import os
 import sys
 
@@ -40,4 +40,15 @@ sd, sv = 5151, 5252
 nets = [(O.synthetic_weights(sd), 1), (O.synthetic_weights(sv), 0)]
 stems = r.separate_cli(nets, L, R, 64, 64, 3)
 np.savez_compressed(os.path.join(HERE, "cascade_T64_F64.npz"), seed_drum=sd, seed_vocal=sv, L=L, R=R, stems=stems)
+# resampler front end (main.c:209-224 -> libsamplerate sinc): the reference's code on a SYNTHETIC coefficient table of
+# the reference's geometry (the real table is reference data and stays out of the repository)
+table = O.synthetic_resampler_table()
+rs = {}
+for tag, fs, n, ch in (("48k_stereo", 48000, 1500, 2), ("48k_mono", 48000, 1600, 1), ("22k05_stereo", 22050, 700, 2), ("96k_mono", 96000, 2000, 1)):
+    x = (rng.standard_normal((n, ch)) * 0.3).astype(np.float32)
+    x = x[:, 0] if ch == 1 else x
+    rs[tag + "_in"] = x
+    rs[tag + "_rate"] = fs
+    rs[tag + "_out"] = O.ref_resample(x, 44100.0 / fs, table)
+np.savez_compressed(os.path.join(HERE, "resample_small.npz"), **rs)
 print("golden fixtures written")

@@ -362,6 +362,41 @@ def test_two_devices_in_one_process(srt, oracle, small_nets):
     assert rms(outs[0] - oracle.separate(small_nets, L, R, 64, 1024)) < 1e-4
 
 
+@pytest.mark.parametrize("fs,n,ch", [(48000, 48000, 2), (48000, 4800, 1), (22050, 9000, 2), (96000, 20000, 1), (8000, 999, 2)])
+def test_resampler_bit_exact_vs_oracle(srt, oracle, xform, fs, n, ch):
+    """srt_resample_host against the oracle converter (itself bit-identical to the reference's libsamplerate build):
+    integer bookkeeping on the host, taps in double on the GPU without FMA contraction -> array_equal."""
+    rng = np.random.default_rng(fs + n)
+    x = (rng.standard_normal((n, ch)) * 0.3).astype(np.float32)
+    x = x[:, 0] if ch == 1 else x
+    table = oracle.resampler_table() if oracle.have_resampler_table() else oracle.synthetic_resampler_table()
+    ref, gen_ref = oracle.resample(x, 44100.0 / fs, table)
+    got, gen = xform.resample(x, 44100.0 / fs, table)
+    assert gen == gen_ref and got.shape == ref.shape
+    assert np.array_equal(got, ref)
+
+
+def test_resampler_golden_and_chain(srt, oracle, small_nets):
+    """The reference-generated fixture, and a 48 kHz stereo clip through resample -> separate on the GPU against the
+    oracle's resample -> separate."""
+    g = np.load(os.path.join(GOLD, "resample_small.npz"))
+    table = oracle.synthetic_resampler_table()
+    sep = srt.Separator(small_nets[:1], 64, 256, max_images=1)
+    for tag in ("48k_stereo", "48k_mono", "22k05_stereo", "96k_mono"):
+        got, _ = sep.resample(g[tag + "_in"], 44100.0 / float(g[tag + "_rate"]), table)
+        assert np.array_equal(got, g[tag + "_out"].reshape(got.shape)), tag
+    x = np.stack(oracle.synth_pcm(70, n=24000), 1)         # the §8d test signal, read as a 48 kHz clip
+    y, gen = sep.resample(x, 44100.0 / 48000.0, table)
+    assert gen == y.shape[0] == 22050
+    stems = sep.separate_interleaved([y])[0]
+    yo, _ = oracle.resample(x, 44100.0 / 48000.0, table)
+    ref = oracle.separate(small_nets[:1], yo[:, 0].copy(), yo[:, 1].copy(), 64, 256)
+    assert rms(stems.transpose(0, 2, 1) - ref) < 1e-4
+    with pytest.raises(srt.SrtError):
+        sep.resample(x, 1e-4, table)
+    sep.close()
+
+
 def test_capacity_errors_are_loud(srt, oracle):
     coeff = oracle.synthetic_weights(5)
     sep = srt.Separator([(coeff, 1)], 64, 64, max_images=1)

@@ -228,3 +228,29 @@ def test_pack_layer_is_a_zero_padded_permutation(oracle, layer, name, form):
     assert abs(blob2.astype(np.float64).sum() - w32.sum()) < 1e-6 * np.abs(w32).sum()
     with pytest.raises(srt.SrtError):
         srt.pack_layer(coeff, 11, 64, 128)
+
+
+# ----------------------------------------------------------------------------- resampler bookkeeping
+@pytest.mark.parametrize("ch", [1, 2])
+def test_resample_plan_matches_the_oracle_converter(oracle, ch):
+    """srt_resample_plan (host only): the product's restatement of the converter's sequential bookkeeping produces as
+    many frames as the oracle (which is pinned bit-exactly to the reference), also where n*ratio is an integer and the
+    stop condition is a knife edge; positions are monotone and table offsets stay inside one table step."""
+    import spleeterrt_b200 as srt
+    table = oracle.synthetic_resampler_table()
+    rng = np.random.default_rng(1)
+    for fs, n in [(48000, 4800), (48000, 160), (48000, 4801), (22050, 1000), (88200, 2000), (96000, 320 * 7), (32000, 3200), (11025, 500),
+                  (44100 * 4, 4000), (47999, 5000), (8000, 80)]:
+        ratio = 44100.0 / fs
+        x = (rng.standard_normal((n, ch)) * 0.1).astype(np.float32)
+        _, gen = oracle.resample(x[:, 0] if ch == 1 else x, ratio, table)
+        frames, starts, n_out = srt.resample_plan(n, ch, ratio)
+        assert n_out == int(np.ceil(n * ratio))
+        assert frames.size == gen, (fs, n, ch, frames.size, gen)
+        assert np.all(np.diff(frames) >= 0) and frames[0] == 0 and frames[-1] < n + 1
+        inc = int(round(491 * min(ratio, 1.0) * 4096))
+        assert starts.min() >= 0 and starts.max() <= inc
+    with pytest.raises(srt.SrtError):
+        srt.resample_plan(100, 3, 1.0)
+    with pytest.raises(srt.SrtError):
+        srt.resample_plan(100, 2, 1000.0)
