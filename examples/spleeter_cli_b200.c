@@ -11,8 +11,10 @@
  * from srt_create_cli) -> WAV writer from pinned memory.  Split, join, cascade and subtraction happen on the
  * device.  spawnNthreads is accepted and ignored (tiles are batched on the GPU instead of threaded).
  *
- * Out of scope on purpose: FLAC/MP3 decoding and sample-rate conversion; the input must
- * be a 44.1 kHz WAV (16-bit PCM or 32-bit float, 1 or 2 channels).
+ * Files that are not at 44.1 kHz are converted like main.c:264-270 does (srt_resample_host = the reference's libsamplerate
+ * sinc converter) when the host's coefficient table is supplied in SRT_RESAMPLER_TABLE (raw float32 file, 22438 entries:
+ * what decompressResamplerMQ produces, main.c:693-694).  Out of scope on purpose: FLAC/MP3 decoding; the input must be a
+ * WAV (16-bit PCM or 32-bit float, 1 or 2 channels).
  *
  *   gcc -O2 -I include examples/spleeter_cli_b200.c -L spleeterrt_b200 -lspleeterrt_b200 \
  *       -Wl,-rpath,$PWD/spleeterrt_b200 -lm -o spleeter_cli_b200
@@ -116,25 +118,47 @@ int main(int argc, char** argv)
     size_t n = 0;
     float* pcm = load_wav(argv[5], &channels, &rate, &n);
     if (!pcm) return -1;
-    if (rate != 44100 || channels < 1 || channels > 2 || n == 0) {
-        fprintf(stderr, "%s: need 1 or 2 channels at 44100 Hz (got %u ch, %u Hz); resample first\n", argv[5], channels, rate);
+    if (channels < 1 || channels > 2 || n == 0 || rate == 0) {
+        fprintf(stderr, "%s: need 1 or 2 channels (got %u ch, %u Hz)\n", argv[5], channels, rate);
         return -1;
+    }
+    float* table = NULL;
+    if (rate != 44100) {      /* main.c:262-270: ratio = 44100 / fs, ceil(n * ratio) frames */
+        const char* tpath = getenv("SRT_RESAMPLER_TABLE");
+        FILE* tf = tpath ? fopen(tpath, "rb") : NULL;
+        table = (float*)malloc(22438 * sizeof(float));
+        if (!tf || fread(table, 4, 22438, tf) != 22438) {
+            fprintf(stderr, "%s is at %u Hz: set SRT_RESAMPLER_TABLE to the sinc table file (22438 float32) to convert it\n", argv[5], rate);
+            return -1;
+        }
+        fclose(tf);
     }
     /* net 0 of the blob = drum net, net 1 = vocal net (main.c:759-760) */
     float* w = (float*)malloc(2 * (size_t)SRT_COEFF_FLOATS * sizeof(float));
     if (srt_load_model_fp16(model, 0, w) || srt_load_model_fp16(model, 1, w + SRT_COEFF_FLOATS)) { fprintf(stderr, "%s\n", srt_last_error()); return 1; }
     const float* coeffs[2] = {w, w + SRT_COEFF_FLOATS};
 
+    /* tiles for the length at 44.1 kHz */
+    const double ratio = 44100.0 / (double)rate;
+    const size_t n_src = n;
+    if (table) n = srt_resample_frames(n_src, ratio);
     const size_t padded = (size_t)SRT_FFTSIZE * ((n + SRT_FFTSIZE - 1) / SRT_FFTSIZE) + 2 * SRT_FFTSIZE;   /* main.c:762-763 */
     const int tiles = (int)((padded / SRT_HOPSIZE + (size_t)T - 1) / (size_t)T);
     srt_config cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.time_step = T; cfg.bin_limit = F;
     cfg.max_batch_images = tiles;
-    cfg.max_images = tiles < 16 ? tiles : 16;           /* U-Net batch per pass; the rest of the tiles queue behind it */
+    cfg.max_images = tiles < 16 ? tiles : 16;           /* U-Net tiles per pass; a longer file runs in several passes */
     srt_ctx* ctx = NULL;
     if (srt_create_cli(&cfg, n_out, n_out == 3 ? coeffs : coeffs + 1, &ctx)) { fprintf(stderr, "srt_create_cli: %s\n", srt_last_error()); return 1; }
 
+    if (table) {
+        float* conv = (float*)srt_host_alloc(n * channels * sizeof(float));
+        size_t gen = 0;
+        if (srt_resample_host(ctx, pcm, n_src, (int)channels, ratio, table, 22438, 491, conv, n, &gen)) { fprintf(stderr, "resample: %s\n", srt_last_error()); return 1; }
+        srt_host_free(pcm);
+        pcm = conv;
+    }
     float* out[3];
     for (int q = 0; q < n_out; q++) out[q] = (float*)srt_host_alloc(n * 2 * sizeof(float));
     const float* in[1] = {pcm};

@@ -843,12 +843,16 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
                          const int* pcm_stride = nullptr, int out_stride = 1)
 {
     const int T = c->T, S = c->S, P = c->pairs();
+    const char* fo = getenv("SRT_FUSED_OLA");
+    const bool fused = !(fo && atoi(fo) == 0);
     BatchMeta m;
     for (int i = 0; i < n_streams; i++) {
         if (n_samples[i] == 0 || n_samples[i] > (size_t)1 << 30) return fail(SRT_ERR_ARG, "stream %d: bad length", i);
         const int nfr = (int)(padded_len(n_samples[i]) / kHop);
         const int tiles = (nfr + T - 1) / T;
-        if (tiles > c->B) return fail(SRT_ERR_CAPACITY, "stream %d needs %d tiles > max_images %d", i, tiles, c->B);
+        // the two-kernel synthesis (SRT_FUSED_OLA=0) keeps a stream's frames in a max_images-sized scratch; the fused kernel
+        // only needs the whole batch to fit max_batch_images
+        if (tiles > c->B && !fused) return fail(SRT_ERR_CAPACITY, "stream %d needs %d tiles > max_images %d", i, tiles, c->B);
         m.n.push_back((int)n_samples[i]);
         m.nfr.push_back(nfr);
         m.img0.push_back(m.total);
@@ -897,8 +901,6 @@ static int separate_core(srt_ctx* c, const float* const* d_pcmL, const float* co
     }
     // ---- mask * spectrum -> inverse FFT -> window -> overlap-add -> un-framing, one fused kernel
     // (SRT_FUSED_OLA=0 selects the two-kernel path through the scratch frames, kept for the tier-A istft())
-    const char* fo = getenv("SRT_FUSED_OLA");
-    const bool fused = !(fo && atoi(fo) == 0);
     if ((c->cli_mode || out_stride != 1) && !fused)
         return fail(SRT_ERR_STATE, "the CLI output modes and interleaved outputs need the fused iSTFT+OLA kernel (unset SRT_FUSED_OLA)");
     int max_fr = 0;

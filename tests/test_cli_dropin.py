@@ -134,3 +134,35 @@ def test_device_level_cli_host_matches_reference_cli(oracle, tmp_path, T, F, ste
         for c in range(2):
             err = float(np.sqrt(np.mean((ref[nm][:, c].astype(np.float64) - got[:, c]) ** 2)))
             assert err < TOL_RMS, (nm, c, err)
+
+
+RESAMPLER_TABLE = os.path.join(ROOT, "spleeterrt_b200", "weights", "resampler_mq.f32")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF_CLI) and os.path.exists(EXAMPLE_CLI) and os.path.exists(MODEL_FP16) and os.path.exists(RESAMPLER_TABLE)),
+                    reason="reference CLI / examples/_build / model blob / resampler table not built")
+def test_device_level_cli_host_resamples_like_the_reference(oracle, tmp_path):
+    """A 48 kHz stereo WAV: main.c:264-270 converts it to 44.1 kHz with libsamplerate before the path; the device-level
+    host does the same conversion with srt_resample_host (bit-identical) and then matches the reference CLI's stems."""
+    n48 = 4 * 48000
+    L, R = oracle.synth_pcm(11, n=n48)
+    wav = str(tmp_path / "in48.wav")
+    write_wav_f32(wav, np.stack([L, R], axis=1), rate=48000)
+    ref = run_cli(REF_CLI, str(tmp_path / "ref"), wav, 64, 512, 2)
+    os.makedirs(tmp_path / "dev", exist_ok=True)
+    env = dict(os.environ, SRT_RESAMPLER_TABLE=RESAMPLER_TABLE)
+    r = subprocess.run([EXAMPLE_CLI, "1", "64", "512", "2", wav, MODEL_FP16], cwd=str(tmp_path / "dev"), env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-500:])
+    n = int(np.ceil(n48 * 44100.0 / 48000.0))
+    for nm in ("Vocal", "Accompaniment"):
+        got = read_wav_f32(str(tmp_path / "dev" / f"in48.wav_{nm}.wav"))
+        assert got.shape == ref[nm].shape == (n, 2)
+        for c in range(2):
+            err = float(np.sqrt(np.mean((ref[nm][:, c].astype(np.float64) - got[:, c]) ** 2)))
+            assert err < TOL_RMS, (nm, c, err)
+    # vocal + accompaniment = the converted input, so the conversions agree to rounding
+    a = read_wav_f32(str(tmp_path / "dev" / "in48.wav_Vocal.wav")) + read_wav_f32(str(tmp_path / "dev" / "in48.wav_Accompaniment.wav"))
+    b = ref["Vocal"] + ref["Accompaniment"]
+    assert float(np.abs(a - b).max()) < 1e-6

@@ -336,6 +336,20 @@ def test_boundary_lengths_vs_oracle(srt, oracle, small_nets, n):
     assert rms(got - ref) < 1e-4 and np.abs(got - ref).max() < 1e-3
 
 
+def test_long_stream_runs_in_several_unet_passes(srt, oracle, small_nets):
+    """A stream with more T-frame tiles than the U-Net batch (max_images): the tiles go through in several passes
+    (processMT walks them one by one, main.c:545-577) and the result equals the all-at-once run bit for bit."""
+    L, R = oracle.synth_pcm(80, n=200000)                      # 4 tiles at T = 64
+    one = srt.Separator(small_nets[:1], 64, 128, max_images=1, max_batch_images=4)
+    a = one.separate([(L, R)])[0]
+    one.close()
+    allb = srt.Separator(small_nets[:1], 64, 128, max_images=4)
+    b = allb.separate([(L, R)])[0]
+    allb.close()
+    assert np.array_equal(a, b)
+    assert rms(a - oracle.separate(small_nets[:1], L, R, 64, 128)) < 1e-4
+
+
 def test_empty_inputs_are_errors(srt, oracle, small_nets):
     sep = srt.Separator(small_nets[:1], 64, 128, max_images=1)
     with pytest.raises(srt.SrtError):
