@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=32, help="10 s stereo streams per GPU per step")
     ap.add_argument("--max-images", type=int, default=0, help="U-Net tiles per pass (0 = streams)")
+    ap.add_argument("--stems", type=int, default=4, help="nets per stream (4 = the metric's configuration; 5 = BASELINE.json config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -195,7 +196,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     srt.load_library()
-    nets, wdesc = W.four_stem_nets()
+    nets, wdesc = W.stem_nets(args.stems)
     S = len(nets)
     ns = args.streams
     B = args.max_images or ns
@@ -360,12 +361,12 @@ def main():
         istft_bytes = 96.8e3 * frames * ns
         other = {k: layer_ms[k] / args.steps for k in ("down1", "up6", "up7", "stft", "istft", "ola")}
         line = {
-            "metric": "realtime_factor_4stem_44k1_stereo", "value": audio_s / (ms_step * 1e-3), "unit": "x_realtime",
+            "metric": f"realtime_factor_{S}stem_44k1_stereo", "value": audio_s / (ms_step * 1e-3), "unit": "x_realtime",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
             "frames_per_sec": frames * ns * world / (ms_step * 1e-3),
-            "config": {"workload": f"4-stem 44.1 kHz stereo, {ns} x 10 s streams per GPU per step, T=512 F=1024 (1 tile/stream), "
-                                   "STFT + 4 U-Nets + mask + iSTFT/OLA", "streams_per_gpu": ns, "time_step": T, "bin_limit": F,
+            "config": {"workload": f"{S}-stem 44.1 kHz stereo, {ns} x 10 s streams per GPU per step, T=512 F=1024 (1 tile/stream), "
+                                   f"STFT + {S} U-Nets + mask + iSTFT/OLA", "streams_per_gpu": ns, "time_step": T, "bin_limit": F,
                        "stems": S, "weights": wdesc, "l2": "per-step working set (activations) >> 126 MB L2; no explicit flush",
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "x_realtime", "ms_per_step": ms_e2e,

@@ -86,6 +86,19 @@ def four_stem_nets():
     return [(np.ascontiguousarray(n), 1) for n in nets], desc
 
 
+def stem_nets(n_stems):
+    """four_stem_nets() extended for BASELINE.json config 4 (5 stems: vocals / drums / bass / piano / other): the reference
+    has no 5-stem model, so stem k >= 4 is one more seeded jitter of a real net (SURVEY §8d recipe), ELU like the rest."""
+    nets, desc = four_stem_nets()
+    if n_stems <= 4:
+        return nets[:n_stems], desc
+    base = [c for c, _ in nets]
+    for k in range(4, n_stems):
+        src = base[k % 2 * 3]                      # alternate between the two real nets (index 0 and 3)
+        nets.append((np.ascontiguousarray(jitter(src, 777 + k) if model_blob_path() else synthetic_net(100 + k)), 1))
+    return nets, desc + f"; stems 5..{n_stems}: further seeded jitter nets"
+
+
 def synth_pcm(stream, n=441000):
     t = np.arange(n) / 44100.0
     out = []
