@@ -202,7 +202,8 @@ void launch_conv_tc(const ConvParams& p, cudaStream_t st)
     const bool want = mt_min_n < 0 ? ((p.n_tile == 256 && p.phases == 1) || (p.n_tile == 128 && p.phases == 4)) : (mt_min_n > 0 && p.n_tile >= mt_min_n);
     const int txy = p.tiles_x * p.tiles_y;
     int pair_mode = -1;
-    if (want) {
+    // pairing halves the CTA count: only where the unpaired grid already covers the SMs
+    if (want && (long)txy * p.tiles_n * p.S * p.n_tiles * p.phases >= 148) {
         if (txy % 2 == 0) pair_mode = 0;
         else if (txy == 1 && p.tiles_n > 1) pair_mode = 1;
     }

@@ -405,7 +405,9 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     for (int s = 0; s < S; s++) split = split || !weights_tf32_exact(coeffs[s]);
     if (const char* we = getenv("SRT_WEIGHT_SPLIT")) split = atoi(we) != 0;
     c->split_weights = split;
-    c->plans = build_plans(NetGeom{T, F}, c->B, split);
+    // small batches: narrower N tiles so that the deep layers fill the SMs (SRT_TC_NARROW=0 keeps the wide tiles)
+    const char* nwe = getenv("SRT_TC_NARROW");
+    c->plans = build_plans(NetGeom{T, F}, c->B, split, S, (nwe && atoi(nwe) == 0) ? 0 : c->sm_count);
     c->conv.resize(c->plans.size());
     for (size_t li = 0; li < c->plans.size(); li++) {
         const LayerPlan& L = c->plans[li];

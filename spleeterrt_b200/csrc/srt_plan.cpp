@@ -102,9 +102,17 @@ bool weights_tf32_exact(const float* coeff)
     return true;
 }
 
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights)
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int n_stems, int min_ctas)
 {
     std::vector<LayerPlan> plans;
+    auto narrow = [&](LayerPlan& L) {
+        if (min_ctas <= 0) return;
+        const long tiles = (long)ceil_div(L.Ws, L.tw) * ceil_div(L.Hs, L.th) * ceil_div(n_img, L.nb) * L.phases * (n_stems > 0 ? n_stems : 1);
+        while (L.n_tile > 64 && tiles * L.n_tiles < min_ctas) {
+            L.n_tile /= 2;
+            L.n_tiles *= 2;
+        }
+    };
     // ---- encoder: down2 .. down6 --------------------------------------------------------
     for (int i = 1; i <= 5; i++) {
         LayerPlan L{};
@@ -120,6 +128,7 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights)
         L.n_tile = L.cout > 256 ? 256 : L.cout;
         L.n_tiles = L.cout / L.n_tile;
         choose_tile(L.Ws, L.Hs, n_img, L.tw, L.th, L.nb);
+        narrow(L);
         if (L.cin >= 32) {
             for (int kh = 0; kh < 5; kh++)
                 for (int kw = 0; kw < 5; kw++) {
@@ -171,6 +180,7 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights)
         L.n_tile = L.cout;
         L.n_tiles = 1;
         choose_tile(L.Ws, L.Hs, n_img, L.tw, L.th, L.nb);
+        narrow(L);
         for (int po = 0; po < 2; po++)
             for (int qo = 0; qo < 2; qo++) {
                 const int p = po * 2 + qo;

@@ -86,7 +86,10 @@ CoeffLayout coeff_layout();
 // Build the 10 tensor-core layers for a T x F image and a batch of n_img images per launch.
 // split_weights: every k-block appears twice (part 0 / part 1) so that fp32 weights that are not exactly
 // representable in TF32 (the VST's fp32 `.dat` dumps) contribute w = tf32(w) + tf32(w - tf32(w)).
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false);
+// min_ctas > 0 (with the number of stems sharing a launch): a layer whose grid would hold fewer CTAs than that - the deep
+// layers of a one-tile batch are 8-16 CTAs of 80 us each on a 148-SM part - gets narrower N tiles (down to 64 columns:
+// below that an MMA does not get cheaper to issue), i.e. more and shorter CTAs.  0 keeps N = min(cout, 256).
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false, int n_stems = 1, int min_ctas = 0);
 
 // Pack one stem's weights for a layer into the k-block-major, 128B-swizzled layout the MMA
 // B operand is read from.  `coeff` is one spleeterCoeff blob.  Values are rounded to TF32
