@@ -13,6 +13,8 @@ using namespace srt;
 
 static bool g_split = false;   // two-term weights (weights not exactly representable in TF32)
 extern "C" void srt_host_model_set_split(int on) { g_split = on != 0; }
+static int g_min_ctas = 0;      // build_plans(min_ctas): narrower N tiles for small grids (what a small-batch context uses)
+extern "C" void srt_host_model_set_min_ctas(int v) { g_min_ctas = v; }
 
 static float act_apply(int act, float x)
 {
@@ -33,7 +35,7 @@ static float act_apply(int act, float x)
 extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
                                     float* out, int want_act)
 {
-    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split);
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split, 1, g_min_ctas);
     if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
     const LayerPlan& L = plans[plan_index];
     const CoeffLayout cl = coeff_layout();
@@ -110,7 +112,7 @@ extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* c
 
 extern "C" int srt_host_model_plan_info(int T, int F, int n_img, int plan_index, int* info /* tw,th,nb,n_tile,n_tiles,phases,nkb0..3 */)
 {
-    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, n_img);
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, n_img, false, 1, g_min_ctas);
     if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
     const LayerPlan& L = plans[plan_index];
     info[0] = L.tw; info[1] = L.th; info[2] = L.nb; info[3] = L.n_tile; info[4] = L.n_tiles; info[5] = L.phases;

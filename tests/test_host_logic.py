@@ -254,3 +254,40 @@ def test_resample_plan_matches_the_oracle_converter(oracle, ch):
         srt.resample_plan(100, 3, 1.0)
     with pytest.raises(srt.SrtError):
         srt.resample_plan(100, 2, 1000.0)
+
+
+def test_narrow_n_tiles_for_small_grids(oracle, host_model, small_nets):
+    """build_plans(min_ctas): a one-tile batch gets N tiles of 64-128 columns for the deep layers (more, shorter CTAs);
+    the gather-GEMM model over those plans (several N tiles per layer, also on decoder layers) still reproduces the
+    oracle's layer tensors, and big batches keep the wide tiles."""
+    info = (C.c_int * 10)()
+    host_model.srt_host_model_set_min_ctas(148)
+    try:
+        host_model.srt_host_model_plan_info(512, 1024, 1, 4, info)       # down6, one image: 512 couts -> 8 tiles of 64
+        assert (info[3], info[4]) == (64, 8)
+        host_model.srt_host_model_plan_info(512, 1024, 1, 5, info)       # up1: 4 phases x 1 tile -> 256 couts in 4 tiles
+        assert (info[3], info[4]) == (64, 4)
+        host_model.srt_host_model_plan_info(512, 1024, 32, 4, info)      # 32 images: 32 x 2 = 64 CTAs < 148 -> 128-wide tiles
+        assert info[3] * info[4] == 512 and info[3] >= 64
+        host_model.srt_host_model_plan_info(512, 1024, 32, 9, info)      # up5 at full batch: untouched
+        assert (info[3], info[4]) == (16, 1)
+        T, F = 64, 128
+        coeff = small_nets[0][0]
+        x = (np.abs(np.random.default_rng(5).standard_normal((2, T, F))) * 3).astype(np.float32)
+        _, tp = oracle.unet(coeff, x, 1, taps=True)
+        taps = oracle.split_taps(tp, T, F)
+        v = oracle.coeff_views(coeff)
+        for i in (4, 5):                                                   # down5, down6
+            bn = v[f"down{i}.bn"]
+            act_in = _act(3, bn[1][:, None, None] * taps[f"skip{i}"] + bn[0][:, None, None]).astype(np.float32)
+            ref = taps[f"skip{i+1}"]
+            got = _run_layer(host_model, T, F, i - 1, coeff, 3, act_in, None, ref.shape)
+            assert np.abs(got - ref).max() / np.abs(ref).max() < 2e-5
+        for d in (0, 1, 2):                                                # up1, up2, up3
+            s0 = taps["skip6"] if d == 0 else taps[f"skip{6-d}"]
+            s1 = None if d == 0 else taps[f"up{d}"]
+            ref = taps[f"up{d+1}"]
+            got = _run_layer(host_model, T, F, 5 + d, coeff, 3, s0, s1, ref.shape)
+            assert np.abs(got - ref).max() / max(1e-6, np.abs(ref).max()) < 2e-5
+    finally:
+        host_model.srt_host_model_set_min_ctas(0)
