@@ -706,11 +706,22 @@ static int run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask
         p.in = c->U[6]; p.w = c->d_w7; p.bias = c->d_b7; p.lut = c->d_lut; p.mask = mask_base;
         p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
         p.mask_stem_stride = mask_stride; p.mask_img0 = mask_img0;
-        for (int s = 0; s < S; s++) {
-            p.stem = s;
-            std::memcpy(p.wk, &c->h_w7[(size_t)s * 36], 36 * sizeof(float));
+        // per-stem launches keep the weights as immediates of the constant bank; when one stem's grid would not even fill
+        // the SMs (small batches) all stems share one launch instead of queueing behind each other
+        const long ctas_per_stem = (long)((c->F + 127) / 128) * ((c->T + 63) / 64) * Bv;
+        const char* m7 = getenv("SRT_UP7_MERGED");
+        if (S > 1 && S <= 8 && (m7 ? atoi(m7) != 0 : ctas_per_stem < 2L * c->sm_count)) {
+            p.merged = 1;
+            for (int s = 0; s < S; s++) std::memcpy(p.wk_all[s], &c->h_w7[(size_t)s * 36], 36 * sizeof(float));
             launch_up7(p, c->stream);
             c->launches++;
+        } else {
+            for (int s = 0; s < S; s++) {
+                p.stem = s;
+                std::memcpy(p.wk, &c->h_w7[(size_t)s * 36], 36 * sizeof(float));
+                launch_up7(p, c->stream);
+                c->launches++;
+            }
         }
     }
     cudaError_t e = cudaGetLastError();

@@ -155,6 +155,8 @@ struct Up7Params {                // 4x4 dilation-2 conv 1->2 + bias + sigmoid, 
     int mask_stem_stride, mask_img0;
     int stem;                     // one launch per stem
     float wk[36];                 // that stem's 32 weights + 2 biases (constant bank)
+    int merged;                   // 1: one launch covers all S stems (blockIdx.z = stem * Bv + image), weights from wk_all[stem]:
+    float wk_all[8][36];          // small batches, where four per-stem grids of a few dozen CTAs would run one after the other
 };
 
 // ---------------------------------------------------------------------------------------

@@ -271,11 +271,13 @@ __device__ __forceinline__ float sigmoid_exact(float a)
 // input rows (dilation 2) and the 4 columns share their 10-float input span, read as 3 LDS.128 per row:
 // 15 vector loads feed 8 pixels x 32 FMAs (the one-pixel-per-thread version issued 16 scalar LDS per pixel).
 // Accumulation order per output (kh-major, kw-minor, bias last) is the reference's (gemm row order).
+template <bool MERGED>
 __global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Params p)
 {
     __shared__ __align__(16) float tile[(U7_TH + 6) * U7_PITCH];
     __shared__ float2 lut_s[1025];
-    const int s = p.stem, b = blockIdx.z, n = s * p.B + b;
+    const int s = MERGED ? (int)blockIdx.z / p.Bv : p.stem, b = MERGED ? (int)blockIdx.z % p.Bv : (int)blockIdx.z, n = s * p.B + b;
+    const float* wk = MERGED ? p.wk_all[s] : p.wk;     // block-uniform: constant-bank operands either way
     const int f0 = blockIdx.x * U7_TW;
     const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
     const float* img = p.in + (size_t)n * p.T * p.F;
@@ -316,12 +318,12 @@ __global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Par
                 for (int j = 0; j < 4; j++) {
                     const float x = v[1 + j + 2 * kw];   // input column f + 2 kw - 3
                     if (q < 4) {
-                        acc[0][j][0] = fmaf(p.wk[q * 4 + kw], x, acc[0][j][0]);
-                        acc[0][j][1] = fmaf(p.wk[16 + q * 4 + kw], x, acc[0][j][1]);
+                        acc[0][j][0] = fmaf(wk[q * 4 + kw], x, acc[0][j][0]);
+                        acc[0][j][1] = fmaf(wk[16 + q * 4 + kw], x, acc[0][j][1]);
                     }
                     if (q >= 1) {
-                        acc[1][j][0] = fmaf(p.wk[(q - 1) * 4 + kw], x, acc[1][j][0]);
-                        acc[1][j][1] = fmaf(p.wk[16 + (q - 1) * 4 + kw], x, acc[1][j][1]);
+                        acc[1][j][0] = fmaf(wk[(q - 1) * 4 + kw], x, acc[1][j][0]);
+                        acc[1][j][1] = fmaf(wk[16 + (q - 1) * 4 + kw], x, acc[1][j][1]);
                     }
                 }
         }
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Par
                 float m[8];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float a0 = acc[a][j][0] + p.wk[32], a1 = acc[a][j][1] + p.wk[33];
+                    const float a0 = acc[a][j][0] + wk[32], a1 = acc[a][j][1] + wk[33];
                     if (p.lut) { m[2 * j] = sigmoid_lut(lut_s, a0); m[2 * j + 1] = sigmoid_lut(lut_s, a1); }
                     else { m[2 * j] = sigmoid_exact(a0); m[2 * j + 1] = sigmoid_exact(a1); }
                 }
@@ -347,8 +349,13 @@ __global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Par
 
 void launch_up7(const Up7Params& p, cudaStream_t st)
 {
-    dim3 grid((p.F + U7_TW - 1) / U7_TW, (p.T + U7_ROWS - 1) / U7_ROWS, p.Bv);   // one launch per stem (p.stem, p.wk)
-    up7_kernel<<<grid, 256, 0, st>>>(p);
+    dim3 grid((p.F + U7_TW - 1) / U7_TW, (p.T + U7_ROWS - 1) / U7_ROWS, p.Bv);   // one launch per stem (p.stem, p.wk) ...
+    if (p.merged) {                                                               // ... or one for all stems (p.wk_all)
+        grid.z = p.Bv * p.S;
+        up7_kernel<true><<<grid, 256, 0, st>>>(p);
+    } else {
+        up7_kernel<false><<<grid, 256, 0, st>>>(p);
+    }
 }
 
 // API layout [n][T][F][2] -> internal space-to-depth layout, TF32-rounded (srt_unet_device)
