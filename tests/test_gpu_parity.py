@@ -350,6 +350,17 @@ def test_long_stream_runs_in_several_unet_passes(srt, oracle, small_nets):
     assert rms(a - oracle.separate(small_nets[:1], L, R, 64, 128)) < 1e-4
 
 
+def test_maximum_bin_limit(srt, oracle, small_nets):
+    """F = 2048, the largest analyseBinLimit the CLI accepts (main.c:744-748): only the Nyquist bin is left to
+    unaffectedWeight."""
+    L, R = oracle.synth_pcm(90, n=30000)
+    sep = srt.Separator(small_nets[:1], 64, 2048, max_images=1)
+    got = sep.separate([(L, R)], unaffected=[0.25])[0]
+    sep.close()
+    ref = oracle.separate(small_nets[:1], L, R, 64, 2048, unaffected=0.25)
+    assert rms(got - ref) < 1e-4 and rms(ref) > 1e-3
+
+
 def test_empty_inputs_are_errors(srt, oracle, small_nets):
     sep = srt.Separator(small_nets[:1], 64, 128, max_images=1)
     with pytest.raises(srt.SrtError):
