@@ -193,3 +193,35 @@ def test_golden_resampler(oracle):
     for tag in ("48k_stereo", "48k_mono", "22k05_stereo", "96k_mono"):
         got, _ = oracle.resample(g[tag + "_in"], 44100.0 / float(g[tag + "_rate"]), table)
         assert np.array_equal(got, g[tag + "_out"].reshape(got.shape)), tag
+
+
+# ----------------------------------------------------------------------------- independent arbiter
+@pytest.mark.parametrize("mode", [0, 1])
+def test_arbiter_float64_functional_unet_matches_port(oracle, small_nets, mode):
+    """oracle/arbiter.py: textbook conv2d / conv_transpose2d semantics in float64 (torch-CPU) against the C restatement
+    (itself pinned to the reference build): layouts, paddings, crops, BN/activation order and the sigmoid LUT agree."""
+    from oracle import arbiter
+    coeff = small_nets[0][0] if mode else small_nets[1][0]
+    x = (np.abs(np.random.default_rng(17 + mode).standard_normal((2, 64, 128))) * 3).astype(np.float32)
+    ref = oracle.unet(coeff, x, mode)
+    got = arbiter.unet(coeff, x, mode).numpy()
+    assert np.abs(got - ref).max() < 2e-5
+    vst = arbiter.unet(coeff, x, mode, flavour=1).numpy()
+    assert np.abs(vst - oracle.unet(coeff, x, mode, flavour=1)).max() < 2e-5
+
+
+def test_tf32_emulation_error_budget(oracle, small_nets):
+    """Rounding the tensors the GPU epilogues store for tensor-core consumers to TF32 (arbiter, float64 otherwise) moves
+    the mask by ~1e-4 RMS: the budget the GPU parity tolerances (5e-4 mask, 1e-4 stem) are set against.  No single
+    tensor dominates (tools/tf32_attribution.py)."""
+    from oracle import arbiter
+    coeff = small_nets[1][0]
+    x = (np.abs(np.random.default_rng(23).standard_normal((2, 64, 256))) * 3).astype(np.float32)
+    ref = arbiter.unet(coeff, x, 0).numpy()
+    emu = arbiter.unet(coeff, x, 0, round_at="all").numpy()
+    err = float(np.sqrt(np.mean((emu - ref) ** 2)))
+    assert 1e-7 < err < 5e-4
+    one = arbiter.unet(coeff, x, 0, round_at=["U2"]).numpy()
+    assert float(np.sqrt(np.mean((one - ref) ** 2))) < err
+    t = arbiter.round_tf32(__import__("torch").tensor([1.0 + 2.0 ** -11, 1.0 + 2.0 ** -12, -3.0], dtype=__import__("torch").float64))
+    assert t.tolist() == [1.0 + 2.0 ** -10, 1.0, -3.0]
