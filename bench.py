@@ -145,11 +145,13 @@ def reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample():
-    """Bounded CPU sample for the GPU arm's JSON line: one 10 s stream, 4 stems, all host threads."""
+def cpu_baseline_sample(nets=None, pcm=None, gpu_stems=None):
+    """Bounded CPU sample for the GPU arm's JSON line: one 10 s stream, 4 stems, all host threads.  The same run is the
+    parity check of the bench's own configuration: `gpu_stems` (stream 0 of the GPU batch, float32[S][2][n]) against
+    the CPU result, RMS per stem (outside every timed region)."""
     from oracle import oracle as O
-    nets = O.four_stem_weights()
-    L, R = O.synth_pcm(0, n=N_SAMPLES)
+    nets = nets if nets is not None else O.four_stem_weights()
+    L, R = pcm if pcm is not None else O.synth_pcm(0, n=N_SAMPLES)
     cores = host_threads()
     have_ref = O.have_ref()
     if have_ref:
@@ -157,13 +159,21 @@ def cpu_baseline_sample():
     set_host_threads(cores)
     t0 = time.perf_counter()
     if have_ref:
-        O.ref_exec().separate(nets, L, R, T, F, unaffected=0.1)
+        ref = O.ref_exec().separate(nets, L, R, T, F, unaffected=0.1)
     else:
-        O.separate(nets, L, R, T, F, unaffected=0.1)
+        ref = O.separate(nets, L, R, T, F, unaffected=0.1)
     dt = time.perf_counter() - t0
-    return {"value": SECONDS / dt, "unit": "x_realtime", "cores": cores, "kind": "reference" if have_ref else "port",
-            "sample": f"1 stream x 10 s x 4 stems, {dt:.2f} s wall; reference C sources (oracle/_ref, -O2 -fopenmp -DCPU_GEMM=1 naive sgemm)"
-            if have_ref else f"1 stream x 10 s x 4 stems, {dt:.2f} s wall; oracle port (oracle/srt_oracle.c)"}
+    S = len(nets)
+    base = {"value": SECONDS / dt, "unit": "x_realtime", "cores": cores, "kind": "reference" if have_ref else "port",
+            "sample": f"1 stream x 10 s x {S} stems, {dt:.2f} s wall; reference C sources (oracle/_ref, -O2 -fopenmp -DCPU_GEMM=1 naive sgemm)"
+            if have_ref else f"1 stream x 10 s x {S} stems, {dt:.2f} s wall; oracle port (oracle/srt_oracle.c)"}
+    parity = None
+    if gpu_stems is not None:
+        err = [float(np.sqrt(np.mean((gpu_stems[s].astype(np.float64) - ref[s]) ** 2))) for s in range(S)]
+        lvl = [float(np.sqrt(np.mean(ref[s].astype(np.float64) ** 2))) for s in range(S)]
+        parity = {"stem_rms_err": err, "stem_rms": lvl, "tolerance": 1e-4, "ok": bool(max(err) < 1e-4),
+                  "against": base["kind"], "what": "stream 0 of the timed batch, every stem, both channels, all 441000 samples"}
+    return base, parity
 
 
 def main():
@@ -176,6 +186,8 @@ def main():
     ap.add_argument("--max-images", type=int, default=0, help="U-Net tiles per pass (0 = streams)")
     ap.add_argument("--stems", type=int, default=4, help="nets per stream (4 = the metric's configuration; 5 = BASELINE.json config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="compensated", choices=["compensated", "tf32"],
+                    help="srt_config.precision: compensated = TF32 main term + bf16 residual term (default, fp32-grade), tf32 = single pass")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -202,7 +214,8 @@ def main():
     B = args.max_images or ns
     stream = torch.cuda.Stream()            # a real (non-default) stream shared by torch events and the context
     torch.cuda.set_stream(stream)
-    sep = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream)
+    sep = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream,
+                        precision=args.precision)
 
     # ---- inputs: stream i of the global batch lives on rank i mod world (dispatch.py) -----------
     from spleeterrt_b200 import dispatch as D
@@ -311,7 +324,8 @@ def main():
     # ---- single stream (BASELINE.json configs[1]): one 10 s stereo stream, 4 stems, latency --------------
     single = None
     if rank == 0:
-        sep1 = srt.Separator(nets, T, F, max_images=1, max_batch_images=1, device=local_rank, cuda_stream=stream.cuda_stream)
+        sep1 = srt.Separator(nets, T, F, max_images=1, max_batch_images=1, device=local_rank, cuda_stream=stream.cuda_stream,
+                             precision=args.precision)
         n1 = (C.c_size_t * 1)(N_SAMPLES)
         d1l, d1r = (C.c_void_p * 1)(din[0, 0].data_ptr()), (C.c_void_p * 1)(din[0, 1].data_ptr())
         d1o = (C.c_void_p * (S * 2))(*[dout[0, s, c].data_ptr() for s in range(S) for c in range(2)])
@@ -363,11 +377,13 @@ def main():
         line = {
             "metric": f"realtime_factor_{S}stem_44k1_stereo", "value": audio_s / (ms_step * 1e-3), "unit": "x_realtime",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32+bf16" if args.precision == "compensated" else "tf32", "data": "synthetic",
             "frames_per_sec": frames * ns * world / (ms_step * 1e-3),
             "config": {"workload": f"{S}-stem 44.1 kHz stereo, {ns} x 10 s streams per GPU per step, T=512 F=1024 (1 tile/stream), "
                                    f"STFT + {S} U-Nets + mask + iSTFT/OLA", "streams_per_gpu": ns, "time_step": T, "bin_limit": F,
-                       "stems": S, "weights": wdesc, "l2": "per-step working set (activations) >> 126 MB L2; no explicit flush",
+                       "stems": S, "precision": args.precision + (" (tf32(a) x w + bf16(a - tf32(a)) x bf16(w), fp32 accumulate)" if args.precision == "compensated"
+                                                                    else " (single-pass TF32 operands, fp32 accumulate)"), "weights": wdesc, "l2": "per-step working set (activations) >> 126 MB L2; no explicit flush",
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
             "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "x_realtime", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(hin.numel() * 4), "d2h_bytes_per_step": int(hout.numel() * 4),
@@ -390,7 +406,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline_sample()
+                gpu0 = dout[0].cpu().numpy() if my_streams[0] == 0 else None      # stream 0 of the timed batch (device path)
+                line["cpu_baseline"], line["parity"] = cpu_baseline_sample([(np.asarray(c), m) for c, m in nets], pcm[0], gpu0)
             except Exception as e:  # the checker being unavailable must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "x_realtime", "cores": os.cpu_count(), "kind": "unavailable",
                                         "sample": repr(e)}

@@ -53,7 +53,15 @@ typedef struct {
     int flavour;           /* 0 = Executable (LUT sigmoid, ELU clamp -15), 1 = VST (exact sigmoid) */
     int conv_impl;         /* 0 = tcgen05 tensor-core kernels (the product), 1 = SIMT verification kernels */
     void* cuda_stream;     /* optional cudaStream_t to enqueue on (NULL = context-owned stream) */
+    int precision;         /* arithmetic of the ten tensor-core layers (accumulation is fp32 in both):
+                            *   0 = SRT_PRECISION_COMPENSATED (default): activations feed the MMAs as tf32(a) PLUS the bf16
+                            *       residual a - tf32(a) (second, half-size contraction into the same accumulator):
+                            *       operand error ~2^-19, stems agree with the fp32 reference to ~1e-6 RMS at any level;
+                            *   1 = SRT_PRECISION_TF32: single-pass TF32 operands (2^-12): ~1.3x faster U-Net, stem error
+                            *       ~1e-4 of the stem's level (3e-5 RMS on the -12 dBFS test signal, above 1e-4 at full scale). */
 } srt_config;
+#define SRT_PRECISION_COMPENSATED 0
+#define SRT_PRECISION_TF32 1
 
 /* coeffs[s]: one spleeterCoeff blob (SRT_COEFF_FLOATS floats, host memory) per stem;
  * stem_modes[s]: 0 = LeakyReLU(0.2)/ReLU, !=0 = ELU/ELU (spleeter.c:130-139).

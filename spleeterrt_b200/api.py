@@ -38,7 +38,20 @@ class SrtError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("n_stems", C.c_int), ("time_step", C.c_int), ("bin_limit", C.c_int),
                 ("max_images", C.c_int), ("max_batch_images", C.c_int), ("flavour", C.c_int),
-                ("conv_impl", C.c_int), ("cuda_stream", C.c_void_p)]
+                ("conv_impl", C.c_int), ("cuda_stream", C.c_void_p), ("precision", C.c_int)]
+
+
+PRECISION_COMPENSATED, PRECISION_TF32 = 0, 1      # srt_config.precision (include/srt_b200.h)
+
+
+def _precision(p):
+    if p is None:
+        return PRECISION_COMPENSATED
+    if p in ("compensated", "tf32+bf16", PRECISION_COMPENSATED):
+        return PRECISION_COMPENSATED
+    if p in ("tf32", PRECISION_TF32):
+        return PRECISION_TF32
+    raise SrtError(f"unknown precision {p!r} (compensated | tf32)")
 
 
 def lib_path():
@@ -193,12 +206,12 @@ class Separator:
     """
 
     def __init__(self, nets, time_step, bin_limit, max_images=1, max_batch_images=0, device=0, flavour=0,
-                 conv_impl=None, cuda_stream=None):
+                 conv_impl=None, cuda_stream=None, precision=None):
         self.lib = load_library()
         if conv_impl is None:
             conv_impl = 1 if os.environ.get("SRT_CONV_IMPL", "") == "simt" else 0
         cfg = _Config(device, len(nets), time_step, bin_limit, max_images, max_batch_images, flavour, conv_impl,
-                      cuda_stream)
+                      cuda_stream, _precision(precision))
         self.S, self.T, self.F = len(nets), time_step, bin_limit
         self.max_images = max_images
         coeffs = [np.ascontiguousarray(c, np.float32) for c, _ in nets]
@@ -258,8 +271,7 @@ class Separator:
     def separate(self, streams, unaffected=None):
         """streams: list of (L, R) float32 arrays.  Returns list of float32[S][2][n]."""
         ns = len(streams)
-        Ls = [np.ascontiguousarray(l, np.float32) for l, _ in streams]
-        Rs = [np.ascontiguousarray(r, np.float32) for _, r in streams]
+        Ls, Rs = self._channels(streams)
         n = (C.c_size_t * ns)(*[l.size for l in Ls])
         pl = (C.c_void_p * ns)(*[l.ctypes.data for l in Ls])
         pr = (C.c_void_p * ns)(*[r.ctypes.data for r in Rs])
@@ -270,6 +282,16 @@ class Separator:
             uw = (C.c_float * self.S)(*[float(u) for u in unaffected])
         self._check(self.lib.srt_separate_batch(self.h, pl, pr, n, ns, uw, po))
         return outs
+
+    @staticmethod
+    def _channels(streams):
+        """contiguous float32 (L, R) per stream; the C side reads n = L.size samples of BOTH, so a shorter R is an error"""
+        Ls = [np.ascontiguousarray(l, np.float32).ravel() for l, _ in streams]
+        Rs = [np.ascontiguousarray(r, np.float32).ravel() for _, r in streams]
+        for i, (l, r) in enumerate(zip(Ls, Rs)):
+            if l.size == 0 or l.size != r.size:
+                raise SrtError(f"stream {i}: L has {l.size} samples, R has {r.size}; both channels need the same non-zero length")
+        return Ls, Rs
 
     def separate_interleaved(self, frames, unaffected=None):
         """frames: list of float32[n][channels] (channels 1 or 2) or float32[n] (mono): interleaved frames as a WAV
@@ -290,8 +312,7 @@ class Separator:
         """Like separate(), but only enqueues the batch (srt_separate_batch_async).  Returns a pending handle;
         result(handle) waits and returns the stems.  Up to three batches are in flight per Separator; a fourth submit first drains the oldest."""
         ns = len(streams)
-        Ls = [np.ascontiguousarray(l, np.float32) for l, _ in streams]
-        Rs = [np.ascontiguousarray(r, np.float32) for _, r in streams]
+        Ls, Rs = self._channels(streams)
         n = (C.c_size_t * ns)(*[l.size for l in Ls])
         pl = (C.c_void_p * ns)(*[l.ctypes.data for l in Ls])
         pr = (C.c_void_p * ns)(*[r.ctypes.data for r in Rs])
@@ -375,13 +396,13 @@ class CliSeparator(Separator):
     """
 
     def __init__(self, coeffs, n_outputs, time_step, bin_limit, max_images=1, max_batch_images=0, device=0,
-                 conv_impl=None, cuda_stream=None):
+                 conv_impl=None, cuda_stream=None, precision=None):
         self.lib = load_library()
         if conv_impl is None:
             conv_impl = 1 if os.environ.get("SRT_CONV_IMPL", "") == "simt" else 0
         if len(coeffs) != n_outputs - 1:
             raise SrtError("n_outputs = 2 takes one net (vocal), n_outputs = 3 two (drum, vocal)")
-        cfg = _Config(device, 1, time_step, bin_limit, max_images, max_batch_images, 0, conv_impl, cuda_stream)
+        cfg = _Config(device, 1, time_step, bin_limit, max_images, max_batch_images, 0, conv_impl, cuda_stream, _precision(precision))
         self.T, self.F = time_step, bin_limit
         self.max_images = max_images
         blobs = [np.ascontiguousarray(c, np.float32) for c in coeffs]
@@ -402,11 +423,11 @@ class Streamer:
     """Real-time streaming flavour: mirrors Spleeter4StemsInit / ProcessSamples / Free
     (VST/Source/Spleeter4Stems.h:67-69).  nets: list of coeff arrays (all ELU, as the VST does)."""
 
-    def __init__(self, coeffs, time_step, bin_limit, device=0, unaffected=None):
+    def __init__(self, coeffs, time_step, bin_limit, device=0, unaffected=None, precision=None):
         self.lib = load_library()
         self.S = len(coeffs)
         self._coeffs = [np.ascontiguousarray(c, np.float32) for c in coeffs]
-        cfg = _Config(device, self.S, time_step, bin_limit, 1, 1, 1, 0, None)
+        cfg = _Config(device, self.S, time_step, bin_limit, 1, 1, 1, 0, None, _precision(precision))
         cp = (C.c_void_p * self.S)(*[c.ctypes.data for c in self._coeffs])
         uw = None
         if unaffected is not None:

@@ -27,7 +27,7 @@
 namespace srt {
 
 // threads per CTA = (EPW epilogue warps + 3 control warps) * 32; EPW = 8, or 16 where shared memory allows (down1)
-constexpr int kRpMaxChunks = 8, kRpMaxKB = 80, kRpMaxWStages = 12;
+constexpr int kRpMaxChunks = 12, kRpMaxKB = 112, kRpMaxWStages = 12;   // up4 with two-term weights + compensation: 6 chunks, 90 k-blocks
 
 struct RpHeader {
     uint64_t patch_full[2], patch_empty[2];
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
     if (warp == kWarpPatch && lane == 0) {
         ptx::tma_prefetch_desc(&p.tmap[0]);
         ptx::tma_prefetch_desc(&p.tmap[1]);
+        ptx::tma_prefetch_desc(&p.tmap[2]);
         for (int i = 0; i < 2; i++) {
             ptx::mbar_init(&hdr->patch_full[i], 1);
             ptx::mbar_init(&hdr->patch_empty[i], 1);
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
     } else if (warp == kWarpMma) {
         // ===== MMA issuer ==========================================================================
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N);
+            constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N), idesc_lo = ptx::umma_idesc_bf16(kTileM, N);
             int ws = 0, ps = 0, as = 0;
             uint32_t wph = 0, pph = 0, aph = 0;
             for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -168,7 +169,17 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
                         const uint32_t b_lo = ptx::umma_desc_lo(wring_base + (uint32_t)ws * kWBytes);
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
-                        if (!(p.dbg & 2))
+                        if (p.dbg & 2) {}
+                        else if (KB == 32 && (kb.part & kPartLo)) {
+                            // compensation block: the patch holds 64 bf16 residuals per pixel in the same 128-byte rows; 4 x K = 16
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) {
+#pragma unroll
+                                for (int r = 0; r < R; r++)
+                                    ptx::mma_bf16_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2),
+                                                        idesc_lo, (kk != 0) ? 1u : (first ? 0u : 1u), kDescHi);
+                            }
+                        } else
                         // K step outer, row inner: consecutive MMAs hit different accumulators (dependent MMAs on one
                         // accumulator cost ~100 cycles each, independent ones ~60: tools/mma_probe.cu)
 #pragma unroll
@@ -261,6 +272,8 @@ static void launch_rp(const RowConvParams& p, cudaStream_t st)
     dim3 grid(n_tiles < sms ? n_tiles : sms, 1, 1);
     conv_rp_kernel<N, R, WS, KB, EPW><<<grid, (EPW + 3) * 32, smem, st>>>(p);
 }
+
+bool conv_rp_fits(int n_chunks, int nkb) { return n_chunks <= kRpMaxChunks && nkb <= kRpMaxKB; }
 
 void launch_conv_rp(const RowConvParams& p, cudaStream_t st)
 {

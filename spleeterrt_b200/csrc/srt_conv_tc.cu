@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     if (warp == 8 && lane == 0) {
         ptx::tma_prefetch_desc(&p.tmap[0]);
         ptx::tma_prefetch_desc(&p.tmap[1]);
+        ptx::tma_prefetch_desc(&p.tmap[2]);
         for (int i = 0; i < stages; i++) {
             ptx::mbar_init(&hdr->full[i], 1);
             ptx::mbar_init(&hdr->empty[i], 1);
@@ -127,14 +128,22 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     } else if (warp == 9) {
         // ===== MMA issuer ================================================================
         if (ptx::elect_one()) {   // not `lane == 0`: see srt_ptx.cuh (straight-line UTCHMMA / UTMALDG issue)
-            constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N_TILE);
+            constexpr uint32_t idesc = ptx::umma_idesc_tf32(kTileM, N_TILE), idesc_lo = ptx::umma_idesc_bf16(kTileM, N_TILE);
             int stage = 0;
             uint32_t ph = 0;
             for (int k = 0; k < nkb; k++) {
+                const bool comp = (hdr->kb[k].part & kPartLo) != 0;   // compensation block: bf16 operands, 4 x K = 16 over the same 128-byte rows
                 ptx::mbar_wait(&hdr->full[stage], ph);
                 ptx::tc_fence_after();
                 const uint32_t a_lo = ptx::umma_desc_lo(tiles_base + (uint32_t)stage * kStageBytes);
                 const uint32_t b_lo = a_lo + ((MT * kABytes) >> 4);
+                if (comp) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                        for (int m = 0; m < MT; m++)
+                            ptx::mma_bf16_ss_lo(tmem_d + m * N_TILE, a_lo + m * (kABytes >> 4) + kk * 2, b_lo + kk * 2, idesc_lo, (kk != 0) ? 1u : (k != 0 ? 1u : 0u));
+                } else
 #pragma unroll
                 for (int kk = 0; kk < kKB / 8; kk++)
 #pragma unroll
@@ -191,7 +200,9 @@ static void launch_one(const ConvParams& p, int pair_mode, cudaStream_t st)
     conv_tc_kernel<N_TILE, MT><<<grid, kConvThreads, smem, st>>>(p, stages, pair_mode);
 }
 
-void launch_conv_tc(const ConvParams& p, cudaStream_t st)
+bool conv_tc_supported(int n_tile) { return n_tile == 16 || n_tile == 32 || n_tile == 64 || n_tile == 128 || n_tile == 256; }
+
+void launch_conv_tc(const ConvParams& p, cudaStream_t st, int sm_count)
 {
     // Two tiles per CTA where the weight stream is the larger part of the SM's intake (see the header).  Measured per layer
     // on the 32-stream bench (profiles/r1q_tc_mt_sweep.txt): down5 0.212 -> 0.198, down6 0.164 -> 0.148, up2 0.362 -> 0.341 ms,
@@ -203,7 +214,7 @@ void launch_conv_tc(const ConvParams& p, cudaStream_t st)
     const int txy = p.tiles_x * p.tiles_y;
     int pair_mode = -1;
     // pairing halves the CTA count: only where the unpaired grid already covers the SMs
-    if (want && (long)txy * p.tiles_n * p.S * p.n_tiles * p.phases >= 148) {
+    if (want && (long)txy * p.tiles_n * p.S * p.n_tiles * p.phases >= sm_count) {
         if (txy % 2 == 0) pair_mode = 0;
         else if (txy == 1 && p.tiles_n > 1) pair_mode = 1;
     }
@@ -221,7 +232,7 @@ void launch_conv_tc(const ConvParams& p, cudaStream_t st)
     case 64: launch_one<64, 1>(p, 0, st); break;
     case 128: launch_one<128, 1>(p, 0, st); break;
     case 256: launch_one<256, 1>(p, 0, st); break;
-    default: break;
+    default: break;   // unreachable: srt_create rejects plans with an N tile conv_tc_supported() does not list
     }
 }
 

@@ -54,6 +54,20 @@ __device__ __forceinline__ void store16_warp(float* dst, const float* v, float4*
     __syncwarp();
 }
 
+// 16 residuals v - tf32(v) of one pixel -> 32 bytes of bf16 (two 16-byte stores per lane; every lane writes one whole
+// 32-byte sector).  dst == nullptr: nothing stored (pixel outside the tensor).
+__device__ __forceinline__ void store16_lo(uint16_t* dst, const float* lo)
+{
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = ptx::pack_bf16x2(lo[2 * i], lo[2 * i + 1]);
+    if (dst) {
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
 // Branch-free activations for the tensor-core epilogues.  The epilogue warps are instruction-latency
 // bound (ncu / tools/stage_sweep.py: the epilogue, not the MMAs, dominates down1 and costs as much as the
 // MMAs of the small-N layers), so the activation kind is resolved once per 16-channel chunk and ELU is
@@ -78,22 +92,26 @@ __device__ __forceinline__ float act_fast(float x)
     return x;
 }
 
+// o = the stored value (TF32-rounded when `round`), l = what the rounding dropped (exact in fp32; stored as bf16 for the
+// consumer's compensation blocks when the layer runs in compensated precision)
 template <int ACT>
-__device__ __forceinline__ void dec16(const float* v, const float* bias, const float* sc, const float* of, bool round, float* o)
+__device__ __forceinline__ void dec16(const float* v, const float* bias, const float* sc, const float* of, bool round, float* o, float* l)
 {
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const float t = fmaf(sc[i], act_fast<ACT>(v[i] + bias[i]), of[i]);
         o[i] = round ? ptx::rna_tf32(t) : t;
+        l[i] = t - o[i];
     }
 }
 template <int ACT>
-__device__ __forceinline__ void enc16(const float* raw, const float* sc, const float* of, bool round, float* a)
+__device__ __forceinline__ void enc16(const float* raw, const float* sc, const float* of, bool round, float* a, float* l)
 {
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const float t = act_fast<ACT>(fmaf(sc[i], raw[i], of[i]));
         a[i] = round ? ptx::rna_tf32(t) : t;
+        l[i] = t - a[i];
     }
 }
 
@@ -108,37 +126,48 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
     float bias[16];
     load16(p.bias + s * p.cout + c0, bias);
     if (p.mode == 2) {
-        float sc[16], of[16], o[16];
+        float sc[16], of[16], o[16], l[16];
         load16(p.bn_scale + s * p.cout + c0, sc);
         load16(p.bn_offset + s * p.cout + c0, of);
-        if (act == ACT_ELU_CLAMP) dec16<ACT_ELU_CLAMP>(v, bias, sc, of, p.round_act, o);
-        else if (act == ACT_RELU) dec16<ACT_RELU>(v, bias, sc, of, p.round_act, o);
-        else dec16<ACT_ELU>(v, bias, sc, of, p.round_act, o);
+        if (act == ACT_ELU_CLAMP) dec16<ACT_ELU_CLAMP>(v, bias, sc, of, p.round_act, o, l);
+        else if (act == ACT_RELU) dec16<ACT_RELU>(v, bias, sc, of, p.round_act, o, l);
+        else dec16<ACT_ELU>(v, bias, sc, of, p.round_act, o, l);
         const int oy = 2 * Y + (phase >> 1), ox = 2 * X + (phase & 1);
-        float* dst = p.out_dec + (((size_t)n * (2 * p.Hs) + oy) * (2 * p.Ws) + ox) * p.cout + c0;
+        const size_t opix = ((size_t)n * (2 * p.Hs) + oy) * (2 * p.Ws) + ox;
+        float* dst = p.out_dec + opix * p.cout + c0;
         if (stage) store16_warp(valid ? dst : nullptr, o, stage);
         else store16(dst, o);
+        if (p.lo_dec) store16_lo(valid ? p.lo_dec + opix * p.lo_dec_C + p.lo_dec_coff + c0 : nullptr, l);
         return;
     }
     float raw[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) raw[i] = v[i] + bias[i];
     if (p.mode == 0) {
-        float sc[16], of[16], a[16];
+        float sc[16], of[16], a[16], l[16];
         load16(p.bn_scale + s * p.cout + c0, sc);
         load16(p.bn_offset + s * p.cout + c0, of);
-        if (act == ACT_ELU_CLAMP) enc16<ACT_ELU_CLAMP>(raw, sc, of, p.round_act, a);
-        else if (act == ACT_LEAKY) enc16<ACT_LEAKY>(raw, sc, of, p.round_act, a);
-        else enc16<ACT_ELU>(raw, sc, of, p.round_act, a);
-        float* dst = p.out_act + ((((size_t)n * (p.Hs / 2) + Y / 2) * (p.Ws / 2) + X / 2) * 4 + (Y & 1) * 2 + (X & 1)) * p.cout + c0;
+        if (act == ACT_ELU_CLAMP) enc16<ACT_ELU_CLAMP>(raw, sc, of, p.round_act, a, l);
+        else if (act == ACT_LEAKY) enc16<ACT_LEAKY>(raw, sc, of, p.round_act, a, l);
+        else enc16<ACT_ELU>(raw, sc, of, p.round_act, a, l);
+        const size_t apix = (((size_t)n * (p.Hs / 2) + Y / 2) * (p.Ws / 2) + X / 2) * 4 + (Y & 1) * 2 + (X & 1);
+        float* dst = p.out_act + apix * p.cout + c0;
         if (stage) store16_warp(valid ? dst : nullptr, a, stage);
         else store16(dst, a);
+        if (p.lo_act) store16_lo(valid ? p.lo_act + apix * p.cout + c0 : nullptr, l);
     }
+    const size_t rpix = ((size_t)n * p.Hs + Y) * p.Ws + X;
     if (p.round_raw) {
+        float l[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) raw[i] = ptx::rna_tf32(raw[i]);
+        for (int i = 0; i < 16; i++) {
+            const float hi = ptx::rna_tf32(raw[i]);
+            l[i] = raw[i] - hi;
+            raw[i] = hi;
+        }
+        if (p.lo_raw) store16_lo(valid ? p.lo_raw + rpix * p.lo_raw_C + p.lo_raw_coff + c0 : nullptr, l);
     }
-    float* dst = p.out_raw + (((size_t)n * p.Hs + Y) * p.Ws + X) * p.cout + c0;
+    float* dst = p.out_raw + rpix * p.cout + c0;
     if (stage) store16_warp(valid ? dst : nullptr, raw, stage);
     else store16(dst, raw);
 }

@@ -43,7 +43,10 @@ struct LaunchState {
 // Image index n runs over S stems x B images, stem-major: n = s*B + b.
 // ---------------------------------------------------------------------------------------
 struct alignas(64) ConvParams {
-    CUtensorMap tmap[2];          // source activation tensors, dims {C, W, H, S*B}, box {32, tw, th, nb}, SW128
+    CUtensorMap tmap[3];          // source activation tensors, dims {C, W, H, S*B}, box {32, tw, th, nb}, SW128; [2] = the bf16 residual
+                                  // tensor of compensated layers (box {64, tw, th, nb}: the same 128-byte rows)
+    const uint16_t* lo_ptr;       // the residual tensor as a raw pointer (SIMT verification path), lo_C channels per pixel
+    int lo_C;
     const float* src_ptr[2];      // same tensors as raw pointers (SIMT verification path)
     int src_C[2];
     const KBlock* kb;             // all phases back to back
@@ -69,11 +72,17 @@ struct alignas(64) ConvParams {
     float* out_act;               // encoder: S2D  [n][Hs/2][Ws/2][4*cout]  act(scale*v+offset)
     float* out_dec;               // decoder: NHWC [n][2Hs][2Ws][cout]  scale*act(v)+offset
     int round_raw, round_act;     // round stored values to TF32 (consumer is a tensor-core layer)
+    // compensated precision: next to every TF32-rounded value hi = tf32(v) the epilogue stores bf16(v - hi) for the
+    // consumer's compensation k-blocks (srt_plan.h build_plans).  nullptr = the consumer runs single-pass TF32.
+    uint16_t* lo_raw;             // residual of out_raw:  [n][Hs][Ws][lo_raw_C], this layer's channels at lo_raw_coff
+    uint16_t* lo_act;             // residual of out_act:  same space-to-depth layout as out_act
+    uint16_t* lo_dec;             // residual of out_dec:  [n][2Hs][2Ws][lo_dec_C], this layer's channels at lo_dec_coff
+    int lo_raw_C, lo_raw_coff, lo_dec_C, lo_dec_coff;
 };
 
 // Row-patch tensor-core kernel (srt_conv_rp.cu): small-N layers, see srt_plan.h RowPlan.
 struct alignas(64) RowConvParams {
-    CUtensorMap tmap[2];          // dims {C, W, H, S*B}, box {32, kPatchW, R+2, 1}, SW128
+    CUtensorMap tmap[3];          // dims {C, W, H, S*B}, box {32, kPatchW, R+2, 1}, SW128; [2] = bf16 residual tensor, box {64, kPatchW, R+2, 1}
     const RowChunk* chunks;
     int n_chunks;
     const KBlock* kb;
@@ -91,6 +100,7 @@ struct alignas(64) RowConvParams {
     ConvParams ep;                // geometry + epilogue (tmap / k-block fields unused)
 };
 void launch_conv_rp(const RowConvParams& p, cudaStream_t st);
+bool conv_rp_fits(int n_chunks, int nkb);   // table sizes the kernel's shared-memory header holds
 
 // ---------------------------------------------------------------------------------------
 // SIMT edge layers
@@ -104,6 +114,7 @@ struct Down1Params {              // 5x5 s2 conv 2->16 on the magnitude image, s
     const float* bn_offset;       // [S][16]
     float* out_raw;               // [S*B][T/2][F/2][16]
     float* out_act;               // S2D [S*B][T/4][F/4][64], TF32-rounded
+    uint16_t* lo_act;             // bf16 residual of out_act (compensated down2) or nullptr
     int T, F, B, Bv, S;
     int act[8];
     int stem;                     // one launch per stem: weights / bias / BN ride in the constant bank
@@ -267,7 +278,8 @@ struct DiffParams {
 void launch_diff(const DiffParams& p, cudaStream_t st);
 
 // launchers (defined in the .cu files)
-void launch_conv_tc(const ConvParams& p, cudaStream_t st);
+void launch_conv_tc(const ConvParams& p, cudaStream_t st, int sm_count);
+bool conv_tc_supported(int n_tile);     // N tiles the generic kernel is instantiated for
 void launch_conv_simt(const ConvParams& p, cudaStream_t st);
 void launch_down1(const Down1Params& p, cudaStream_t st);
 void launch_up6(const Up6Params& p, cudaStream_t st);

@@ -40,6 +40,22 @@ float round_tf32(float x)
     return r;
 }
 
+uint16_t bf16_rn(float x)
+{
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);   // inf / nan
+    u += 0x7fffu + ((u >> 16) & 1u);                                     // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+float bf16_to_float(uint16_t h)
+{
+    const uint32_t u = (uint32_t)h << 16;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+}
+
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 static void choose_tile(int W, int H, int n_img, int& tw, int& th, int& nb)
@@ -67,6 +83,30 @@ static int dec_taps(int par, int kh[3], int dy[3])
     if (par == 0) { kh[0] = 1; dy[0] = 0; kh[1] = 3; dy[1] = -1; return 2; }
     kh[0] = 0; dy[0] = 1; kh[1] = 2; dy[1] = 0; kh[2] = 4; dy[2] = -1;
     return 3;
+}
+
+// Encoder, space-to-depth source [py][px][cin]: the (kh, kw) tap that channel `c` of the S2D pixel at offset (dy, dx) carries
+// (input row 2*oh + kh - 1 = S2D row oh + dy, parity py), or false if none.
+static bool enc_slab_tap(int cin, int c, int dy, int dx, int& ci, int& kh, int& kw)
+{
+    const int pp = c / cin, py = pp >> 1, px = pp & 1;
+    ci = c % cin;
+    for (kh = 0; kh < 5; kh++)
+        for (kw = 0; kw < 5; kw++) {
+            int d1, p1, d2, p2;
+            enc_tap(kh, d1, p1);
+            enc_tap(kw, d2, p2);
+            if (d1 == dy && p1 == py && d2 == dx && p2 == px) return true;
+        }
+    return false;
+}
+
+static std::vector<int32_t> kelem_offsets(const std::vector<KBlock>& kb)
+{
+    std::vector<int32_t> off(kb.size());
+    int32_t o = 0;
+    for (size_t k = 0; k < kb.size(); k++) { off[k] = o; o += kb_channels(kb[k]); }
+    return off;
 }
 
 // duplicate every k-block (and its k-elements) as a part-1 twin right after it
@@ -102,7 +142,7 @@ bool weights_tf32_exact(const float* coeff)
     return true;
 }
 
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int n_stems, int min_ctas)
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int n_stems, int min_ctas, unsigned comp_mask)
 {
     std::vector<LayerPlan> plans;
     auto narrow = [&](LayerPlan& L) {
@@ -201,7 +241,43 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int
     if (split_weights)
         for (auto& L : plans)
             for (int p = 0; p < L.phases; p++) split_kblocks(L.kb[p], L.kelem[p], kKB);
+    // ---- compensation blocks (after the main term: small contributions are added last) ------------
     for (auto& L : plans) {
+        L.comp = (comp_mask >> L.index) & 1u;
+        if (!L.comp) continue;
+        if (!L.transposed) {
+            L.lo_src = SrcDesc{4 * L.cin, L.Ws, L.Hs};
+            for (int c_off = 0; c_off < 4 * L.cin; c_off += kKBlo)
+                for (int dy = -1; dy <= 1; dy++)
+                    for (int dx = -1; dx <= 1; dx++) {
+                        std::vector<KElem> el(kKBlo, KElem{-1, 0, 0});
+                        bool any = false;
+                        for (int j = 0; j < kKBlo; j++) {
+                            int ci, kh, kw;
+                            if (enc_slab_tap(L.cin, c_off + j, dy, dx, ci, kh, kw)) { el[j] = KElem{ci, (int8_t)kh, (int8_t)kw}; any = true; }
+                        }
+                        if (!any) continue;
+                        L.kb[0].push_back(KBlock{(int8_t)kSrcLo, (int8_t)dy, (int8_t)dx, (int8_t)kPartLo, c_off});
+                        L.kelem[0].insert(L.kelem[0].end(), el.begin(), el.end());
+                    }
+        } else {
+            L.lo_src = SrcDesc{L.cin, L.Ws, L.Hs};      // [skip residual | up residual] = the reference's concatenated channel order
+            for (int po = 0; po < 2; po++)
+                for (int qo = 0; qo < 2; qo++) {
+                    const int p = po * 2 + qo;
+                    int khs[3], dys[3], kws[3], dxs[3];
+                    const int nh = dec_taps(po, khs, dys), nw = dec_taps(qo, kws, dxs);
+                    for (int a = 0; a < nh; a++)
+                        for (int b = 0; b < nw; b++)
+                            for (int c0 = 0; c0 < L.cin; c0 += kKBlo) {
+                                L.kb[p].push_back(KBlock{(int8_t)kSrcLo, (int8_t)dys[a], (int8_t)dxs[b], (int8_t)kPartLo, c0});
+                                for (int j = 0; j < kKBlo; j++) L.kelem[p].push_back(KElem{c0 + j, (int8_t)khs[a], (int8_t)kws[b]});
+                            }
+                }
+        }
+    }
+    for (auto& L : plans) {
+        for (int p = 0; p < L.phases; p++) L.ke_off[p] = kelem_offsets(L.kb[p]);
         size_t off = 0;
         for (int p = 0; p < L.phases; p++) {
             L.w_phase_off[p] = off;
@@ -221,18 +297,21 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
         for (int nt = 0; nt < L.n_tiles; nt++)
             for (size_t kb = 0; kb < nkb; kb++) {
                 float* blk = out + L.w_phase_off[p] + ((size_t)nt * nkb + kb) * L.n_tile * kKB;
+                const bool lo = (L.kb[p][kb].part & kPartLo) != 0;     // [n_tile][64] bf16 in the same bytes
+                const int width = kb_channels(L.kb[p][kb]);
                 for (int n = 0; n < L.n_tile; n++) {
                     const int o = nt * L.n_tile + n;
-                    for (int j = 0; j < kKB; j++) {
-                        const KElem e = L.kelem[p][kb * kKB + j];
+                    for (int j = 0; j < width; j++) {
+                        const KElem e = L.kelem[p][L.ke_off[p][kb] + j];
                         float v = 0.0f;
                         if (e.cin >= 0) {
                             const size_t idx = L.transposed
                                 ? (((size_t)e.cin * L.cout + o) * 5 + e.kh) * 5 + e.kw      // [I][O][kh][kw]
                                 : (((size_t)o * L.cin + e.cin) * 5 + e.kh) * 5 + e.kw;     // [O][I][kh][kw]
-                            v = weight_part(w[idx], L.kb[p][kb].part);
+                            v = lo ? w[idx] : weight_part(w[idx], L.kb[p][kb].part);
                         }
-                        blk[swz128_index(n, j)] = v;
+                        if (lo) reinterpret_cast<uint16_t*>(blk)[swz128_index16(n, j)] = bf16_rn(v);
+                        else blk[swz128_index(n, j)] = v;
                     }
                 }
             }
@@ -251,7 +330,7 @@ static int dec_kh(int par, int d)
     return d == 1 ? 0 : (d == 0 ? 2 : 4);
 }
 
-RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights)
+RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp)
 {
     RowPlan L{};
     L.index = layer_index;
@@ -275,15 +354,9 @@ RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights)
                     std::vector<KElemP> el(kKB);
                     bool any = false;
                     for (int j = 0; j < kKB; j++) {
-                        const int c = c_off + j, pp = c / L.cin, cin = c % L.cin, py = pp >> 1, px = pp & 1;
                         KElemP e{-1, {-1, -1, -1, -1}, {-1, -1, -1, -1}};
-                        for (int kh = 0; kh < 5; kh++)
-                            for (int kw = 0; kw < 5; kw++) {
-                                int d1, p1, d2, p2;
-                                enc_tap(kh, d1, p1);
-                                enc_tap(kw, d2, p2);
-                                if (d1 == dy && p1 == py && d2 == dx && p2 == px) { e.cin = cin; e.kh[0] = (int8_t)kh; e.kw[0] = (int8_t)kw; any = true; }
-                            }
+                        int ci, kh, kw;
+                        if (enc_slab_tap(L.cin, c_off + j, dy, dx, ci, kh, kw)) { e.cin = ci; e.kh[0] = (int8_t)kh; e.kw[0] = (int8_t)kw; any = true; }
                         el[j] = e;
                     }
                     if (!any) continue;
@@ -329,6 +402,39 @@ RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights)
         split_kblocks(L.kb, L.kelem, kKB);
         for (auto& ch : L.chunks) { ch.kb0 *= 2; ch.nkb *= 2; }
     }
+    // compensation chunks: 64-channel slabs of the bf16 residual tensor, same taps, bf16 weights (see build_plans)
+    L.comp = comp;
+    if (comp) {
+        const int Clo = L.transposed ? L.cin : 4 * L.cin;
+        L.lo_src = SrcDesc{Clo, L.Ws, L.Hs};
+        for (int c_off = 0; c_off < Clo; c_off += kKBlo) {
+            RowChunk ch{(int8_t)kSrcLo, c_off, (int32_t)L.kb.size(), 0};
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    std::vector<KElemP> el(kKBlo, KElemP{-1, {-1, -1, -1, -1}, {-1, -1, -1, -1}});
+                    bool any = false;
+                    for (int j = 0; j < kKBlo; j++) {
+                        if (L.transposed) {
+                            el[j].cin = c_off + j;
+                            for (int ph = 0; ph < 4; ph++) {
+                                const int kh = dec_kh(ph >> 1, dy), kw = dec_kh(ph & 1, dx);
+                                if (kh >= 0 && kw >= 0) { el[j].kh[ph] = (int8_t)kh; el[j].kw[ph] = (int8_t)kw; }
+                            }
+                            any = true;
+                        } else {
+                            int ci, kh, kw;
+                            if (enc_slab_tap(L.cin, c_off + j, dy, dx, ci, kh, kw)) { el[j].cin = ci; el[j].kh[0] = (int8_t)kh; el[j].kw[0] = (int8_t)kw; any = true; }
+                        }
+                    }
+                    if (!any) continue;
+                    L.kb.push_back(KBlock{(int8_t)kSrcLo, (int8_t)dy, (int8_t)dx, (int8_t)kPartLo, c_off});
+                    L.kelem.insert(L.kelem.end(), el.begin(), el.end());
+                    ch.nkb++;
+                }
+            L.chunks.push_back(ch);
+        }
+    }
+    L.ke_off = kelem_offsets(L.kb);
     L.R = row_plan_R(L.N);
     L.w_floats_per_stem = L.kb.size() * (size_t)L.N * kKB;
     return L;
@@ -340,17 +446,20 @@ void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
     const float* w = coeff + (L.transposed ? cl.up_w[L.index - 5] : cl.down_w[L.index + 1]);
     for (size_t kb = 0; kb < L.kb.size(); kb++) {
         float* blk = out + kb * (size_t)L.N * kKB;
+        const bool lo = (L.kb[kb].part & kPartLo) != 0;
+        const int width = kb_channels(L.kb[kb]);
         for (int n = 0; n < L.N; n++) {
             const int ph = L.transposed ? n / L.cout : 0, o = L.transposed ? n % L.cout : n;
-            for (int j = 0; j < kKB; j++) {
-                const KElemP& e = L.kelem[kb * kKB + j];
+            for (int j = 0; j < width; j++) {
+                const KElemP& e = L.kelem[L.ke_off[kb] + j];
                 float v = 0.0f;
                 if (e.cin >= 0 && e.kh[ph] >= 0) {
                     const size_t idx = L.transposed ? (((size_t)e.cin * L.cout + o) * 5 + e.kh[ph]) * 5 + e.kw[ph]
                                                     : (((size_t)o * L.cin + e.cin) * 5 + e.kh[ph]) * 5 + e.kw[ph];
-                    v = weight_part(w[idx], L.kb[kb].part);
+                    v = lo ? w[idx] : weight_part(w[idx], L.kb[kb].part);
                 }
-                blk[swz128_index(n, j)] = v;
+                if (lo) reinterpret_cast<uint16_t*>(blk)[swz128_index16(n, j)] = bf16_rn(v);
+                else blk[swz128_index(n, j)] = v;
             }
         }
     }

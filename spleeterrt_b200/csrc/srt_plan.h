@@ -29,6 +29,7 @@ constexpr int kHop = 1024;
 constexpr int kBins = 2049;
 constexpr int kCoeffFloats = 9822725;   // sizeof(spleeterCoeff)/4, Executable/spleeter.h:5-31
 constexpr int kKB = 32;                 // channels per k-block (= one 128-byte swizzle row of fp32)
+constexpr int kKBlo = 64;               // channels per compensation k-block (= one 128-byte swizzle row of bf16)
 constexpr int kTileM = 128;             // pixels per CTA tile (UMMA M)
 
 enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_ELU_CLAMP = 3, ACT_ELU = 4 };
@@ -37,9 +38,14 @@ enum Act : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_ELU_CLAMP = 3, A
 struct KBlock {
     int8_t src;      // 0 or 1 (decoder: 0 = skip tensor, 1 = up tensor)
     int8_t dy, dx;   // offset in tile-space pixels
-    int8_t part;     // 0: weights tf32(w); 1: weights tf32(w - tf32(w)) (second term for weights that are not TF32-exact)
-    int32_t c_off;   // channel coordinate in the source tensor (multiple of 32, or of 16 for paired taps)
+    int8_t part;     // bit 0: weights tf32(w) / tf32(w - tf32(w)) (second term for weights that are not TF32-exact)
+                     // bit 1 (kPartLo): compensation block - A = the bf16 residual tensor a - tf32(a) of the source (src = 2),
+                     //        W = bf16(w), 64 channels wide, contracted with kind::f16 MMAs into the same accumulator
+    int32_t c_off;   // channel coordinate in the source tensor (multiple of 32, or of 16 for paired taps; of 64 for compensation blocks)
 };
+constexpr int kPartLo = 2;
+constexpr int kSrcLo = 2;               // KBlock::src / RowChunk::src of the residual tensor
+SRT_HD inline int kb_channels(const KBlock& kb) { return (kb.part & kPartLo) ? kKBlo : kKB; }
 
 // For the weight packer: where k-element j of a k-block comes from.
 struct KElem {
@@ -65,7 +71,12 @@ struct LayerPlan {
     int nsrc;
     SrcDesc src[2];
     std::vector<KBlock> kb[4];          // per phase
-    std::vector<KElem> kelem[4];        // per phase, 32 per k-block
+    std::vector<KElem> kelem[4];        // per phase, kb_channels() per k-block, k-block k starts at ke_off[k]
+    std::vector<int32_t> ke_off[4];
+    // compensated precision (see build_plans): the residual source, bf16, same pixel grid as src[]; encoder layers: the
+    // space-to-depth tensor's twin; decoder layers: ONE tensor holding [skip residual | up residual] per pixel
+    bool comp;
+    SrcDesc lo_src;
     // weights blob: [phase][n_tile_idx][kb][n_tile*32 floats], pre-swizzled (see pack_layer)
     size_t w_floats_per_stem;
     size_t w_phase_off[4];              // float offset of each phase inside the per-stem blob
@@ -89,7 +100,11 @@ CoeffLayout coeff_layout();
 // min_ctas > 0 (with the number of stems sharing a launch): a layer whose grid would hold fewer CTAs than that - the deep
 // layers of a one-tile batch are 8-16 CTAs of 80 us each on a 148-SM part - gets narrower N tiles (down to 64 columns:
 // below that an MMA does not get cheaper to issue), i.e. more and shorter CTAs.  0 keeps N = min(cout, 256).
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false, int n_stems = 1, int min_ctas = 0);
+// comp_mask bit i: layer i runs in compensated precision.  Its activation operands are rounded to TF32 by the producing
+// epilogue (as always), which also stores the residual a - tf32(a) as bf16; the layer then contracts tf32(a) with w (kind::tf32)
+// AND the residual with bf16(w) (kind::f16, 64 channels per 128-byte row, i.e. half the MMAs and half the bytes of the main
+// term).  Operand error drops from 2^-12 to ~2^-19 relative: fp32-grade results for 1.5x the tensor work.
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false, int n_stems = 1, int min_ctas = 0, unsigned comp_mask = 0);
 
 // Pack one stem's weights for a layer into the k-block-major, 128B-swizzled layout the MMA
 // B operand is read from.  `coeff` is one spleeterCoeff blob.  Values are rounded to TF32
@@ -98,6 +113,8 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = fa
 void pack_layer(const LayerPlan& L, const float* coeff, float* out);
 
 float round_tf32(float x);
+uint16_t bf16_rn(float x);              // round to nearest even (cvt.rn.bf16.f32)
+float bf16_to_float(uint16_t h);
 // value stored for a weight in a k-block of the given part
 inline float weight_part(float w, int part) { const float hi = round_tf32(w); return part == 0 ? hi : round_tf32(w - hi); }
 bool weights_tf32_exact(const float* coeff);   // all tensor-core conv weights of one net representable in TF32?
@@ -132,7 +149,10 @@ struct RowPlan {
     SrcDesc src[2];
     std::vector<RowChunk> chunks;
     std::vector<KBlock> kb;             // dy, dx per k-block (src / c_off copied from the chunk)
-    std::vector<KElemP> kelem;          // 32 per k-block
+    std::vector<KElemP> kelem;          // kb_channels() per k-block, k-block k starts at ke_off[k]
+    std::vector<int32_t> ke_off;
+    bool comp;                          // compensated precision: extra chunks with src = kSrcLo (see build_plans)
+    SrcDesc lo_src;
     size_t w_floats_per_stem;           // kb.size() * N * 32
 };
 // rows per CTA for a given N (fixed by the shared-memory / TMEM budget, see srt_conv_rp.cu)
@@ -156,10 +176,12 @@ SRT_HD inline int swz32_index(int row, int j) { return row * 8 + ((((j >> 2) ^ (
 SRT_HD inline size_t mag_s2d_index(int T, int F, int t, int f) { return (((size_t)(t >> 1) * (F >> 1) + (f >> 1)) << 2) + ((t & 1) << 1) + (f & 1); }
 
 bool row_plan_supported(int layer_index);                 // down2, down3, up4, up5
-RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights = false);
+RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights = false, bool comp = false);
 void pack_row_layer(const RowPlan& L, const float* coeff, float* out);
 
 // index of (row n, k-element j) inside a swizzled [rows][32] fp32 block
 SRT_HD inline int swz128_index(int row, int j) { return row * 32 + ((((j >> 2) ^ (row & 7)) << 2) | (j & 3)); }
+// same for a [rows][64] block of 2-byte elements (16-byte chunks of 8 elements)
+SRT_HD inline int swz128_index16(int row, int j) { return row * 64 + ((((j >> 3) ^ (row & 7)) << 3) | (j & 7)); }
 
 }  // namespace srt

@@ -163,6 +163,21 @@ __device__ __forceinline__ void mma_tf32_ss_lo(uint32_t tmem_d, uint32_t a_lo, u
         : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
         : "memory");
 }
+// The compensation blocks (srt_plan.h kPartLo): A = bf16 residuals, B = bf16 weights, 64 per 128-byte row, K = 16 per MMA (the same
+// 32-byte descriptor advance as a K = 8 TF32 step), accumulating into the same fp32 TMEM tile as the TF32 MMAs.
+__device__ __forceinline__ void mma_bf16_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t desc_hi = kDescHiSw128)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+        : "memory");
+}
 // same, with separate descriptor high words for A and B (operands in different swizzle modes)
 __device__ __forceinline__ void mma_tf32_ss_ab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                                uint32_t accumulate)
@@ -239,6 +254,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
            | (0u << 15)         // a K-major
            | (0u << 16)         // b K-major
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Instruction descriptor of the compensation MMAs: D fp32, A/B bf16, both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
+{
+    return (1u << 4)            // c_format = F32
+           | (1u << 7)          // a_format = BF16
+           | (1u << 10)         // b_format = BF16
+           | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// two floats -> packed bf16x2 (round to nearest even): lo in bits 0-15, hi in bits 16-31
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 
 __device__ __forceinline__ float rna_tf32(float x)

@@ -32,9 +32,19 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
             const KBlock kb = kbt[k];
             const int yy = Y + kb.dy, xx = X + kb.dx;
             if (!valid || yy < 0 || yy >= p.Hs || xx < 0 || xx >= p.Ws) continue;   // zero padding
+            const float* wb = wbase + (size_t)k * p.n_tile * kKB;
+            if (kb.part & kPartLo) {   // compensation block: bf16 residuals x bf16 weights, 64 channels
+                const uint16_t* a = p.lo_ptr + (((size_t)n * p.Hs + yy) * p.Ws + xx) * p.lo_C + kb.c_off;
+                const uint16_t* wh = reinterpret_cast<const uint16_t*>(wb);
+                for (int j = 0; j < kKBlo; j++) {
+                    const float av = __uint_as_float((uint32_t)a[j] << 16);
+#pragma unroll
+                    for (int i = 0; i < 16; i++) acc[i] = fmaf(av, __uint_as_float((uint32_t)wh[swz128_index16(c0 + i, j)] << 16), acc[i]);
+                }
+                continue;
+            }
             const int C = p.src_C[kb.src];
             const float* a = p.src_ptr[kb.src] + (((size_t)n * p.Hs + yy) * p.Ws + xx) * C + kb.c_off;
-            const float* wb = wbase + (size_t)k * p.n_tile * kKB;
             for (int j = 0; j < kKB; j++) {
                 const float av = a[j];
 #pragma unroll
@@ -121,12 +131,14 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const __grid_consta
         for (int c = 0; c < 2; c++) {
             const int oh = oh0 + ty + D1_BY * a, ow = ow0 + tx + D1_BX * c;
             if (ow >= Wo || oh >= Ho) continue;
-            float raw[16], av[16];
+            float raw[16], av[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const float t = acc[a][c][i] + p.bk[i];
                 raw[i] = t;
-                av[i] = ptx::rna_tf32(apply_act(act, p.bk[16 + i] * t + p.bk[32 + i]));
+                const float full = apply_act(act, p.bk[16 + i] * t + p.bk[32 + i]);
+                av[i] = ptx::rna_tf32(full);
+                lo[i] = full - av[i];
             }
             float4* d0 = reinterpret_cast<float4*>(p.out_raw + (((size_t)n * Ho + oh) * Wo + ow) * 16);
             float4* d1 = reinterpret_cast<float4*>(
@@ -136,6 +148,8 @@ __global__ void __launch_bounds__(D1_BX* D1_BY) down1_kernel(const __grid_consta
                 d0[q] = make_float4(raw[4 * q], raw[4 * q + 1], raw[4 * q + 2], raw[4 * q + 3]);
                 d1[q] = make_float4(av[4 * q], av[4 * q + 1], av[4 * q + 2], av[4 * q + 3]);
             }
+            if (p.lo_act)
+                store16_lo(p.lo_act + ((((size_t)n * (Ho / 2) + oh / 2) * (Wo / 2) + ow / 2) * 4 + (oh & 1) * 2 + (ow & 1)) * 16, lo);
         }
 }
 

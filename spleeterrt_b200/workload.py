@@ -111,6 +111,23 @@ def synth_pcm(stream, n=441000):
     return out
 
 
+def synth_pcm_fullscale(stream, n=441000):
+    """A full-scale programme-like clip for the precision tests: three tones (one gliding), an amplitude-modulated
+    partial and noise, normalised to peak 0.999 (RMS ~0.3).  Errors of the TF32 path scale with the signal level, so
+    this - not the -12 dBFS §8d signal - is the input that decides whether 1e-4 RMS per stem holds."""
+    t = np.arange(n) / 44100.0
+    out = []
+    for seed in (4321 + stream, 4321 + stream + 10000):
+        rng = np.random.default_rng(seed)
+        x = (0.35 * np.sin(2 * np.pi * 220 * t + rng.uniform(0, 6.28))
+             + 0.25 * np.sin(2 * np.pi * 3300 * t * (1 + 0.1 * np.sin(2 * np.pi * 0.5 * t)))
+             + 0.10 * np.sin(2 * np.pi * 82.4 * t)
+             + 0.15 * np.sin(2 * np.pi * 987 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 2.0 * t))
+             + 0.12 * rng.standard_normal(n))
+        out.append((x * (0.999 / np.abs(x).max())).astype(np.float32))
+    return out
+
+
 def padded_frames(n):
     return (4096 * ((n + 4095) // 4096) + 8192) // 1024
 

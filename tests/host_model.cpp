@@ -13,6 +13,9 @@ using namespace srt;
 
 static bool g_split = false;   // two-term weights (weights not exactly representable in TF32)
 extern "C" void srt_host_model_set_split(int on) { g_split = on != 0; }
+static bool g_comp = false;    // compensated precision: sources rounded to TF32 + bf16 residual tensors contracted by extra k-blocks
+static bool g_comp_drop = false;   // (control experiment) sources rounded, compensation blocks ignored
+extern "C" void srt_host_model_set_comp(int on) { g_comp = on != 0; g_comp_drop = on == 2; }
 static int g_min_ctas = 0;      // build_plans(min_ctas): narrower N tiles for small grids (what a small-batch context uses)
 extern "C" void srt_host_model_set_min_ctas(int v) { g_min_ctas = v; }
 
@@ -27,6 +30,26 @@ static float act_apply(int act, float x)
     }
 }
 
+
+// What the producing epilogue stores in compensated mode: hi = tf32(a) in place, residual bf16(a - hi) in the layer's
+// residual tensor (encoder: same layout; decoder: channel q's block of the concatenated [skip | up] tensor).
+static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const SrcDesc* sd, int H, int W, const SrcDesc& lo_sd, std::vector<uint16_t>& lo)
+{
+    lo.assign((size_t)H * W * lo_sd.C, 0);
+    int coff = 0;
+    for (int q = 0; q < nsrc; q++) {
+        const int C = sd[q].C;
+        for (size_t px = 0; px < (size_t)H * W; px++)
+            for (int c = 0; c < C; c++) {
+                float& a = src[q][px * C + c];
+                const float hi = round_tf32(a);
+                lo[px * lo_sd.C + coff + c] = bf16_rn(a - hi);
+                a = hi;
+            }
+        coff += C;
+    }
+}
+
 // src0/src1: planar [C][H][W] fp32 in the *reference's* layout:
 //   encoder: src0 = activated input of the layer at resolution (2*Hs, 2*Ws)
 //   decoder: src0 = skip, src1 = previous decoder output, both at (Hs, Ws); layer up1 has src0 only
@@ -35,9 +58,10 @@ static float act_apply(int act, float x)
 extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
                                     float* out, int want_act)
 {
-    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split, 1, g_min_ctas);
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split, 1, g_min_ctas, g_comp ? 0x3ffu : 0u);
     if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
     const LayerPlan& L = plans[plan_index];
+    if (L.comp != g_comp) return -5;
     const CoeffLayout cl = coeff_layout();
     // ---- device layouts of the sources -------------------------------------------------
     std::vector<std::vector<float>> src(L.nsrc);
@@ -59,6 +83,8 @@ extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* c
                     for (int x = 0; x < W; x++) src[q][((size_t)y * W + x) * C + c] = in[q][((size_t)c * H + y) * W + x];
         }
     }
+    std::vector<uint16_t> lo;
+    if (L.comp) split_sources(src, L.nsrc, L.src, H, W, L.lo_src, lo);
     // ---- weights and epilogue vectors ----------------------------------------------------
     std::vector<float> wpk(L.w_floats_per_stem);
     pack_layer(L, coeff, wpk.data());
@@ -83,10 +109,22 @@ extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* c
                             const KBlock kb = L.kb[ph][k];
                             const int yy = Y + kb.dy, xx = X + kb.dx;
                             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;   // TMA zero fill
+                            const float* wb = &wpk[L.w_phase_off[ph] + ((size_t)nt * nkb + k) * L.n_tile * kKB];
+                            if (kb.part & kPartLo) {                                // compensation block: bf16 residuals x bf16 weights
+                                if (!L.comp || kb.src != kSrcLo || kb.c_off < 0 || kb.c_off + kKBlo > L.lo_src.C) return -2;
+                                if (g_comp_drop) continue;
+                                const uint16_t* a = &lo[((size_t)yy * W + xx) * L.lo_src.C + kb.c_off];
+                                const uint16_t* wh = reinterpret_cast<const uint16_t*>(wb);
+                                for (int n = 0; n < L.n_tile; n++) {
+                                    float s = 0.f;
+                                    for (int j = 0; j < kKBlo; j++) s += bf16_to_float(a[j]) * bf16_to_float(wh[swz128_index16(n, j)]);
+                                    acc[n] += s;
+                                }
+                                continue;
+                            }
                             const int C = L.src[kb.src].C;
                             if (kb.c_off < 0 || kb.c_off + kKB > C) return -2;      // box must stay inside the channel dim
                             const float* a = &src[kb.src][((size_t)yy * W + xx) * C + kb.c_off];
-                            const float* wb = &wpk[L.w_phase_off[ph] + ((size_t)nt * nkb + k) * L.n_tile * kKB];
                             for (int n = 0; n < L.n_tile; n++) {
                                 float s = 0.f;
                                 for (int j = 0; j < kKB; j++) s += a[j] * wb[swz128_index(n, j)];
@@ -127,7 +165,7 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                                         float* out, int want_act)
 {
     if (!row_plan_supported(plan_index)) return -1;
-    const RowPlan L = build_row_plan(NetGeom{T, F}, plan_index, g_split);
+    const RowPlan L = build_row_plan(NetGeom{T, F}, plan_index, g_split, g_comp);
     const CoeffLayout cl = coeff_layout();
     const int H = L.Hs, W = L.Ws;
     std::vector<std::vector<float>> src(L.nsrc);
@@ -148,6 +186,8 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                     for (int x = 0; x < W; x++) src[q][((size_t)y * W + x) * C + c] = in[q][((size_t)c * H + y) * W + x];
         }
     }
+    std::vector<uint16_t> lo;
+    if (L.comp) split_sources(src, L.nsrc, L.src, H, W, L.lo_src, lo);
     std::vector<float> wpk(L.w_floats_per_stem);
     pack_row_layer(L, coeff, wpk.data());
     const float* bias = coeff + (L.transposed ? cl.up_b[L.index - 5] : cl.down_b[L.index + 1]);
@@ -170,10 +210,22 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                             if (r + kb.dy + 1 < 0 || r + kb.dy + 1 >= L.R + 2 || m + kb.dx + 1 < 0 || m + kb.dx + 1 >= kPatchW) return -4;
                             const int yy = Y + kb.dy, xx = X + kb.dx;
                             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                            const float* wb = &wpk[(size_t)k * L.N * kKB];
+                            if (kb.part & kPartLo) {
+                                if (!L.comp || ch.src != kSrcLo || kb.c_off + kKBlo > L.lo_src.C) return -2;
+                                if (g_comp_drop) continue;
+                                const uint16_t* a = &lo[((size_t)yy * W + xx) * L.lo_src.C + kb.c_off];
+                                const uint16_t* wh = reinterpret_cast<const uint16_t*>(wb);
+                                for (int n = 0; n < L.N; n++) {
+                                    float s = 0.f;
+                                    for (int j = 0; j < kKBlo; j++) s += bf16_to_float(a[j]) * bf16_to_float(wh[swz128_index16(n, j)]);
+                                    acc[n] += s;
+                                }
+                                continue;
+                            }
                             const int C = L.src[kb.src].C;
                             if (kb.c_off + kKB > C) return -2;
                             const float* a = &src[kb.src][((size_t)yy * W + xx) * C + kb.c_off];
-                            const float* wb = &wpk[(size_t)k * L.N * kKB];
                             for (int n = 0; n < L.N; n++) {
                                 float s = 0.f;
                                 for (int j = 0; j < kKB; j++) s += a[j] * wb[swz128_index(n, j)];

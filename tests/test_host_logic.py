@@ -104,6 +104,47 @@ def test_two_term_weights_for_fp32_blobs(oracle, host_model, small_nets):
         assert errs[(name, 0)] > 3 * errs[(name, 1)], errs      # single-term weights are visibly worse
 
 
+@pytest.mark.parametrize("mode", [1, 0])
+def test_compensated_precision_tables(oracle, host_model, small_nets, mode):
+    """precision 0 (the default): every tensor-core layer contracts tf32(a) with w and the bf16 residual a - tf32(a) with
+    bf16(w) (extra 64-channel k-blocks; decoder layers read ONE residual tensor [skip | up]).  The CPU model of both
+    kernel forms, fed TF32-rounded sources + bf16 residuals, must agree with the oracle as well as the unrounded model."""
+    T, F = 64, 128
+    coeff = small_nets[0][0] if mode else small_nets[1][0]
+    rng = np.random.default_rng(5 + mode)
+    x = (np.abs(rng.standard_normal((2, T, F))) * 3).astype(np.float32)
+    _, tp = oracle.unet(coeff, x, mode, taps=True)
+    taps = oracle.split_taps(tp, T, F)
+    v = oracle.coeff_views(coeff)
+    a_enc, a_dec = (3, 3) if mode else (1, 2)
+    host_model.srt_host_model_set_comp(1)
+    try:
+        for i in range(1, 6):
+            bn = v[f"down{i}.bn"]
+            act_in = _act(a_enc, bn[1][:, None, None] * taps[f"skip{i}"] + bn[0][:, None, None]).astype(np.float32)
+            ref = taps[f"skip{i+1}"]
+            for row in ([False, True] if i - 1 in (0, 1) else [False]):
+                got = _run_layer(host_model, T, F, i - 1, coeff, a_enc, act_in, None, ref.shape, row=row)
+                err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
+                assert err < 2e-5, f"down{i+1} compensated (row-patch={row}): rel err {err}"
+        for d in range(5):
+            s0 = taps["skip6"] if d == 0 else taps[f"skip{6-d}"]
+            s1 = None if d == 0 else taps[f"up{d}"]
+            ref = taps[f"up{d+1}"]
+            for row in ([False, True] if 5 + d in (8, 9) else [False]):
+                got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, s0, s1, ref.shape, row=row)
+                err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
+                assert err < 2e-5, f"up{d+1} compensated (row-patch={row}): rel err {err}"
+        # control: the same rounded sources WITHOUT the compensation blocks are visibly worse (so the blocks above did the work)
+        host_model.srt_host_model_set_comp(2)
+        for row in (False, True):
+            got = _run_layer(host_model, T, F, 9, coeff, a_dec, taps["skip2"], taps["up4"], taps["up5"].shape, row=row)
+            err = np.abs(got - taps["up5"]).max() / np.abs(taps["up5"]).max()
+            assert err > 5e-5, f"control (row-patch={row}): {err}"
+    finally:
+        host_model.srt_host_model_set_comp(0)
+
+
 def test_plan_shapes(host_model):
     info = (C.c_int * 10)()
     # shape A (T=512, F=1024), batch 32: tiles are full and the k-block counts match the design
