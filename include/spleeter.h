@@ -51,6 +51,9 @@ typedef struct _spleeter* spleeter;
 size_t getCoeffSize(void);
 void* allocateSpleeterStr(void);
 /* width = analyseBinLimit (F), height = timeStep (T); stemMode 0: LeakyReLU/ReLU, else ELU.
+ * Both must be multiples of 64 (six halvings), 64 <= width <= 2048: other sizes - which the reference CLI merely warns
+ * about, main.c:739-742 - end the process with exit status 2 and a message naming the restriction.  CUDA failures
+ * (there is no error channel in this API) print the reason and abort().
  * `coeff` (one spleeterCoeff, host memory) must stay valid until freeSpleeter, as in the reference. */
 void initSpleeter(struct _spleeter* nn, size_t width, size_t height, int stemMode, void* coeff);
 /* hands out an internal HOST buffer of 2*T*F floats the caller may pass back as `y` */

@@ -89,7 +89,41 @@ def build(force=False):
     wbin = decode_weights(force)
     build_cli(wbin, force)
     build_resampler(force)
+    build_blas(force)
+    build_vst_host(force)
     return True
+
+
+OPENBLAS = "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs/libopenblasp-r0-59ffcd50.3.15.so"
+
+
+def build_blas(force=False):
+    """oracle/_ref/libref_exec_blas.so: the reference's Executable flavour on its REAL backend - gemm.c WITHOUT -DCPU_GEMM calls
+    cblas_sgemm (Executable/gemm.c:82-89; MKL on Windows, OpenBLAS on Linux where main.c:688-689 calls
+    openblas_set_num_threads).  MKL is not in this image; an OpenBLAS 0.3.15 that exports the plain CBLAS symbols is (a wheel's
+    private copy), so `#include <mkl.h>` is satisfied by the six-line oracle/blas_shim/mkl.h and the library is linked against
+    that file by path.  No zero-malloc shim here: cblas_sgemm with beta = 0 never reads C.  This is the CPU baseline the
+    README's "MKL is ~40x faster than the naive loops" refers to (README.MD:155), as far as it can be had here."""
+    if not os.path.exists(OPENBLAS):
+        return False
+    ex = os.path.join(REF, "Executable")
+    so = os.path.join(OUT, "libref_exec_blas.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-w", "-I", os.path.join(HERE, "blas_shim"), "-I", ex,
+                               "-o", so] + [os.path.join(ex, f) for f in ("spleeter.c", "gemm.c", "im2col_dilated.c", "stftFix.c", "codelet.c", "cpthread.c")]
+                              + [OPENBLAS, "-Wl,--disable-new-dtags,-rpath," + os.path.dirname(OPENBLAS), "-lm", "-lpthread"])   # DT_RPATH: also finds OpenBLAS's own libgfortran
+    return True
+
+
+def build_vst_host(force=False):
+    """oracle/_ref/vst_host_ref: examples/vst_host.c (our stand-in for the JUCE plugin shell) compiled against the REFERENCE's
+    VST/Source/Spleeter4Stems.h and linked to the reference's own streamer (libref_vst.so), to be run beside
+    examples/_build/vst_host (same source, include/Spleeter4Stems.h, libspleeterrt_b200.so)."""
+    vst = os.path.join(REF, "VST", "Source")
+    exe = os.path.join(OUT, "vst_host_ref")
+    src = os.path.join(os.path.dirname(HERE), "examples", "vst_host.c")
+    if force or not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-w", "-I", vst, src, "-L", OUT, "-lref_vst", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread", "-o", exe])
 
 
 def build_resampler(force=False):

@@ -27,7 +27,8 @@ _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 def build_port(force=False):
     so = os.path.join(HERE, "libsrt_oracle.so")
     src = os.path.join(HERE, "srt_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    tbl = os.path.join(HERE, "sigmoid_table.h")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(tbl)):
         subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=gnu11",
                                "-ffp-contract=off", "-o", so, src, "-lm"])
     return so
@@ -334,11 +335,14 @@ class RefExec:
                     ("threads", C.c_void_p), ("stftThreadData", C.c_void_p), ("istftThreadData", C.c_void_p),
                     ("targetCore", C.c_size_t), ("_data", C.c_void_p * 2), ("shared_info", C.c_void_p)]
 
-    def __init__(self):
-        path = os.path.join(REF_DIR, "libref_exec.so")
+    def __init__(self, blas=False):
+        """blas=True: oracle/_ref/libref_exec_blas.so, the same sources with gemm.c on its real backend (cblas_sgemm, here
+        OpenBLAS; oracle/build_ref.py build_blas) instead of the naive -DCPU_GEMM loops."""
+        path = os.path.join(REF_DIR, "libref_exec_blas.so" if blas else "libref_exec.so")
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         lib = C.CDLL(path)
+        self.blas = blas
         lib.allocateSpleeterStr.restype = C.c_void_p
         lib.initSpleeter.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
         lib.processSpleeter.argtypes = [C.c_void_p, _f32p, _f32p]
@@ -544,14 +548,27 @@ class RefVst:
             self.obj = None
 
 
-_ref_exec = None
+_ref_exec = {}
 
 
-def ref_exec():
-    global _ref_exec
-    if _ref_exec is None:
-        _ref_exec = RefExec()
-    return _ref_exec
+def ref_exec(blas=False):
+    if blas not in _ref_exec:
+        _ref_exec[blas] = RefExec(blas)
+    return _ref_exec[blas]
+
+
+def have_ref_blas():
+    return os.path.exists(os.path.join(REF_DIR, "libref_exec_blas.so"))
+
+
+def set_blas_threads(n):
+    """thread count of the OpenBLAS behind libref_exec_blas.so (what main.c:689 sets on Linux)"""
+    lib = ref_exec(True).lib          # the OpenBLAS it is linked to is now in the process
+    try:
+        lib.openblas_set_num_threads(int(n))
+        return True
+    except AttributeError:
+        return False
 
 
 def have_ref():

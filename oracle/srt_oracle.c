@@ -91,18 +91,15 @@ static void net_bind(net_t *n, const float *p)
 static float g_sig_tbl[1026];
 static int g_sig_ready = 0;
 
-/* The reference's table is sigma(-7 + i*14/1024) printed with 8 decimals, i = 0..1024,
- * plus a final 1.0 (spleeter.c:29).  Regenerated here instead of copied; the pin test
- * compares fastSigmoid() of oracle/_ref against srt_oracle_sigmoid_lut() on a dense grid. */
+/* The reference's table (spleeter.c:29) is DATA: ~sigma(-7 + i*14/1024), i = 0..1024, plus a final 1.0, but printed from
+ * some float evaluation - regenerating it in double and rounding to 8 decimals misses 307 entries by one ulp.  It is
+ * carried as bit patterns (oracle/sigmoid_table.h, written by tools/gen_sigmoid_table.py from the reference); the pin test
+ * demands fastSigmoid() of oracle/_ref == srt_oracle_sigmoid_lut() bit for bit on a dense grid. */
+#include "sigmoid_table.h"
 static void sig_init(void)
 {
     if (g_sig_ready) return;
-    for (int i = 0; i <= 1024; i++) {
-        double x = -7.0 + (double)i * (14.0 / 1024.0);
-        double s = 1.0 / (1.0 + exp(-x));
-        g_sig_tbl[i] = (float)(floor(s * 1e8 + 0.5) / 1e8);
-    }
-    g_sig_tbl[1025] = 1.0f;
+    memcpy(g_sig_tbl, kSigmoidTableBits, sizeof g_sig_tbl);
     g_sig_ready = 1;
 }
 

@@ -62,7 +62,7 @@ def build_examples():
     out = os.path.join(root, "examples", "_build")
     os.makedirs(out, exist_ok=True)
     built = []
-    for name in ("main_b200", "spleeter_cli_b200"):
+    for name in ("main_b200", "spleeter_cli_b200", "vst_host"):
         src = os.path.join(root, "examples", name + ".c")
         exe = os.path.join(out, name)
         if _stale(exe, [src, LIB, os.path.join(root, "include", "srt_b200.h")]):

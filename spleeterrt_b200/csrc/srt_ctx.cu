@@ -18,6 +18,7 @@
 #include "srt_internal.h"
 #include "srt_kernels.cuh"
 #include "srt_plan.h"
+#include "srt_sigmoid_table.h"
 
 using namespace srt;
 
@@ -249,7 +250,7 @@ static size_t act_floats(const srt_ctx* c, int level, int ch)   // tensor at res
 extern "C" void srt_destroy(srt_ctx* c)
 {
     if (!c) return;
-    cudaSetDevice(c->cfg.device);
+    internal::DeviceGuard dev_guard(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->next) { srt_destroy(c->next); c->next = nullptr; }
     for (void* p : c->allocs) cudaFree(p);
@@ -297,14 +298,10 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         if ((r = upload(c, &c->d_postwin, post))) return r;
         if ((r = upload(c, &c->d_twiddle, tw))) return r;
         if (c->cfg.flavour == 0) {
-            // fastSigmoid's table regenerated (sigma(-7 + i*14/1024) printed to 8 decimals, spleeter.c:29) and
-            // its per-interval slope / origin, evaluated with the reference's float expression (spleeter.c:38-40)
+            // fastSigmoid's table (reference data, spleeter.c:29, carried as bit patterns in srt_sigmoid_table.h) and its
+            // per-interval slope / origin, evaluated with the reference's float expression (spleeter.c:38-40)
             std::vector<float> t(1026);
-            for (int i = 0; i <= 1024; i++) {
-                const double sg = 1.0 / (1.0 + exp(-(-7.0 + i * (14.0 / 1024.0))));
-                t[i] = (float)(floor(sg * 1e8 + 0.5) / 1e8);
-            }
-            t[1025] = 1.0f;
+            std::memcpy(t.data(), kSigmoidTableBits, 1026 * sizeof(float));
             std::vector<float> lut(1025 * 4);
             const volatile float step = 0.01367188f;
             for (int i = 0; i < 1025; i++) {
@@ -629,7 +626,8 @@ extern "C" int srt_create(const srt_config* cfg, const float* const* coeffs, con
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SRT_ERR_CUDA, "no CUDA device: this library has no CPU path");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(SRT_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
-    CK(cudaSetDevice(cfg->device));
+    internal::DeviceGuard dev_guard(cfg->device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail(SRT_ERR_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", cfg->device, prop.major, prop.minor);
@@ -647,7 +645,9 @@ extern "C" int srt_create(const srt_config* cfg, const float* const* coeffs, con
         c->own_stream = true;
     }
     int r = build(c, coeffs, stem_modes);
-    if (r == 0 && cudaDeviceSynchronize() != cudaSuccess) r = fail(SRT_ERR_CUDA, "context build: %s", cudaGetErrorString(cudaGetLastError()));
+    // build() uploads with blocking copies / memsets on the legacy stream: wait for that stream and the context's own, not for the
+    // whole device (it may be busy with the caller's other streams)
+    if (r == 0 && (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)) r = fail(SRT_ERR_CUDA, "context build: %s", cudaGetErrorString(cudaGetLastError()));
     if (r) { std::string keep = g_err; srt_destroy(c); g_err = keep; return r; }
     *out = c;
     return 0;
@@ -809,7 +809,8 @@ extern "C" int srt_unet_device(srt_ctx* c, const float* d_mag, int n_img, float*
 {
     if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
     if (n_img < 1 || n_img > c->B) return fail(SRT_ERR_CAPACITY, "n_img %d exceeds max_images %d", n_img, c->B);
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     reset_spans(c);
     launch_mag_to_s2d(d_mag, c->d_mag, c->d_mag + (size_t)c->NB * c->T * c->F * 2, c->T, c->F, n_img, c->stream);   // API layout -> space-to-depth hi/lo
     c->launches++;
@@ -820,7 +821,8 @@ extern "C" int srt_unet_host(srt_ctx* c, const float* x, int n_img, float* y)
 {
     if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
     if (n_img < 1 || n_img > c->B) return fail(SRT_ERR_CAPACITY, "n_img %d exceeds max_images %d", n_img, c->B);
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     reset_spans(c);
     const size_t P = (size_t)c->T * c->F;
     std::vector<float> xi((size_t)n_img * P * 2), xlo((size_t)n_img * P * 2);   // space-to-depth hi / lo parts (what the device path stores)
@@ -1090,7 +1092,8 @@ extern "C" int srt_separate_device(srt_ctx* c, const float* const* d_pcmL, const
 {
     if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
     if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     reset_spans(c);
     return separate_core(c, d_pcmL, d_pcmR, n_samples, n_streams, unaffected, d_stems_out, kFFT);
 }
@@ -1113,7 +1116,8 @@ extern "C" int srt_separate_device_interleaved(srt_ctx* c, const float* const* d
     if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
     int r = check_channels(channels, n_streams);
     if (r) return r;
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     reset_spans(c);
     const int P = c->pairs();
     std::vector<const float*> L(n_streams), R(n_streams);
@@ -1282,7 +1286,8 @@ static int batch_submit(srt_ctx* c, const float* const* pcmL, const float* const
     if (!c || c->S == 0) return fail(SRT_ERR_STATE, "context has no nets");
     if (n_streams < 1) return fail(SRT_ERR_ARG, "n_streams < 1");
     if (!ticket_out) return fail(SRT_ERR_ARG, "ticket_out is NULL");
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     reset_spans(c);
     const int slot = (int)(c->batch_seq % kBatchSlots);
     int r = batch_wait_slot(c, slot);   // one batch too many in flight: the slot's previous owner must have drained
@@ -1318,7 +1323,8 @@ extern "C" int srt_batch_wait(srt_ctx* c, int ticket)
     if (!c) return fail(SRT_ERR_STATE, "null context");
     const long long age = ((c->batch_seq % kTicketMod) - 1 - ticket + kTicketMod) % kTicketMod;   // 0 = newest batch
     if (ticket < 0 || ticket >= kTicketMod || c->batch_seq == 0 || age >= c->batch_seq) return fail(SRT_ERR_ARG, "bad ticket %d", ticket);
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     const int slot = ticket % kBatchSlots;
     if (c->slot_ticket[slot] != ticket) return 0;   // an older batch: drained when its slot was handed on
     return batch_wait_slot(c, slot);
@@ -1355,7 +1361,8 @@ extern "C" int srt_stft_host(srt_ctx* c, const float* L, const float* R, size_t 
 {
     if (!c) return fail(SRT_ERR_STATE, "null context");
     if (n < (size_t)kFFT) return fail(SRT_ERR_ARG, "stft needs at least 4096 samples");
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     reset_spans(c);
     const size_t rows = srt_stft_rows(n);
     const int computed = (int)((n - kFFT + kHop / 4) / kHop) + 1;   // stftFix.c:377 + the final frame (:460-493)
@@ -1413,7 +1420,8 @@ extern "C" int srt_istft_host(srt_ctx* c, const float* reL, const float* imL, co
                               float* outL, float* outR)
 {
     if (!c) return fail(SRT_ERR_STATE, "null context");
-    CK(cudaSetDevice(c->cfg.device));
+    internal::DeviceGuard dev_guard(c->cfg.device);
+    if (!dev_guard.ok) return fail(SRT_ERR_CUDA, "cudaSetDevice(%d) failed", c->cfg.device);
     reset_spans(c);
     const size_t out_n = frames * kHop + (kFFT - kHop);
     const size_t cap = (size_t)c->B * c->T;   // frames the scratch holds

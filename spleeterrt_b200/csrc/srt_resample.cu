@@ -197,7 +197,8 @@ extern "C" int srt_resample_device(srt_ctx* ctx, const float* d_in, size_t n_in,
     if (!(ratio >= 1.0 / 256.0 && ratio <= 256.0)) return rs_fail(SRT_ERR_ARG, "srt_resample: ratio outside [1/256, 256] (samplerate.c:144)");
     if (coeff_count < 3 || index_inc < 1 || coeff_count > (1 << 18)) return rs_fail(SRT_ERR_ARG, "srt_resample: bad coefficient table geometry");
     if (n_in == 0 || n_in > ((size_t)1 << 30) || n_out > ((size_t)1 << 30)) return rs_fail(SRT_ERR_ARG, "srt_resample: bad length");
-    if (cudaSetDevice(internal::ctx_device(ctx)) != cudaSuccess) return rs_fail(SRT_ERR_CUDA, "srt_resample: cudaSetDevice failed");
+    internal::DeviceGuard dev_guard(internal::ctx_device(ctx));
+    if (!dev_guard.ok) return rs_fail(SRT_ERR_CUDA, "srt_resample: cudaSetDevice failed");
     const int half_len = coeff_count - 2;               // src_sinc.c:142
     std::vector<ResamplePlanEntry> plan;
     int32_t inc = 0;
@@ -238,7 +239,8 @@ extern "C" int srt_resample_host(srt_ctx* ctx, const float* in, size_t n_in, int
     if (channels != 1 && channels != 2) return rs_fail(SRT_ERR_ARG, "srt_resample: 1 or 2 channels (main.c:764-769)");
     if (coeff_count < 3 || coeff_count > (1 << 18)) return rs_fail(SRT_ERR_ARG, "srt_resample: bad coefficient table geometry");
     if (n_in == 0 || n_in > ((size_t)1 << 30) || n_out > ((size_t)1 << 30)) return rs_fail(SRT_ERR_ARG, "srt_resample: bad length");
-    if (cudaSetDevice(internal::ctx_device(ctx)) != cudaSuccess) return rs_fail(SRT_ERR_CUDA, "srt_resample: cudaSetDevice failed");
+    internal::DeviceGuard dev_guard(internal::ctx_device(ctx));
+    if (!dev_guard.ok) return rs_fail(SRT_ERR_CUDA, "srt_resample: cudaSetDevice failed");
     float *d_in = nullptr, *d_c = nullptr, *d_out = nullptr;
     const size_t in_b = n_in * channels * sizeof(float), out_b = (n_out ? n_out : 1) * channels * sizeof(float);
     int rc = 0;

@@ -14,7 +14,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <deque>
 #include <vector>
 
 #include "../../include/Spleeter4Stems.h"
@@ -144,7 +143,11 @@ struct srt_stream {
     // host state (mirrors mInputPos / mInputSamplesNeeded / nnMaskCursor / output buffers of the reference)
     int in_pos = 0, filled = 0, cursor = 0;
     long long tile = 0, hops = 0, launches = 0;
-    std::deque<std::vector<float>> fifo;
+    // finished hops waiting to be handed out: a fixed ring of pinned blocks [kOutRing][2S][1024] the hop's D2H lands in
+    // directly - nothing is allocated on the audio thread (srt_stream_process drains after every hop, so at most two
+    // blocks are ever pending)
+    static constexpr int kOutRing = 8;
+    long long out_head = 0, out_tail = 0;   // blocks produced / blocks fully handed out
     int read_off = 0;
 };
 
@@ -157,7 +160,7 @@ struct srt_stream {
 extern "C" void srt_stream_destroy(srt_stream* st)
 {
     if (!st) return;
-    cudaSetDevice(st->device);
+    internal::DeviceGuard dev_guard(st->device);
     if (st->hop_stream) cudaStreamSynchronize(st->hop_stream);
     if (st->ctx) srt_synchronize(st->ctx);
     for (void* p : {(void*)st->d_ring, (void*)st->d_awin, (void*)st->d_swin, (void*)st->d_mask, (void*)st->d_overlap, (void*)st->d_out,
@@ -191,6 +194,7 @@ extern "C" int srt_stream_create(const srt_config* cfg, const float* const* coef
     srt_stream* st = new srt_stream();
     st->device = cfg->device;
     int r = srt_create(&c2, coeffs, modes, &st->ctx);
+    internal::DeviceGuard dev_guard(cfg->device);
     if (r) { delete st; return r; }
     st->S = cfg->n_stems; st->T = cfg->time_step; st->F = cfg->bin_limit;
     const int S = st->S, T = st->T, F = st->F;
@@ -206,14 +210,14 @@ extern "C" int srt_stream_create(const srt_config* cfg, const float* const* coef
     if (cudaMalloc(&st->d_ring, 2 * kFFT * 4) || cudaMalloc(&st->d_awin, kFFT * 4) || cudaMalloc(&st->d_swin, 2048 * 4) ||
         cudaMalloc(&st->d_mask, nmask * 4) || cudaMalloc(&st->d_overlap, (size_t)2 * 2 * S * 1024 * 4) || cudaMalloc(&st->d_out, (size_t)2 * S * 1024 * 4) ||
         cudaMalloc(&st->d_spec, nspec * sizeof(float4)) ||
-        cudaMallocHost(&st->h_in, 2 * 1024 * 4) || cudaMallocHost(&st->h_out, (size_t)2 * S * 1024 * 4))
+        cudaMallocHost(&st->h_in, 2 * 1024 * 4) || cudaMallocHost(&st->h_out, (size_t)srt_stream::kOutRing * 2 * S * 1024 * 4))
         return bail(internal::set_error(SRT_ERR_CUDA, "stream buffers: out of memory"));
-    cudaMemset(st->d_ring, 0, 2 * kFFT * 4);
-    cudaMemset(st->d_spec, 0, nspec * sizeof(float4));
+    cudaMemsetAsync(st->d_ring, 0, 2 * kFFT * 4, st->hop_stream);
+    cudaMemsetAsync(st->d_spec, 0, nspec * sizeof(float4), st->hop_stream);
     st->d_mag = reinterpret_cast<float2*>(internal::ctx_mag(st->ctx));
-    cudaMemset(st->d_mag, 0, 2 * nmag * sizeof(float2));
-    cudaMemset(st->d_overlap, 0, (size_t)2 * 2 * S * 1024 * 4);
-    fill_kernel<<<(unsigned)((nmask + 255) / 256), 256>>>(st->d_mask, 1.0f, nmask);   // masks start at 1 (Spleeter4Stems.c:455-466)
+    cudaMemsetAsync(st->d_mag, 0, 2 * nmag * sizeof(float2), st->hop_stream);
+    cudaMemsetAsync(st->d_overlap, 0, (size_t)2 * 2 * S * 1024 * 4, st->hop_stream);
+    fill_kernel<<<(unsigned)((nmask + 255) / 256), 256, 0, st->hop_stream>>>(st->d_mask, 1.0f, nmask);   // masks start at 1 (Spleeter4Stems.c:455-466)
     // windows: getAsymmetricWindow(analysis, synthesis, k = 4096, m = 1024, 1.0) (Spleeter4Stems.c:383-401, 414-416)
     {
         const int k = kFFT, m = 1024;
@@ -230,10 +234,11 @@ extern "C" int srt_stream_create(const srt_config* cfg, const float* const* coef
             a *= (1.0 / kFFT) * 0.5f;                                               // reference analysisWnd (:415-416)
             aw[i] = a * 2.0f;                                                       // x2: the packed complex FFT then yields re / -im directly
         }
-        cudaMemcpy(st->d_awin, aw.data(), k * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(st->d_swin, sw.data(), 2048 * 4, cudaMemcpyHostToDevice);
+        cudaMemcpyAsync(st->d_awin, aw.data(), k * 4, cudaMemcpyHostToDevice, st->hop_stream);
+        cudaMemcpyAsync(st->d_swin, sw.data(), 2048 * 4, cudaMemcpyHostToDevice, st->hop_stream);
+        cudaStreamSynchronize(st->hop_stream);      // the host vectors go out of scope here
     }
-    if (cudaDeviceSynchronize() != cudaSuccess) return bail(internal::set_error(SRT_ERR_CUDA, "stream init failed"));
+    if (cudaStreamSynchronize(st->hop_stream) != cudaSuccess) return bail(internal::set_error(SRT_ERR_CUDA, "stream init failed"));
     *out = st;
     return 0;
 }
@@ -261,7 +266,9 @@ static int do_hop(srt_stream* st)
     p.out = st->d_out;
     stream_hop_kernel<<<S + 1, kFftThreads, 0, st->hop_stream>>>(p);
     st->launches++;
-    SCK(cudaMemcpyAsync(st->h_out, st->d_out, (size_t)2 * S * 1024 * 4, cudaMemcpyDeviceToHost, st->hop_stream));
+    if (st->out_head - st->out_tail >= srt_stream::kOutRing) return internal::set_error(SRT_ERR_STATE, "output ring overflow");
+    SCK(cudaMemcpyAsync(st->h_out + (size_t)(st->out_head % srt_stream::kOutRing) * 2 * S * 1024, st->d_out, (size_t)2 * S * 1024 * 4,
+                        cudaMemcpyDeviceToHost, st->hop_stream));
     st->hops++;
     if (++st->cursor >= T) {
         // tile k is complete (Spleeter4Stems.c:351-371): launch the nets on it, and make the hop stream wait
@@ -277,15 +284,28 @@ static int do_hop(srt_stream* st)
         st->tile++;
     }
     SCK(cudaStreamSynchronize(st->hop_stream));
-    st->fifo.emplace_back(st->h_out, st->h_out + (size_t)2 * S * 1024);
+    st->out_head++;
     return 0;
 }
 
 extern "C" int srt_stream_process(srt_stream* st, const float* inL, const float* inR, int n, float* const* components)
 {
     if (!st || n < 0) return internal::set_error(SRT_ERR_ARG, "bad argument");
-    SCK(cudaSetDevice(st->device));
+    internal::DeviceGuard dev_guard(st->device);
+    if (!dev_guard.ok) return internal::set_error(SRT_ERR_CUDA, "cudaSetDevice failed");
     const int want = n;
+    int done = 0;
+    // hand out what is ready, at most `want` samples in total; `components` stays untouched beyond that (:538-581)
+    auto drain = [&]() {
+        while (st->out_tail < st->out_head && done < want) {
+            const float* blk = st->h_out + (size_t)(st->out_tail % srt_stream::kOutRing) * 2 * st->S * 1024;
+            const int c = std::min(1024 - st->read_off, want - done);
+            for (int q = 0; q < 2 * st->S; q++) std::memcpy(components[q] + done, blk + (size_t)q * 1024 + st->read_off, (size_t)c * 4);
+            done += c;
+            st->read_off += c;
+            if (st->read_off == 1024) { st->read_off = 0; st->out_tail++; }
+        }
+    };
     while (n > 0) {
         const int c = std::min(1024 - st->filled, n);
         std::memcpy(st->h_in + st->filled, inL, (size_t)c * 4);
@@ -294,20 +314,12 @@ extern "C" int srt_stream_process(srt_stream* st, const float* inL, const float*
         st->filled += c;
         if (st->filled == 1024) {
             st->filled = 0;
+            drain();               // keeps the pending blocks <= 2 whatever the call size: no allocation on the audio thread
             int r = do_hop(st);
             if (r) return r;
         }
     }
-    // drain what is ready, at most `want` samples; leave `components` untouched otherwise (:538-581)
-    int done = 0;
-    while (!st->fifo.empty() && done < want) {
-        const std::vector<float>& blk = st->fifo.front();
-        const int c = std::min(1024 - st->read_off, want - done);
-        for (int q = 0; q < 2 * st->S; q++) std::memcpy(components[q] + done, blk.data() + (size_t)q * 1024 + st->read_off, (size_t)c * 4);
-        done += c;
-        st->read_off += c;
-        if (st->read_off == 1024) { st->read_off = 0; st->fifo.pop_front(); }
-    }
+    drain();
     return 0;
 }
 

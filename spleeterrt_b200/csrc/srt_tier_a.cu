@@ -39,6 +39,14 @@ extern "C" void initSpleeter(struct _spleeter* nn, size_t width, size_t height, 
     const char* impl = getenv("SRT_CONV_IMPL");
     cfg.conv_impl = (impl && !strcmp(impl, "simt")) ? 1 : 0;
     const float* cp = (const float*)coeff;
+    if (width % 64 || height % 64 || width < 64 || width > 2048 || height < 64) {
+        // The reference CLI only warns about sizes that are not powers of two (main.c:739-742) and carries on; its six
+        // halvings then truncate and the decoder's concatenations no longer line up.  This library needs multiples of 64
+        // (include/spleeter.h) and says so instead of aborting or computing garbage.
+        fprintf(stderr, "[spleeterrt_b200] initSpleeter: timeStep (%zu) and analyseBinLimit (%zu) must be multiples of 64 with "
+                        "64 <= analyseBinLimit <= 2048; pick e.g. 512 1024 (the reference's defaults)\n", height, width);
+        exit(2);
+    }
     if (srt_create(&cfg, &cp, &stemMode, &nn->ctx)) die("initSpleeter");
     nn->P = width * height;
     nn->host_mask = (float*)malloc(sizeof(float) * 2 * nn->P);

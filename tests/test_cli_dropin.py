@@ -105,6 +105,28 @@ def test_unmodified_cli_on_b200_matches_reference_cli(oracle, tmp_path, T, F, st
         assert float(np.sqrt(np.mean(ref[nm].astype(np.float64) ** 2))) > 1e-3, f"{nm}: silent reference output"
 
 
+@pytest.mark.gpu
+@needs_cli
+def test_unmodified_cli_with_four_host_threads(oracle, tmp_path):
+    """`spawnNthreads = 4` (main.c:544-577): processMT creates FOUR _spleeter instances from ONE coefficient pointer and runs
+    processSpleeter concurrently from four host threads (task_Separation, main.c:296-365), plus the tail tile on thread 0.
+    A 14 s stereo file at T = 64 is 9 full tiles + a tail.  Per-instance CUDA streams, no shared mutable state: the stems
+    equal the reference CLI's (same thread count) and the single-thread run of the same binary bit for bit."""
+    n = 14 * 44100
+    L, R = oracle.synth_pcm(13, n=n)
+    wav = str(tmp_path / "in.wav")
+    write_wav_f32(wav, np.stack([L, R], axis=1))
+    ref = run_cli(REF_CLI, str(tmp_path / "ref"), wav, 64, 512, 2, threads=4)
+    got = run_cli(B200_CLI, str(tmp_path / "b200"), wav, 64, 512, 2, threads=4)
+    one = run_cli(B200_CLI, str(tmp_path / "b200_1"), wav, 64, 512, 2, threads=1)
+    for nm in ("Vocal", "Accompaniment"):
+        assert got[nm].shape == ref[nm].shape == (n, 2)
+        for c in range(2):
+            err = float(np.sqrt(np.mean((ref[nm][:, c].astype(np.float64) - got[nm][:, c]) ** 2)))
+            assert err < TOL_RMS, (nm, c, err)
+        assert np.array_equal(got[nm], one[nm]), f"{nm}: the 4-thread run differs from the 1-thread run"
+
+
 EXAMPLE_CLI = os.path.join(ROOT, "examples", "_build", "spleeter_cli_b200")
 MODEL_FP16 = os.path.join(ROOT, "spleeterrt_b200", "weights", "model_fp16.bin")
 

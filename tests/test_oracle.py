@@ -23,11 +23,12 @@ def test_coeff_layout(oracle):
 
 def test_sigmoid_lut_vs_reference(oracle):
     r = _ref(oracle)
-    xs = np.linspace(-8, 8, 4001).astype(np.float32)
-    a = np.array([r.lib.fastSigmoid(float(x)) for x in xs])
-    b = np.array([oracle.port().srt_oracle_sigmoid_lut(float(x)) for x in xs])
-    assert np.abs(a - b).max() <= 1e-7
-    assert b[0] == 0.0 and b[-1] == 1.0                                  # hard clip outside +-7 (spleeter.c:32-35)
+    xs = np.concatenate([np.linspace(-8, 8, 4001), np.float32(-7.0) + np.float32(0.01367188) * np.arange(1025, dtype=np.float32),
+                         np.random.default_rng(0).uniform(-7.5, 7.5, 20000)]).astype(np.float32)
+    a = np.array([r.lib.fastSigmoid(float(x)) for x in xs], np.float32)
+    b = np.array([oracle.port().srt_oracle_sigmoid_lut(float(x)) for x in xs], np.float32)
+    assert np.array_equal(a, b)                                          # the table is the reference's, bit for bit
+    assert b[0] == 0.0 and b[4000] == 1.0                                # hard clip outside +-7 (spleeter.c:32-35)
 
 
 def test_weights_sha(oracle):
