@@ -211,6 +211,18 @@ int srt_set_timing(srt_ctx* ctx, int enable);
  * reference's planar [stem][img][C][H][W] order.  name: "skip1".."skip6", "up1".."up6".
  * Returns the number of floats written, or a negative status. */
 long long srt_debug_tensor(srt_ctx* ctx, const char* name, float* dst, size_t max_floats);
+/* ---- measured roofline denominators (no context needed) ------------------------------------------------------------
+ * srt_probe_tensor_peak: every SM issues M = 128, N = 256 tcgen05 MMAs back to back from shared memory for `seconds` of device
+ *   time; kind 0 = kind::tf32 (the main term of the tensor-core layers), 1 = kind::f16 on bf16 operands (the compensation term).
+ *   The result is the MMA pipe's issue rate x the clock the board holds under that load: the tensor roofline bench.py reports
+ *   against (a short probe gives the burst figure, a multi-second one the power-capped sustained figure).
+ * srt_probe_copy_bandwidth: best of 5 device-to-device copies of `bytes` bytes (read + write bytes per second): the HBM roofline
+ *   measured by this library's own kernel, beside MEASURED_PEAKS.json. */
+int srt_probe_tensor_peak(int device, int kind, double seconds, double* tflops_out);
+int srt_probe_copy_bandwidth(int device, size_t bytes, double* gbs_out);
+/* the cudaStream_t the context enqueues on (its own, or srt_config.cuda_stream): for callers that order their own device work
+ * or CUDA events against the library's kernels (bench.py, the NCCL dispatcher of srt_dispatch.h) */
+void* srt_cuda_stream(srt_ctx* ctx);
 /* pinned host memory helpers (so callers can hand page-locked buffers to *_batch) */
 void* srt_host_alloc(size_t bytes);
 void srt_host_free(void* p);

@@ -22,13 +22,17 @@ HEADER_SYMBOLS = {
                    "srt_separate_device_interleaved", "srt_resample_frames", "srt_resample_host", "srt_resample_device",
                    "srt_resample_plan", "srt_stft_rows",
                    "srt_stft_host", "srt_istft_host", "srt_launch_count", "srt_last_timing", "srt_set_timing",
-                   "srt_debug_tensor", "srt_host_alloc", "srt_host_free", "srt_synchronize",
+                   "srt_debug_tensor", "srt_probe_tensor_peak", "srt_probe_copy_bandwidth", "srt_cuda_stream", "srt_host_alloc", "srt_host_free", "srt_synchronize",
                    "srt_stream_create", "srt_stream_process", "srt_stream_destroy", "srt_stream_launch_count"],
     "spleeter.h": ["getCoeffSize", "allocateSpleeterStr", "initSpleeter", "getMaskPtr", "processSpleeter",
                    "freeSpleeter"],
     "stftFix.h": ["InitSTFT", "FreeSTFT", "stft", "istft"],
     "Spleeter4Stems.h": ["Spleeter4StemsInit", "Spleeter4StemsFree", "Spleeter4StemsProcessSamples"],
 }
+# include/srt_dispatch.h lives in its own library (libspleeterrt_dispatch.so: links libnccl)
+DISPATCH_SYMBOLS = ["srt_dispatch_get_id", "srt_dispatch_create", "srt_dispatch_destroy", "srt_dispatch_last_error",
+                    "srt_dispatch_broadcast_weights", "srt_dispatch_broadcast_sizes", "srt_dispatch_separate_device", "srt_dispatch_wait",
+                    "srt_dispatch_comm_stream", "srt_dispatch_schedule", "srt_dispatch_local_streams"]
 
 
 class SrtError(RuntimeError):
@@ -122,11 +126,126 @@ def load_library():
     return lib
 
 
-def exported_symbols():
+def exported_symbols(path=None):
     """Dynamic symbols of the built library (used by the CPU tests; no GPU needed)."""
     import subprocess
-    out = subprocess.check_output(["nm", "-D", "--defined-only", lib_path()], text=True)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", path or lib_path()], text=True)
     return {line.split()[-1] for line in out.splitlines() if line.strip()}
+
+
+def dispatch_lib_path():
+    return os.path.join(PKG, "libspleeterrt_dispatch.so")
+
+
+_dlib = None
+
+
+def load_dispatch_library():
+    """libspleeterrt_dispatch.so (include/srt_dispatch.h).  Load torch (its NCCL) first when the process uses torch.distributed."""
+    global _dlib
+    if _dlib is not None:
+        return _dlib
+    load_library()
+    if not os.path.exists(dispatch_lib_path()):
+        raise SrtError("libspleeterrt_dispatch.so has not been built: python -m spleeterrt_b200.build")
+    lib = C.CDLL(dispatch_lib_path())
+    lib.srt_dispatch_last_error.restype = C.c_char_p
+    lib.srt_dispatch_get_id.argtypes = [C.c_void_p]
+    lib.srt_dispatch_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.srt_dispatch_destroy.argtypes = [C.c_void_p]
+    lib.srt_dispatch_broadcast_weights.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.srt_dispatch_broadcast_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.srt_dispatch_separate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                                 C.c_void_p, C.c_int]
+    lib.srt_dispatch_wait.argtypes = [C.c_void_p]
+    lib.srt_dispatch_comm_stream.restype = C.c_void_p
+    lib.srt_dispatch_comm_stream.argtypes = [C.c_void_p]
+    lib.srt_dispatch_schedule.restype = C.c_longlong
+    lib.srt_dispatch_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
+    lib.srt_dispatch_local_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    _dlib = lib
+    return lib
+
+
+def dispatch_schedule(world, rank, root, n_samples, pairs, chunks):
+    """The point-to-point schedule of one rank (host only): int32[n][6] rows {group, kind, peer, stream, slot, count}."""
+    lib = load_dispatch_library()
+    ns = (C.c_size_t * len(n_samples))(*[int(x) for x in n_samples])
+    n = lib.srt_dispatch_schedule(world, rank, root, ns, len(n_samples), pairs, chunks, None, 0)
+    if n < 0:
+        raise SrtError(lib.srt_dispatch_last_error().decode())
+    rows = np.zeros((max(n, 1), 6), np.int32)
+    lib.srt_dispatch_schedule(world, rank, root, ns, len(n_samples), pairs, chunks, rows.ctypes.data, n)
+    return rows[:n]
+
+
+class NcclDispatcher:
+    """include/srt_dispatch.h: one per rank.  `exchange_id(id_bytes_or_None) -> id_bytes` is the launcher's job (rank 0 passes its
+    fresh id, everybody gets it back): torch.distributed.broadcast_object_list under torchrun, a file or MPI elsewhere."""
+
+    def __init__(self, world, rank, device, exchange_id):
+        self.lib = load_dispatch_library()
+        self.world, self.rank = world, rank
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(self.lib.srt_dispatch_get_id(buf))
+        ident = exchange_id(bytes(buf) if rank == 0 else None)
+        buf = (C.c_ubyte * 128)(*ident)
+        h = C.c_void_p()
+        self._check(self.lib.srt_dispatch_create(buf, world, rank, device, C.byref(h)))
+        self.h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SrtError(f"dispatch error {rc}: {self.lib.srt_dispatch_last_error().decode()}")
+
+    def broadcast_nets(self, nets, n_nets, root=0):
+        """nets: [(coeff, mode)] on root (None elsewhere) -> the same list on every rank (one ncclBroadcast of the blobs)."""
+        flat = np.zeros((n_nets, COEFF_FLOATS), np.float32)
+        modes = np.zeros(n_nets, np.uint64)
+        if self.rank == root:
+            for k, (c, m) in enumerate(nets):
+                flat[k] = np.asarray(c, np.float32)
+                modes[k] = int(m)
+        self._check(self.lib.srt_dispatch_broadcast_weights(self.h, flat.ctypes.data, n_nets, root))
+        self._check(self.lib.srt_dispatch_broadcast_sizes(self.h, modes.ctypes.data, n_nets, root))
+        return [(np.ascontiguousarray(flat[k]), int(modes[k])) for k in range(n_nets)]
+
+    def separate_device(self, sep, root, pl, pr, n_arr, n_streams, uw, po, chunks=4):
+        """pl / pr / po: ctypes arrays of device pointers on root (None elsewhere); n_arr: c_size_t array, same on all ranks."""
+        self._check(self.lib.srt_dispatch_separate_device(self.h, sep.h, root, pl, pr, n_arr, n_streams, uw, po, chunks))
+
+    def wait(self):
+        self._check(self.lib.srt_dispatch_wait(self.h))
+
+    def comm_stream(self):
+        return self.lib.srt_dispatch_comm_stream(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.srt_dispatch_destroy(self.h)
+            self.h = None
+
+
+def probe_tensor_peak(kind="tf32", seconds=0.1, device=0):
+    """TFLOP/s of back-to-back N = 256 tcgen05 MMAs on every SM (srt_probe_tensor_peak): kind "tf32" or "bf16"."""
+    lib = load_library()
+    out = C.c_double(0.0)
+    lib.srt_probe_tensor_peak.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    rc = lib.srt_probe_tensor_peak(device, 0 if kind == "tf32" else 1, float(seconds), C.byref(out))
+    if rc != 0:
+        raise SrtError(f"srt error {rc}: {lib.srt_last_error().decode()}")
+    return out.value
+
+
+def probe_copy_bandwidth(nbytes=1 << 30, device=0):
+    lib = load_library()
+    out = C.c_double(0.0)
+    lib.srt_probe_copy_bandwidth.argtypes = [C.c_int, C.c_size_t, C.POINTER(C.c_double)]
+    rc = lib.srt_probe_copy_bandwidth(device, int(nbytes), C.byref(out))
+    if rc != 0:
+        raise SrtError(f"srt error {rc}: {lib.srt_last_error().decode()}")
+    return out.value
 
 
 def half_to_float(halves):

@@ -11,7 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libspleeterrt_b200.so")
-SOURCES = ["srt_plan.cpp", "srt_weights.cpp", "srt_ctx.cu", "srt_conv_tc.cu", "srt_conv_rp.cu", "srt_up6_tc.cu", "srt_unet_simt.cu", "srt_stft.cu", "srt_stream.cu", "srt_tier_a.cu", "srt_resample.cu"]
+SOURCES = ["srt_plan.cpp", "srt_weights.cpp", "srt_ctx.cu", "srt_conv_tc.cu", "srt_conv_rp.cu", "srt_up6_tc.cu", "srt_unet_simt.cu", "srt_stft.cu", "srt_stream.cu", "srt_tier_a.cu", "srt_resample.cu", "srt_probe.cu"]
 HEADERS = ["srt_plan.h", "srt_kernels.cuh", "srt_ptx.cuh", "srt_epilogue.cuh", "srt_fft.cuh", "srt_internal.h",
            "../../include/srt_b200.h", "../../include/spleeter.h", "../../include/stftFix.h", "../../include/Spleeter4Stems.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -53,7 +53,29 @@ def build(force=False, verbose=False):
     if force or procs or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
         subprocess.check_call(cmd)
+    build_dispatch(force, verbose)
     return LIB
+
+
+DISPATCH_LIB = os.path.join(PKG, "libspleeterrt_dispatch.so")
+
+
+def build_dispatch(force=False, verbose=False):
+    """libspleeterrt_dispatch.so: the NCCL stream dispatcher (include/srt_dispatch.h), a separate library so that the product
+    library itself depends on nothing but libc/libstdc++.  Links the system libnccl (SONAME libnccl.so.2: inside a torch process the
+    loader resolves it to the copy torch has already loaded) and libspleeterrt_b200.so."""
+    src = os.path.join(CSRC, "srt_dispatch.cu")
+    obj = os.path.join(PKG, "_build", "srt_dispatch.o")
+    hdrs = [os.path.join(PKG, "..", "include", h) for h in ("srt_dispatch.h", "srt_b200.h")]
+    if force or _stale(obj, [src] + hdrs):
+        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    if force or _stale(DISPATCH_LIB, [obj, LIB]):
+        subprocess.check_call([NVCC, "-shared", "-o", DISPATCH_LIB, obj, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+                               "-L", PKG, "-lspleeterrt_b200", "-lnccl", "-Xlinker", "-rpath=$ORIGIN"])
+    return DISPATCH_LIB
 
 
 def build_examples():

@@ -1507,6 +1507,7 @@ extern "C" int srt_synchronize(srt_ctx* c)
     }
     return 0;
 }
+extern "C" void* srt_cuda_stream(srt_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" void* srt_host_alloc(size_t bytes)
 {
     void* p = nullptr;

@@ -192,6 +192,44 @@ def test_library_exports_every_declared_symbol():
     assert lib.getCoeffSize() == 9822725 * 4          # pure host query, no device touched
 
 
+def test_dispatch_library_exports_and_schedule_pairs_up():
+    """include/srt_dispatch.h: every declared symbol is exported by libspleeterrt_dispatch.so, and the point-to-point schedule
+    (the part of the NCCL dispatcher that can be wrong without a GPU) is consistent: for every ordered pair of ranks the sender's
+    list of sends and the receiver's list of recvs agree element by element (group, stream, slot, count) - NCCL's matching
+    rule - every stream of a non-root rank is scattered exactly once per channel and gathered once per output, root moves
+    nothing to itself, and ragged lengths / more ranks than streams / one chunk per stream all hold."""
+    import spleeterrt_b200 as srt
+    declared = _declared("srt_dispatch.h")
+    assert declared == set(srt.DISPATCH_SYMBOLS), declared ^ set(srt.DISPATCH_SYMBOLS)
+    exported = srt.exported_symbols(srt.dispatch_lib_path())
+    assert declared <= exported, declared - exported
+    rng = np.random.default_rng(3)
+    for world, root, n_streams, pairs, chunks in [(2, 0, 5, 4, 2), (8, 0, 37, 5, 4), (4, 2, 3, 2, 3), (8, 0, 1024, 5, 4), (3, 1, 7, 1, 8)]:
+        n = rng.integers(1, 500000, n_streams)
+        sched = [srt.dispatch_schedule(world, r, root, n, pairs, chunks) for r in range(world)]
+        for a in range(world):
+            for b in range(world):
+                if a == b:
+                    continue
+                sends = [tuple(x[[0, 3, 4, 5]]) for x in sched[a] if x[1] == 0 and x[2] == b]
+                recvs = [tuple(x[[0, 3, 4, 5]]) for x in sched[b] if x[1] == 1 and x[2] == a]
+                assert sends == recvs, (world, root, a, b)
+                if a != root and b != root:
+                    assert not sends
+        assert all(x[2] != root for x in sched[root])                                   # nothing to itself
+        for r in range(world):
+            if r == root:
+                continue
+            ids = list(range(r, n_streams, world))
+            got_in = sorted((int(x[3]), int(x[4])) for x in sched[r] if x[1] == 1)
+            got_out = sorted((int(x[3]), int(x[4])) for x in sched[r] if x[1] == 0)
+            assert got_in == sorted((i, s) for i in ids for s in (0, 1))
+            assert got_out == sorted((i, 2 + s) for i in ids for s in range(2 * pairs))
+            assert all(int(x[5]) == int(n[x[3]]) for x in sched[r])
+            groups = [int(x[0]) for x in sched[r]]
+            assert groups == sorted(groups) and (not groups or max(groups) < 2 * chunks)  # scatter chunks, then gather chunks
+
+
 def test_no_cpu_fallback_without_gpu(oracle):
     """Without a CUDA device the product must fail loudly, not fall back."""
     import torch
