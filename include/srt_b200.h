@@ -59,6 +59,12 @@ typedef struct {
                             *       operand error ~2^-19, stems agree with the fp32 reference to ~1e-6 RMS at any level;
                             *   1 = SRT_PRECISION_TF32: single-pass TF32 operands (2^-12): ~1.3x faster U-Net, stem error
                             *       ~1e-4 of the stem's level (3e-5 RMS on the -12 dBFS test signal, above 1e-4 at full scale). */
+    int share_weights;     /* 1: contexts created on the same device with the same coeffs POINTERS, stem modes and configuration
+                            * share one device copy of the packed weights and tables (created once, reference-counted) instead of
+                            * packing and uploading per context.  The caller promises the blobs stay unchanged while any such
+                            * context lives - exactly the contract of the reference's initSpleeter, which keeps the pointer
+                            * (spleeter.c:129) and is handed ONE pointer for all instances of a run (main.c:557).  The tier-A
+                            * initSpleeter sets it; 0 (default) copies as before. */
 } srt_config;
 #define SRT_PRECISION_COMPENSATED 0
 #define SRT_PRECISION_TF32 1

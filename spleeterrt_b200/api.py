@@ -42,7 +42,7 @@ class SrtError(RuntimeError):
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int), ("n_stems", C.c_int), ("time_step", C.c_int), ("bin_limit", C.c_int),
                 ("max_images", C.c_int), ("max_batch_images", C.c_int), ("flavour", C.c_int),
-                ("conv_impl", C.c_int), ("cuda_stream", C.c_void_p), ("precision", C.c_int)]
+                ("conv_impl", C.c_int), ("cuda_stream", C.c_void_p), ("precision", C.c_int), ("share_weights", C.c_int)]
 
 
 PRECISION_COMPENSATED, PRECISION_TF32 = 0, 1      # srt_config.precision (include/srt_b200.h)
@@ -325,12 +325,12 @@ class Separator:
     """
 
     def __init__(self, nets, time_step, bin_limit, max_images=1, max_batch_images=0, device=0, flavour=0,
-                 conv_impl=None, cuda_stream=None, precision=None):
+                 conv_impl=None, cuda_stream=None, precision=None, share_weights=False):
         self.lib = load_library()
         if conv_impl is None:
             conv_impl = 1 if os.environ.get("SRT_CONV_IMPL", "") == "simt" else 0
         cfg = _Config(device, len(nets), time_step, bin_limit, max_images, max_batch_images, flavour, conv_impl,
-                      cuda_stream, _precision(precision))
+                      cuda_stream, _precision(precision), 1 if share_weights else 0)
         self.S, self.T, self.F = len(nets), time_step, bin_limit
         self.max_images = max_images
         coeffs = [np.ascontiguousarray(c, np.float32) for c, _ in nets]
@@ -342,6 +342,7 @@ class Separator:
         h = C.c_void_p()
         self._check(self.lib.srt_create(C.byref(cfg), cp if self.S else None, modes if self.S else None, C.byref(h)))
         self.h = h
+        self._coeffs = coeffs if share_weights else None      # shared sets are keyed by these host pointers: keep them alive
 
     def _check(self, rc):
         if rc != 0:

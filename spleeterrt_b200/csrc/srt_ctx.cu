@@ -7,6 +7,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -109,8 +112,40 @@ constexpr int kMetaSlots = 16;    // per-call metadata ring
 constexpr int kTicketMod = 3 << 28;   // tickets wrap here (multiple of kBatchSlots)
 constexpr int kBatchSlots = 3;    // host-pointer batches in flight (upload of k+1 | kernels of k | download of k-1)
 
+// srt_config.share_weights: the constant device data of a context (packed weights, k-block tables, epilogue vectors,
+// transform tables - everything build() uploads) keyed by what it is a function of.  Contexts with an equal key take the
+// uploads of the first one, in build()'s call order.
+struct SharedUploads {
+    std::vector<void*> ptrs;
+    int device = 0;
+    ~SharedUploads()
+    {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(device);
+        for (void* p : ptrs) cudaFree(p);
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+struct SharedKey {
+    std::vector<const void*> coeffs;
+    std::vector<int> ints;          // device, S, T, F, B, NB, flavour, conv_impl, precision, modes...
+    std::vector<float> fingerprint; // sampled weights: a pointer that was freed and reused for other weights must not hit
+    bool operator<(const SharedKey& o) const
+    {
+        if (coeffs != o.coeffs) return coeffs < o.coeffs;
+        if (ints != o.ints) return ints < o.ints;
+        return fingerprint < o.fingerprint;
+    }
+};
+static std::mutex g_shared_mu;
+static std::map<SharedKey, std::weak_ptr<SharedUploads>> g_shared;
+
 struct srt_ctx {
     srt_config cfg{};
+    std::shared_ptr<SharedUploads> shared;   // non-null: uploads go through / come from the shared set
+    bool shared_hit = false;                 // the set already existed: skip packing, take pointers in order
+    size_t shared_next = 0;
     int S = 0, T = 0, F = 0, B = 0, NB = 0;   // B = U-Net batch capacity, NB = batch images capacity
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -168,6 +203,17 @@ struct srt_ctx {
     long long batch_seq = 0;
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer API (H2D / D2H overlap compute)
     cudaEvent_t ev_in[8]{}, ev_c[8]{};
+    // CUDA graphs of the U-Net pass, one per distinct (first image, images, mask destination): the 15-19 launches of a pass
+    // replay as one graph launch (their parameter blocks are baked into the nodes, and a pass with the same key has the same
+    // parameters).  Matters for small batches: one 10 s stream is ~0.6 ms of kernels and the launch gaps were visible.
+    struct UnetGraph {
+        int mag_img0, Bv, mask_stride, mask_img0;
+        float* mask_base;
+        cudaGraphExec_t exec;
+        int kernels;
+    };
+    std::vector<UnetGraph> graphs;
+    bool use_graphs = true;
     // bookkeeping
     long long launches = 0;
     bool timing = false;
@@ -195,8 +241,20 @@ static int dalloc(srt_ctx* c, Tp** p, size_t count)
 template <class Tp>
 static int upload(srt_ctx* c, Tp** p, const std::vector<Tp>& h)
 {
-    int r = dalloc(c, p, h.size());
-    if (r) return r;
+    if (c->shared && c->shared_hit) {          // same key, same call order: the data is already on the device
+        if (c->shared_next >= c->shared->ptrs.size()) return fail(SRT_ERR_STATE, "shared weight set is shorter than this context's uploads");
+        *p = (Tp*)c->shared->ptrs[c->shared_next++];
+        return 0;
+    }
+    if (c->shared) {
+        void* q = nullptr;
+        CK(cudaMalloc(&q, std::max<size_t>(h.size(), 1) * sizeof(Tp)));
+        c->shared->ptrs.push_back(q);          // owned by the set, freed with its last context
+        *p = (Tp*)q;
+    } else {
+        int r = dalloc(c, p, h.size());
+        if (r) return r;
+    }
     CK(cudaMemcpy(*p, h.data(), h.size() * sizeof(Tp), cudaMemcpyHostToDevice));
     return 0;
 }
@@ -253,6 +311,8 @@ extern "C" void srt_destroy(srt_ctx* c)
     internal::DeviceGuard dev_guard(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->next) { srt_destroy(c->next); c->next = nullptr; }
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : c->allocs) cudaFree(p);
     if (c->d_meta_base) cudaFree(c->d_meta_base);
     if (c->h_meta_base) cudaFreeHost(c->h_meta_base);
@@ -434,7 +494,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     // Weights that are exactly TF32-representable (the reference's fp16 model) need one MMA term; anything else
     // (fp32 `.dat` dumps) is contracted as tf32(w) + tf32(w - tf32(w)) so rounding the weights never costs parity.
     bool split = false;
-    for (int s = 0; s < S; s++) split = split || !weights_tf32_exact(coeffs[s]);
+    for (int s = 0; s < S; s++) split = split || !weights_tf32_exact(coeffs[s]);     // ~10 ms per net: cheap next to packing
     if (const char* we = getenv("SRT_WEIGHT_SPLIT")) split = atoi(we) != 0;
     c->split_weights = split;
     // small batches: narrower N tiles so that the deep layers fill the SMs (SRT_TC_NARROW=0 keeps the wide tiles)
@@ -451,7 +511,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         // weights + epilogue vectors
         std::vector<float> wpk((size_t)S * L.w_floats_per_stem), bias((size_t)S * L.cout), sc((size_t)S * L.cout, 1.0f), of((size_t)S * L.cout, 0.0f);
         for (int s = 0; s < S; s++) {
-            pack_layer(L, coeffs[s], &wpk[(size_t)s * L.w_floats_per_stem]);
+            if (!c->shared_hit) pack_layer(L, coeffs[s], &wpk[(size_t)s * L.w_floats_per_stem]);
             const float* k = coeffs[s];
             const size_t bo = L.transposed ? cl.up_b[L.index - 5] : cl.down_b[L.index + 1];
             const size_t bn = L.transposed ? cl.up_bn[L.index - 5] : cl.down_bn[L.index + 1];
@@ -540,7 +600,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         RowConvParams& q = c->rp[li];
         std::memset(&q, 0, sizeof q);
         std::vector<float> wpk((size_t)S * rpl.w_floats_per_stem);
-        for (int s = 0; s < S; s++) pack_row_layer(rpl, coeffs[s], &wpk[(size_t)s * rpl.w_floats_per_stem]);
+        for (int s = 0; s < S && !c->shared_hit; s++) pack_row_layer(rpl, coeffs[s], &wpk[(size_t)s * rpl.w_floats_per_stem]);
         float* dw;
         RowChunk* dch;
         KBlock* dkb;
@@ -579,7 +639,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             RowConvParams& q = c->d1[c->n_d1];
             std::memset(&q, 0, sizeof q);
             std::vector<float> wpk((size_t)dp.kb.size() * 16 * g * kKB1);
-            pack_down1(dp, coeffs + s0, g, wpk.data());
+            if (!c->shared_hit) pack_down1(dp, coeffs + s0, g, wpk.data());
             float* dw;
             if ((r = upload(c, &dw, wpk))) return r;
             q.chunks = dch; q.n_chunks = 2; q.kb = dkb; q.nkb = (int)dp.kb.size();
@@ -685,7 +745,7 @@ extern "C" int srt_create_cli(const srt_config* cfg, int n_outputs, const float*
 // U-Net on Bv images whose magnitudes sit at d_mag (layout [Bv][T][F][2]); masks go to
 // mask_base[s][mask_img0 + b] with `mask_stride` images between stems.
 // ------------------------------------------------------------------------------------------
-static int run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask_stride, int mask_img0)
+static int run_unet_launches(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask_stride, int mask_img0)
 {
     const int S = c->S;
     c->last_Bv = Bv;
@@ -778,6 +838,58 @@ static int run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(SRT_ERR_CUDA, "U-Net launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// The pass as a CUDA graph (captured on first use per key, then replayed).  Per-kernel timing (srt_set_timing) and the SIMT
+// verification path launch directly.  SRT_GRAPHS=0 disables.
+static int run_unet(srt_ctx* c, int mag_img0, int Bv, float* mask_base, int mask_stride, int mask_img0)
+{
+    if (!c->use_graphs || c->timing || c->cfg.conv_impl == 1) return run_unet_launches(c, mag_img0, Bv, mask_base, mask_stride, mask_img0);
+    srt_ctx::UnetGraph* slot = nullptr;
+    for (auto& g : c->graphs)
+        if (g.mag_img0 == mag_img0 && g.Bv == Bv && g.mask_base == mask_base && g.mask_stride == mask_stride && g.mask_img0 == mask_img0) { slot = &g; break; }
+    if (slot && slot->exec) {
+        c->last_Bv = Bv;
+        CK(cudaGraphLaunch(slot->exec, c->stream));
+        c->launches += slot->kernels;
+        return 0;
+    }
+    if (!slot) {
+        // first pass with this key: plain launches (they also do the kernels' one-time setup - opt-in shared-memory attributes -
+        // outside any capture); a key that comes back is captured on its second pass
+        if (c->graphs.size() < 64) c->graphs.push_back(srt_ctx::UnetGraph{mag_img0, Bv, mask_stride, mask_img0, mask_base, nullptr, 0});
+        return run_unet_launches(c, mag_img0, Bv, mask_base, mask_stride, mask_img0);
+    }
+    const long long before = c->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        (void)cudaGetLastError();
+        c->use_graphs = false;                                   // e.g. the caller is already capturing this stream
+        return run_unet_launches(c, mag_img0, Bv, mask_base, mask_stride, mask_img0);
+    }
+    const int r = run_unet_launches(c, mag_img0, Bv, mask_base, mask_stride, mask_img0);
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    const int kernels = (int)(c->launches - before);
+    c->launches = before;
+    if (r || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        c->use_graphs = false;
+        return r ? r : run_unet_launches(c, mag_img0, Bv, mask_base, mask_stride, mask_img0);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess || !exec) {
+        (void)cudaGetLastError();
+        c->use_graphs = false;
+        return run_unet_launches(c, mag_img0, Bv, mask_base, mask_stride, mask_img0);
+    }
+    slot->exec = exec;
+    slot->kernels = kernels;
+    CK(cudaGraphLaunch(exec, c->stream));
+    c->launches += kernels;
     return 0;
 }
 

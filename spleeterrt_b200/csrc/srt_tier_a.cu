@@ -36,6 +36,7 @@ extern "C" void initSpleeter(struct _spleeter* nn, size_t width, size_t height, 
     cfg.bin_limit = (int)width;
     cfg.max_images = 1;
     cfg.flavour = 0;   // Executable flavour: LUT sigmoid, ELU clamp
+    cfg.share_weights = 1;   // processMT hands ONE coefficient pointer to all its instances (main.c:557): pack / upload once
     const char* impl = getenv("SRT_CONV_IMPL");
     cfg.conv_impl = (impl && !strcmp(impl, "simt")) ? 1 : 0;
     const float* cp = (const float*)coeff;

@@ -504,3 +504,50 @@ def test_fp32_weights_use_two_term_split(srt, oracle, small_nets):
     ref = oracle.separate(nets, L, R, 64, 512)
     for s in range(len(nets)):
         assert rms(got[s] - ref[s]) < 1e-4, f"stem {s}: {rms(got[s] - ref[s])}"
+
+
+def test_unet_pass_replays_as_a_cuda_graph(srt, oracle, small_nets, monkeypatch):
+    """The U-Net pass is captured into a CUDA graph on its second use per (first image, images, mask destination) and replayed
+    afterwards: results are bit-identical to plain launches (SRT_GRAPHS=0), call after call, with a changing batch in between,
+    and the launch counter keeps counting kernels."""
+    T, F = 64, 512
+    a, b = oracle.synth_pcm(81, n=60000), oracle.synth_pcm(82, n=30000)
+    monkeypatch.setenv("SRT_GRAPHS", "0")
+    plain = srt.Separator(small_nets, T, F, max_images=2, max_batch_images=2)
+    want_a, want_ab = plain.separate([a])[0], plain.separate([a, b])
+    n_plain = plain.launch_count()
+    plain.close()
+    monkeypatch.delenv("SRT_GRAPHS")
+    sep = srt.Separator(small_nets, T, F, max_images=2, max_batch_images=2)
+    for _ in range(4):                                         # direct, capture + replay, replay, replay
+        assert np.array_equal(sep.separate([a])[0], want_a)
+    got_ab = sep.separate([a, b])                              # another key
+    assert np.array_equal(got_ab[0], want_ab[0]) and np.array_equal(got_ab[1], want_ab[1])
+    assert np.array_equal(sep.separate([a])[0], want_a)
+    assert sep.launch_count() > 2 * n_plain                    # replays are counted per kernel, not per graph
+    sep.close()
+
+
+def test_shared_weight_sets(srt, oracle, small_nets):
+    """srt_config.share_weights (what the tier-A initSpleeter uses: processMT creates its instances from ONE coefficient
+    pointer, main.c:557): contexts with the same blobs and configuration share one device copy of the packed weights;
+    results equal a private context's bit for bit, in any destruction order, and a different configuration gets its own set."""
+    T, F = 64, 256
+    L, R = oracle.synth_pcm(83, n=40000)
+    nets = [(np.ascontiguousarray(c), m) for c, m in small_nets]
+    private = srt.Separator(nets, T, F, max_images=1)
+    want = private.separate([(L, R)])[0]
+    private.close()
+    a = srt.Separator(nets, T, F, max_images=1, share_weights=True)
+    b = srt.Separator(nets, T, F, max_images=1, share_weights=True)          # hit: no packing, no upload
+    c = srt.Separator(nets, T, 2 * F, max_images=1, share_weights=True)      # other geometry: own set
+    assert np.array_equal(a.separate([(L, R)])[0], want)
+    a.close()                                                                # b keeps the set alive
+    assert np.array_equal(b.separate([(L, R)])[0], want)
+    ref_c = oracle.separate(nets, L, R, T, 2 * F)
+    assert rms(c.separate([(L, R)])[0] - ref_c) < 1e-4
+    b.close()
+    c.close()
+    d = srt.Separator(nets, T, F, max_images=1, share_weights=True)          # the set died with b: rebuilt
+    assert np.array_equal(d.separate([(L, R)])[0], want)
+    d.close()
