@@ -278,9 +278,11 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-objects (other configs, probes, sustained run)")
     ap.add_argument("--precision", default="compensated", choices=["compensated", "tf32"],
                     help="srt_config.precision: compensated = TF32 main term + bf16 residual term (default, fp32-grade), tf32 = single pass")
-    ap.add_argument("--dispatch", default="none", choices=["none", "nccl"],
-                    help="nccl: rank 0 holds the PCM of ALL streams in its HBM; scatter / gather over NCCL (include/srt_dispatch.h)")
+    ap.add_argument("--dispatch", default="none", choices=["none", "nccl", "peer", "both"],
+                    help="rank 0 holds the PCM of ALL streams in its HBM (include/srt_dispatch.h).  nccl: grouped ncclSend / ncclRecv scatter and "
+                         "gather; peer: every rank's kernels load / store rank 0's memory over NVLink (CUDA IPC), no copies; both: time both")
     ap.add_argument("--chunks", type=int, default=4, help="pipelined groups of the NCCL dispatcher")
+    ap.add_argument("--verbose", action="store_true", help="phase milestones on stderr (every rank)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -289,6 +291,11 @@ def main():
         reference_arm(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    t_start = time.perf_counter()
+
+    def log(msg):
+        if args.verbose:
+            print(f"[bench rank {rank} +{time.perf_counter() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
     pin_info = numa_pin(local_rank) if world > 1 else {"pinned": False, "why": "single rank"}
 
     import torch
@@ -359,6 +366,7 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
+    log("context and buffers ready")
     # ---- device-resident throughput ----------------------------------------------------------
     for _ in range(args.warmup):
         step_device()
@@ -382,6 +390,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     gpu0_stems = dout[0].cpu().numpy() if rank == 0 else None           # stream 0 of the timed batch, for the parity object
 
+    log(f"device-resident: {ms_step:.3f} ms/step")
     # ---- end to end through the host-pointer C ABI --------------------------------------------
     # (a) one synchronous call per step: returns after the D2H of every stem
     for _ in range(2):
@@ -430,15 +439,17 @@ def main():
     d2h_ceiling = hout.numel() * 4 * 3 / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
     d2h_ceiling_min = -max_over_ranks(-d2h_ceiling)
     barrier()
+    log(f"e2e: {ms_e2e:.3f} ms/step pipelined, D2H ceiling {d2h_ceiling:.1f} GB/s")
 
     # ---- BASELINE.json configs[3]: one rank holds every stream, NCCL scatter / gather (include/srt_dispatch.h) -------------------
     dispatch = None
-    if args.dispatch == "nccl" and world > 1:
+    if args.dispatch != "none" and world > 1:
         def exchange(ident):
             box = [ident]
             dist.broadcast_object_list(box, src=0)
             return box[0]
         nd = srt.NcclDispatcher(world, rank, local_rank, exchange)
+        log("NCCL dispatcher up")
         total = ns * world
         n_all = (C.c_size_t * total)(*([N_SAMPLES] * total))
         if rank == 0:
@@ -450,32 +461,64 @@ def main():
         else:
             gpl = gpr = gpo = None
 
-        def step_dispatch():
-            nd.separate_device(sep, 0, gpl, gpr, n_all, total, None, gpo, chunks=args.chunks)
-        for _ in range(2):
-            step_dispatch()
-            nd.wait()
-        barrier()
         cstream = torch.cuda.ExternalStream(nd.comm_stream())
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_dispatch()
-        e1.record(cstream)
-        nd.wait()
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3 / args.steps
-        ms_disp = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-        ok = None
-        if rank == 0:
-            # every stream of the global batch is one of the four synthetic streams of rank 0's own batch: compare with the local result
-            ok = float(max((gout[i] - dout[i % ns]).abs().max() for i in range(0, total, max(1, total // 16))))
-        dispatch = {"mode": "rank 0 holds all PCM in HBM; grouped ncclSend/ncclRecv scatter, per-rank srt_separate_device, gather into rank 0's HBM",
-                    "streams_total": total, "chunks": args.chunks, "ms_per_step": ms_disp, "host_wall_ms_per_step": max_over_ranks(wall),
-                    "value": SECONDS * total / (ms_disp * 1e-3), "unit": "x_realtime",
-                    "bytes_scattered_per_step": int((world - 1) * ns * 2 * N_SAMPLES * 4), "bytes_gathered_per_step": int((world - 1) * ns * S * 2 * N_SAMPLES * 4),
-                    "max_abs_diff_vs_local_path": ok}
+
+        def time_dispatch(step_fn):
+            for _ in range(2):
+                step_fn()
+                nd.wait()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_fn()
+            e1.record(cstream)
+            nd.wait()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3 / args.steps
+            return max_over_ranks(e0.elapsed_time(e1) / args.steps), max_over_ranks(wall)
+        dispatch = {"streams_total": total, "chunks": args.chunks,
+                    "bytes_in_per_step": int((world - 1) * ns * 2 * N_SAMPLES * 4), "bytes_out_per_step": int((world - 1) * ns * S * 2 * N_SAMPLES * 4),
+                    "note": "rank 0 holds the PCM of all streams in its HBM and receives all stems there; device-timed from rank 0's first enqueue "
+                            "to the completion of the last transfer, max over ranks"}
+        if args.dispatch in ("nccl", "both"):
+            ms_disp, wall = time_dispatch(lambda: nd.separate_device(sep, 0, gpl, gpr, n_all, total, None, gpo, chunks=args.chunks))
+            ok = None
+            if rank == 0:
+                # every stream of the global batch is one of the four synthetic streams of rank 0's own batch: compare with the local result
+                ok = float(max((gout[i] - dout[i % ns]).abs().max() for i in range(0, total, max(1, total // 16))))
+            dispatch["nccl_send_recv"] = {"mode": "grouped ncclSend/ncclRecv scatter, per-rank srt_separate_device, gather into rank 0's HBM, pipelined in chunks",
+                                          "ms_per_step": ms_disp, "host_wall_ms_per_step": wall, "value": SECONDS * total / (ms_disp * 1e-3),
+                                          "unit": "x_realtime", "max_abs_diff_vs_local_path": ok}
+            log(f"dispatch (nccl send/recv): {ms_disp:.3f} ms/step")
+        if args.dispatch in ("peer", "both"):
+            p_in, p_out, in_off, out_off, fin, fout = nd.peer_buffers(0, [N_SAMPLES] * total, S)
+            if rank == 0:
+                # the batch lives in root's peer-visible buffer in the dispatcher's layout: [stream][L | R], results [stream][stem][channel]
+                npad = (N_SAMPLES + 3) & ~3
+                assert npad == N_SAMPLES
+                cudart = C.CDLL("libcudart.so.12")               # torch's runtime, already in the process
+                cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+                rc = cudart.cudaMemcpy(p_in, gin.data_ptr(), total * 2 * N_SAMPLES * 4, 3)      # cudaMemcpyDeviceToDevice = 3
+                assert int(rc) == 0, rc
+            barrier()
+            ms_peer, wall = time_dispatch(lambda: nd.separate_peer(sep, 0, n_all, total, None, chunks=args.chunks))
+            ok = None
+            if rank == 0:
+                chk = torch.empty((S, 2, N_SAMPLES), dtype=torch.float32, device="cuda")
+                ok = 0.0
+                for i in range(0, total, max(1, total // 16)):
+                    rc = cudart.cudaMemcpy(chk.data_ptr(), p_out + out_off[i] * 4, S * 2 * N_SAMPLES * 4, 3)
+                    assert int(rc) == 0, rc
+                    ok = max(ok, float((chk - dout[i % ns]).abs().max()))
+            dispatch["peer_memory"] = {"mode": "no copies: every rank's STFT kernel loads the PCM from rank 0's HBM and its overlap-add kernel stores the stems "
+                                               "into rank 0's HBM over NVLink (CUDA IPC mappings); NCCL carries the handles and two one-word all-reduces per step",
+                                       "ms_per_step": ms_peer, "host_wall_ms_per_step": wall, "value": SECONDS * total / (ms_peer * 1e-3),
+                                       "unit": "x_realtime", "max_abs_diff_vs_local_path": ok}
+            log(f"dispatch (peer memory): {ms_peer:.3f} ms/step")
+        best = max((v for k, v in dispatch.items() if isinstance(v, dict)), key=lambda v: v["value"])
+        dispatch["ms_per_step"], dispatch["value"], dispatch["unit"] = best["ms_per_step"], best["value"], "x_realtime"
         barrier()
         nd.close()
         if rank == 0:

@@ -52,6 +52,25 @@ int srt_dispatch_wait(srt_dispatch* d);
 /* The CUDA stream (cudaStream_t) the transfers of the last call ran on, for callers that time with CUDA events. */
 void* srt_dispatch_comm_stream(srt_dispatch* d);
 
+/* ---- peer-memory mode: no copies at all ---------------------------------------------------------------------------------
+ * On an NVSwitch box every GPU can load and store every other GPU's memory at NVLink speed.  Root allocates the batch's PCM and
+ * stem buffers ONCE (srt_dispatch_peer_buffers), the other ranks map them (CUDA IPC handles travel over the NCCL communicator),
+ * and every rank then runs its share of the streams with its STFT kernel LOADING the PCM straight from root's memory and its
+ * overlap-add kernel STORING the stems straight into root's memory: the transfer is the kernels' own global accesses, spread
+ * over the whole step, instead of a send/recv phase before and after.  NCCL only carries the handles and a one-word
+ * all-reduce that tells root when everybody is done.
+ *   layout of root's buffers (srt_dispatch_peer_layout, host only): stream i's channels at in_off[i] (L) and in_off[i] + np_i (R),
+ *   its output pair q / channel c at out_off[i] + (q * 2 + c) * np_i, np_i = n_samples[i] rounded up to 4 floats.
+ * srt_dispatch_peer_buffers: collective; in_floats / out_floats = capacities (root's values are used); returns root's buffers
+ *   as seen from this rank (on root: its own allocation).  The buffers live until the dispatcher is destroyed or re-requested.
+ * srt_dispatch_separate_peer: collective; every rank separates streams rank, rank + world, ... in `chunks` calls of
+ *   srt_separate_device.  srt_dispatch_wait() on root returns when all ranks' stems are in the buffer. */
+int srt_dispatch_peer_layout(const size_t* n_samples, int n_streams, int pairs, size_t* in_off, size_t* out_off,
+                             size_t* in_floats, size_t* out_floats);
+int srt_dispatch_peer_buffers(srt_dispatch* d, int root, size_t in_floats, size_t out_floats, float** d_in, float** d_out);
+int srt_dispatch_separate_peer(srt_dispatch* d, srt_ctx* ctx, int root, const size_t* n_samples, int n_streams,
+                               const float* unaffected, int chunks);
+
 /* ---- the schedule, without NCCL (host only; unit-tested on the CPU) ----------------------------------------------
  * The point-to-point operations rank `rank` issues for one batch, in issue order, as rows of 6 ints:
  *   {group, kind (0 = send, 1 = recv), peer, stream, slot, count}

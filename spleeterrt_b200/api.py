@@ -32,7 +32,8 @@ HEADER_SYMBOLS = {
 # include/srt_dispatch.h lives in its own library (libspleeterrt_dispatch.so: links libnccl)
 DISPATCH_SYMBOLS = ["srt_dispatch_get_id", "srt_dispatch_create", "srt_dispatch_destroy", "srt_dispatch_last_error",
                     "srt_dispatch_broadcast_weights", "srt_dispatch_broadcast_sizes", "srt_dispatch_separate_device", "srt_dispatch_wait",
-                    "srt_dispatch_comm_stream", "srt_dispatch_schedule", "srt_dispatch_local_streams"]
+                    "srt_dispatch_comm_stream", "srt_dispatch_schedule", "srt_dispatch_local_streams",
+                    "srt_dispatch_peer_layout", "srt_dispatch_peer_buffers", "srt_dispatch_separate_peer"]
 
 
 class SrtError(RuntimeError):
@@ -163,6 +164,9 @@ def load_dispatch_library():
     lib.srt_dispatch_schedule.restype = C.c_longlong
     lib.srt_dispatch_schedule.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong]
     lib.srt_dispatch_local_streams.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.srt_dispatch_peer_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.srt_dispatch_peer_buffers.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.srt_dispatch_separate_peer.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     _dlib = lib
     return lib
 
@@ -214,6 +218,21 @@ class NcclDispatcher:
     def separate_device(self, sep, root, pl, pr, n_arr, n_streams, uw, po, chunks=4):
         """pl / pr / po: ctypes arrays of device pointers on root (None elsewhere); n_arr: c_size_t array, same on all ranks."""
         self._check(self.lib.srt_dispatch_separate_device(self.h, sep.h, root, pl, pr, n_arr, n_streams, uw, po, chunks))
+
+    def peer_buffers(self, root, n_samples, pairs):
+        """Peer-memory mode: root's PCM / stem buffers for this batch shape as this rank sees them.
+        Returns (d_in, d_out, in_off, out_off, in_floats, out_floats): device addresses and per-stream float offsets."""
+        ns = len(n_samples)
+        n_arr = (C.c_size_t * ns)(*[int(x) for x in n_samples])
+        in_off, out_off = (C.c_size_t * ns)(), (C.c_size_t * ns)()
+        fi, fo = C.c_size_t(), C.c_size_t()
+        self._check(self.lib.srt_dispatch_peer_layout(n_arr, ns, pairs, in_off, out_off, C.byref(fi), C.byref(fo)))
+        pi, po = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.srt_dispatch_peer_buffers(self.h, root, fi.value, fo.value, C.byref(pi), C.byref(po)))
+        return pi.value, po.value, list(in_off), list(out_off), fi.value, fo.value
+
+    def separate_peer(self, sep, root, n_arr, n_streams, uw=None, chunks=4):
+        self._check(self.lib.srt_dispatch_separate_peer(self.h, sep.h, root, n_arr, n_streams, uw, chunks))
 
     def wait(self):
         self._check(self.lib.srt_dispatch_wait(self.h))

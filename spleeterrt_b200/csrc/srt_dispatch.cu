@@ -104,7 +104,23 @@ struct srt_dispatch {
     size_t in_cap = 0, out_cap = 0;
     float* d_bcast = nullptr;
     size_t bcast_cap = 0;
+    // peer-memory mode: root's buffers as this rank sees them (own allocation on root, IPC mappings elsewhere)
+    float *peer_in = nullptr, *peer_out = nullptr;
+    size_t peer_in_floats = 0, peer_out_floats = 0;
+    int peer_root = -1;
+    bool peer_mapped = false;      // the pointers are IPC mappings (close, not free)
+    float* d_flag = nullptr;       // the one-word all-reduce buffer
+    cudaEvent_t ev_done = nullptr;
 };
+
+static void release_peer(srt_dispatch* d)
+{
+    if (d->peer_in) { if (d->peer_mapped) cudaIpcCloseMemHandle(d->peer_in); else cudaFree(d->peer_in); }
+    if (d->peer_out) { if (d->peer_mapped) cudaIpcCloseMemHandle(d->peer_out); else cudaFree(d->peer_out); }
+    d->peer_in = d->peer_out = nullptr;
+    d->peer_in_floats = d->peer_out_floats = 0;
+    d->peer_root = -1;
+}
 
 extern "C" const char* srt_dispatch_last_error(void) { return g_derr.c_str(); }
 
@@ -147,6 +163,9 @@ extern "C" void srt_dispatch_destroy(srt_dispatch* d)
     if (d->d_in) cudaFree(d->d_in);
     if (d->d_out) cudaFree(d->d_out);
     if (d->d_bcast) cudaFree(d->d_bcast);
+    release_peer(d);
+    if (d->d_flag) cudaFree(d->d_flag);
+    if (d->ev_done) cudaEventDestroy(d->ev_done);
     if (d->comm) ncclCommDestroy(d->comm);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
     delete d;
@@ -322,5 +341,108 @@ extern "C" int srt_dispatch_separate_device(srt_dispatch* d, srt_ctx* ctx, int r
     if (is_root) {   // root's own share finishes on the compute stream: the comm stream (what srt_dispatch_wait waits on) joins it
         DCK(cudaStreamWaitEvent(d->comm_stream, d->ev_out[chunks - 1], 0));
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// peer-memory mode
+// ---------------------------------------------------------------------------------------------------------------------------
+extern "C" int srt_dispatch_peer_layout(const size_t* n_samples, int n_streams, int pairs, size_t* in_off, size_t* out_off,
+                                        size_t* in_floats, size_t* out_floats)
+{
+    if (!n_samples || n_streams < 1 || pairs < 1) return dfail(SRT_ERR_ARG, "bad argument");
+    size_t a = 0, b = 0;
+    for (int i = 0; i < n_streams; i++) {
+        const size_t np = (n_samples[i] + 3) & ~(size_t)3;
+        if (in_off) in_off[i] = a;
+        if (out_off) out_off[i] = b;
+        a += 2 * np;
+        b += (size_t)2 * pairs * np;
+    }
+    if (in_floats) *in_floats = a;
+    if (out_floats) *out_floats = b;
+    return 0;
+}
+
+extern "C" int srt_dispatch_peer_buffers(srt_dispatch* d, int root, size_t in_floats, size_t out_floats, float** d_in, float** d_out)
+{
+    if (!d || !d_in || !d_out || root < 0 || root >= d->world) return dfail(SRT_ERR_ARG, "bad argument");
+    Guard g(d->device);
+    DCK(cudaStreamSynchronize(d->comm_stream));
+    release_peer(d);
+    // {in_floats, out_floats, in handle, out handle} from root to everybody
+    struct Msg {
+        size_t in_floats, out_floats;
+        cudaIpcMemHandle_t hin, hout;
+    } msg;
+    std::memset(&msg, 0, sizeof msg);
+    if (d->rank == root) {
+        if (in_floats < 1 || out_floats < 1) return dfail(SRT_ERR_ARG, "empty peer buffers");
+        DCK(cudaMalloc((void**)&d->peer_in, in_floats * sizeof(float)));     // plain cudaMalloc: whole allocations, exportable
+        DCK(cudaMalloc((void**)&d->peer_out, out_floats * sizeof(float)));
+        d->peer_mapped = false;
+        msg.in_floats = in_floats; msg.out_floats = out_floats;
+        DCK(cudaIpcGetMemHandle(&msg.hin, d->peer_in));
+        DCK(cudaIpcGetMemHandle(&msg.hout, d->peer_out));
+    }
+    int r = bcast_bytes(d, &msg, sizeof msg, root);
+    if (r) return r;
+    if (d->rank != root) {
+        DCK(cudaIpcOpenMemHandle((void**)&d->peer_in, msg.hin, cudaIpcMemLazyEnablePeerAccess));
+        DCK(cudaIpcOpenMemHandle((void**)&d->peer_out, msg.hout, cudaIpcMemLazyEnablePeerAccess));
+        d->peer_mapped = true;
+    }
+    d->peer_in_floats = msg.in_floats; d->peer_out_floats = msg.out_floats; d->peer_root = root;
+    if (!d->d_flag) DCK(cudaMalloc((void**)&d->d_flag, 2 * sizeof(float)));
+    if (!d->ev_done) DCK(cudaEventCreateWithFlags(&d->ev_done, cudaEventDisableTiming));
+    *d_in = d->peer_in;
+    *d_out = d->peer_out;
+    return 0;
+}
+
+extern "C" int srt_dispatch_separate_peer(srt_dispatch* d, srt_ctx* ctx, int root, const size_t* n_samples, int n_streams,
+                                          const float* unaffected, int chunks)
+{
+    if (!d || !ctx || !n_samples || n_streams < 1 || root != d->peer_root) return dfail(SRT_ERR_ARG, "bad argument (srt_dispatch_peer_buffers first)");
+    if (chunks < 1) chunks = 1;
+    Guard g(d->device);
+    const int pairs = srt_output_pairs(ctx);
+    std::vector<size_t> in_off(n_streams), out_off(n_streams);
+    size_t need_in = 0, need_out = 0;
+    srt_dispatch_peer_layout(n_samples, n_streams, pairs, in_off.data(), out_off.data(), &need_in, &need_out);
+    if (need_in > d->peer_in_floats || need_out > d->peer_out_floats) return dfail(SRT_ERR_CAPACITY, "batch exceeds the peer buffers");
+    cudaStream_t cs = (cudaStream_t)srt_cuda_stream(ctx);
+    const std::vector<int> mine = local_streams(d->world, d->rank, n_streams);
+    const int n_local = (int)mine.size();
+    // start line: a one-word all-reduce behind whatever every rank's compute stream already holds - on root that is the work
+    // that produced the PCM (and consumed the previous batch's stems) - and in front of this batch's kernels
+    DCK(cudaEventRecord(d->ev_start, cs));
+    DCK(cudaStreamWaitEvent(d->comm_stream, d->ev_start, 0));
+    NCK(ncclAllReduce(d->d_flag, d->d_flag + 1, 1, ncclFloat, ncclSum, d->comm, d->comm_stream));
+    DCK(cudaEventRecord(d->ev_done, d->comm_stream));
+    DCK(cudaStreamWaitEvent(cs, d->ev_done, 0));
+    for (int c = 0; c < chunks; c++) {
+        int a, b;
+        chunk_range(n_local, chunks, c, a, b);
+        if (a >= b) continue;
+        std::vector<const float*> L(b - a), R(b - a);
+        std::vector<size_t> n(b - a);
+        std::vector<float*> o((size_t)(b - a) * pairs * 2);
+        for (int k = a; k < b; k++) {
+            const int i = mine[k];
+            const size_t np = (n_samples[i] + 3) & ~(size_t)3;
+            L[k - a] = d->peer_in + in_off[i];
+            R[k - a] = d->peer_in + in_off[i] + np;
+            n[k - a] = n_samples[i];
+            for (int sl = 0; sl < pairs * 2; sl++) o[(size_t)(k - a) * pairs * 2 + sl] = d->peer_out + out_off[i] + (size_t)sl * np;
+        }
+        // the kernels' own loads / stores cross NVLink: PCM from root's memory, stems into root's memory
+        if (srt_separate_device(ctx, L.data(), R.data(), n.data(), b - a, unaffected, o.data()))
+            return dfail(SRT_ERR_STATE, "rank %d chunk %d: %s", d->rank, c, srt_last_error());
+    }
+    // completion: a one-word all-reduce behind every rank's kernels (stream order makes their stores visible first)
+    DCK(cudaEventRecord(d->ev_done, cs));
+    DCK(cudaStreamWaitEvent(d->comm_stream, d->ev_done, 0));
+    NCK(ncclAllReduce(d->d_flag, d->d_flag + 1, 1, ncclFloat, ncclSum, d->comm, d->comm_stream));
     return 0;
 }

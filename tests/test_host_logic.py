@@ -230,6 +230,21 @@ def test_dispatch_library_exports_and_schedule_pairs_up():
             assert groups == sorted(groups) and (not groups or max(groups) < 2 * chunks)  # scatter chunks, then gather chunks
 
 
+def test_dispatch_peer_layout():
+    """Peer-memory mode: the layout of root's buffers (host only): 16-byte aligned, disjoint, in stream order."""
+    import spleeterrt_b200 as srt
+    lib = srt.load_dispatch_library()
+    n = [441000, 1, 4097, 300001]
+    arr = (C.c_size_t * 4)(*n)
+    io, oo = (C.c_size_t * 4)(), (C.c_size_t * 4)()
+    fi, fo = C.c_size_t(), C.c_size_t()
+    assert lib.srt_dispatch_peer_layout(arr, 4, 5, io, oo, C.byref(fi), C.byref(fo)) == 0
+    pad = [(x + 3) // 4 * 4 for x in n]
+    assert list(io) == [0, 2 * pad[0], 2 * (pad[0] + pad[1]), 2 * (pad[0] + pad[1] + pad[2])] and fi.value == 2 * sum(pad)
+    assert list(oo) == [10 * sum(pad[:k]) for k in range(4)] and fo.value == 10 * sum(pad)
+    assert all(v % 4 == 0 for v in list(io) + list(oo))
+
+
 def test_no_cpu_fallback_without_gpu(oracle):
     """Without a CUDA device the product must fail loudly, not fall back."""
     import torch
