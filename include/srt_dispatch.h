@@ -64,7 +64,10 @@ void* srt_dispatch_comm_stream(srt_dispatch* d);
  * srt_dispatch_peer_buffers: collective; in_floats / out_floats = capacities (root's values are used); returns root's buffers
  *   as seen from this rank (on root: its own allocation).  The buffers live until the dispatcher is destroyed or re-requested.
  * srt_dispatch_separate_peer: collective; every rank separates streams rank, rank + world, ... in `chunks` calls of
- *   srt_separate_device.  srt_dispatch_wait() on root returns when all ranks' stems are in the buffer. */
+ *   srt_separate_device.  chunks == 1: the overlap-add kernel stores into root's memory directly.  chunks > 1: a chunk's stems are
+ *   written locally and leave with one copy-engine transfer per stream (cudaMemcpyAsync into the mapping) while the next chunk
+ *   computes - on 8 GPUs the direct form ends in a burst of stores from seven GPUs into one (they run in lockstep), the
+ *   pipelined form hides all but the last chunk's transfer.  srt_dispatch_wait() on root returns when all stems are in the buffer. */
 int srt_dispatch_peer_layout(const size_t* n_samples, int n_streams, int pairs, size_t* in_off, size_t* out_off,
                              size_t* in_floats, size_t* out_floats);
 int srt_dispatch_peer_buffers(srt_dispatch* d, int root, size_t in_floats, size_t out_floats, float** d_in, float** d_out);

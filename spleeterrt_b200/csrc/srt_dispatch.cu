@@ -421,6 +421,29 @@ extern "C" int srt_dispatch_separate_peer(srt_dispatch* d, srt_ctx* ctx, int roo
     NCK(ncclAllReduce(d->d_flag, d->d_flag + 1, 1, ncclFloat, ncclSum, d->comm, d->comm_stream));
     DCK(cudaEventRecord(d->ev_done, d->comm_stream));
     DCK(cudaStreamWaitEvent(cs, d->ev_done, 0));
+    // chunks == 1 (or root): the overlap-add kernel stores straight into root's memory.  chunks > 1 on the other ranks: a chunk's
+    // stems land in local memory first and leave with ONE copy-engine transfer per stream while the next chunk computes - a burst
+    // of NVLink stores from seven GPUs at the end of everybody's step (they run in lockstep) is what limits the direct form.
+    const bool staged = chunks > 1 && d->rank != root;
+    std::vector<size_t> loff(n_local + 1, 0);
+    if (staged) {
+        for (int k = 0; k < n_local; k++) loff[k + 1] = loff[k] + (size_t)2 * pairs * ((n_samples[mine[k]] + 3) & ~(size_t)3);
+        if (loff[n_local] > d->out_cap) {
+            DCK(cudaStreamSynchronize(d->comm_stream));
+            DCK(cudaStreamSynchronize(cs));
+            if (d->d_out) cudaFree(d->d_out);
+            d->d_out = nullptr; d->out_cap = 0;
+            DCK(cudaMalloc((void**)&d->d_out, loff[n_local] * sizeof(float)));
+            d->out_cap = loff[n_local];
+        }
+        while ((int)d->ev_out.size() < chunks) {
+            cudaEvent_t e1, e2;
+            DCK(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            DCK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            d->ev_in.push_back(e1);
+            d->ev_out.push_back(e2);
+        }
+    }
     for (int c = 0; c < chunks; c++) {
         int a, b;
         chunk_range(n_local, chunks, c, a, b);
@@ -434,11 +457,19 @@ extern "C" int srt_dispatch_separate_peer(srt_dispatch* d, srt_ctx* ctx, int roo
             L[k - a] = d->peer_in + in_off[i];
             R[k - a] = d->peer_in + in_off[i] + np;
             n[k - a] = n_samples[i];
-            for (int sl = 0; sl < pairs * 2; sl++) o[(size_t)(k - a) * pairs * 2 + sl] = d->peer_out + out_off[i] + (size_t)sl * np;
+            float* base = staged ? d->d_out + loff[k] : d->peer_out + out_off[i];
+            for (int sl = 0; sl < pairs * 2; sl++) o[(size_t)(k - a) * pairs * 2 + sl] = base + (size_t)sl * np;
         }
-        // the kernels' own loads / stores cross NVLink: PCM from root's memory, stems into root's memory
+        // the kernels' own loads cross NVLink (PCM from root's memory); so do their stores in the direct form
         if (srt_separate_device(ctx, L.data(), R.data(), n.data(), b - a, unaffected, o.data()))
             return dfail(SRT_ERR_STATE, "rank %d chunk %d: %s", d->rank, c, srt_last_error());
+        if (staged) {
+            DCK(cudaEventRecord(d->ev_out[c], cs));
+            DCK(cudaStreamWaitEvent(d->comm_stream, d->ev_out[c], 0));
+            for (int k = a; k < b; k++)
+                DCK(cudaMemcpyAsync(d->peer_out + out_off[mine[k]], d->d_out + loff[k], (loff[k + 1] - loff[k]) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    d->comm_stream));
+        }
     }
     // completion: a one-word all-reduce behind every rank's kernels (stream order makes their stores visible first)
     DCK(cudaEventRecord(d->ev_done, cs));
