@@ -172,7 +172,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
                 float v[16];
                 ptx::tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * N_TILE + c0), v);
                 // tmem_full means every MMA has finished reading the stage ring: its first 16 KB become the warps' staging buffers
-                epilogue16(p, s, n, Y, X, phase, nt * N_TILE + c0, v, reinterpret_cast<float4*>(tiles) + warp * 128, valid);
+                const int col = nt * N_TILE + c0;
+                epilogue16(p, s, n, Y, X, p.fused ? col / p.cout : phase, p.fused ? col % p.cout : col, v, reinterpret_cast<float4*>(tiles) + warp * 128, valid);
             }
         }
     }

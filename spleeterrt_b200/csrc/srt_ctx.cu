@@ -499,7 +499,8 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     c->split_weights = split;
     // small batches: narrower N tiles so that the deep layers fill the SMs (SRT_TC_NARROW=0 keeps the wide tiles)
     const char* nwe = getenv("SRT_TC_NARROW");
-    c->plans = build_plans(NetGeom{T, F}, c->B, split, S, (nwe && atoi(nwe) == 0) ? 0 : c->sm_count, c->comp_mask);
+    const char* fze = getenv("SRT_TC_FUSE");      // "0": decoder layers stay phase-separated (A/B timing)
+    c->plans = build_plans(NetGeom{T, F}, c->B, split, S, (nwe && atoi(nwe) == 0) ? 0 : c->sm_count, c->comp_mask, !(fze && atoi(fze) == 0));
     c->conv.resize(c->plans.size());
     for (size_t li = 0; li < c->plans.size(); li++) {
         const LayerPlan& L = c->plans[li];
@@ -542,6 +543,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         p.n_tile = L.n_tile;
         p.n_tiles = L.n_tiles;
         p.phases = L.phases;
+        p.fused = L.fused ? 1 : 0;
         p.Hs = L.Hs;
         p.Ws = L.Ws;
         p.B = c->B;

@@ -55,6 +55,7 @@ struct alignas(64) ConvParams {
     size_t w_stem_stride;         // floats between stems
     size_t w_phase_off[4];
     int n_tile, n_tiles, phases;
+    int fused;                    // decoder with the four output parities fused into N (LayerPlan::fused): column = parity * cout + channel
     int Hs, Ws;                   // tile-space extent
     int B;                        // images per stem in the buffer layout (capacity)
     int Bv;                       // images per stem actually present in this launch

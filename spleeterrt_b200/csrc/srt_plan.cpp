@@ -109,6 +109,13 @@ static std::vector<int32_t> kelem_offsets(const std::vector<KBlock>& kb)
     return off;
 }
 
+// transposed conv: which kernel row serves output parity `par` at input offset d (o = 2h + kh - 1); -1 = none
+int dec_kh(int par, int d)
+{
+    if (par == 0) return d == 0 ? 1 : (d == -1 ? 3 : -1);
+    return d == 1 ? 0 : (d == 0 ? 2 : 4);
+}
+
 // duplicate every k-block (and its k-elements) as a part-1 twin right after it
 template <class KE>
 static void split_kblocks(std::vector<KBlock>& kb, std::vector<KE>& ke, int per)
@@ -142,7 +149,7 @@ bool weights_tf32_exact(const float* coeff)
     return true;
 }
 
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int n_stems, int min_ctas, unsigned comp_mask)
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int n_stems, int min_ctas, unsigned comp_mask, bool fuse_phases)
 {
     std::vector<LayerPlan> plans;
     auto narrow = [&](LayerPlan& L) {
@@ -220,6 +227,23 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int
         L.n_tile = L.cout;
         L.n_tiles = 1;
         choose_tile(L.Ws, L.Hs, n_img, L.tw, L.th, L.nb);
+        // fused parities (see LayerPlan::fused) where N = 4 * cout fits one MMA and the grid still fills the SMs
+        const long fused_ctas = (long)ceil_div(L.Ws, L.tw) * ceil_div(L.Hs, L.th) * ceil_div(n_img, L.nb) * (n_stems > 0 ? n_stems : 1);
+        if (fuse_phases && 4 * L.cout <= 256 && (min_ctas <= 0 || fused_ctas >= min_ctas)) {
+            L.fused = true;
+            L.phases = 1;
+            L.n_tile = 4 * L.cout;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++)
+                    for (int s = 0; s < L.nsrc; s++)
+                        for (int c0 = 0; c0 < L.src[s].C; c0 += kKB) {
+                            L.kb[0].push_back(KBlock{(int8_t)s, (int8_t)dy, (int8_t)dx, 0, c0});
+                            const int base = (s ? L.src[0].C : 0) + c0;
+                            for (int j = 0; j < kKB; j++) L.kelem[0].push_back(KElem{base + j, -1, -1});   // (kh, kw) follow from the column's parity
+                        }
+            plans.push_back(L);
+            continue;
+        }
         narrow(L);
         for (int po = 0; po < 2; po++)
             for (int qo = 0; qo < 2; qo++) {
@@ -259,6 +283,14 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int
                         if (!any) continue;
                         L.kb[0].push_back(KBlock{(int8_t)kSrcLo, (int8_t)dy, (int8_t)dx, (int8_t)kPartLo, c_off});
                         L.kelem[0].insert(L.kelem[0].end(), el.begin(), el.end());
+                    }
+        } else if (L.fused) {
+            L.lo_src = SrcDesc{L.cin, L.Ws, L.Hs};
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++)
+                    for (int c0 = 0; c0 < L.cin; c0 += kKBlo) {
+                        L.kb[0].push_back(KBlock{(int8_t)kSrcLo, (int8_t)dy, (int8_t)dx, (int8_t)kPartLo, c0});
+                        for (int j = 0; j < kKBlo; j++) L.kelem[0].push_back(KElem{c0 + j, -1, -1});
                     }
         } else {
             L.lo_src = SrcDesc{L.cin, L.Ws, L.Hs};      // [skip residual | up residual] = the reference's concatenated channel order
@@ -300,9 +332,20 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
                 const bool lo = (L.kb[p][kb].part & kPartLo) != 0;     // [n_tile][64] bf16 in the same bytes
                 const int width = kb_channels(L.kb[p][kb]);
                 for (int n = 0; n < L.n_tile; n++) {
-                    const int o = nt * L.n_tile + n;
+                    int o = nt * L.n_tile + n;
+                    int fkh = 0, fkw = 0;
+                    if (L.fused) {          // column = parity * cout + channel; the tap follows from the parity and the k-block's offset
+                        const int ph = o / L.cout;
+                        o %= L.cout;
+                        fkh = dec_kh(ph >> 1, L.kb[p][kb].dy);
+                        fkw = dec_kh(ph & 1, L.kb[p][kb].dx);
+                    }
                     for (int j = 0; j < width; j++) {
-                        const KElem e = L.kelem[p][L.ke_off[p][kb] + j];
+                        KElem e = L.kelem[p][L.ke_off[p][kb] + j];
+                        if (L.fused) {
+                            if (fkh < 0 || fkw < 0) e.cin = -1;
+                            e.kh = (int8_t)fkh; e.kw = (int8_t)fkw;
+                        }
                         float v = 0.0f;
                         if (e.cin >= 0) {
                             const size_t idx = L.transposed
@@ -323,12 +366,6 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
 // ------------------------------------------------------------------------------------------
 bool row_plan_supported(int layer_index) { return layer_index == 0 || layer_index == 1 || layer_index == 8 || layer_index == 9; }
 
-// transposed conv: which kernel row serves output parity `par` at input offset d (o = 2h + kh - 1); -1 = none
-static int dec_kh(int par, int d)
-{
-    if (par == 0) return d == 0 ? 1 : (d == -1 ? 3 : -1);
-    return d == 1 ? 0 : (d == 0 ? 2 : 4);
-}
 
 RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp)
 {

@@ -77,6 +77,11 @@ struct LayerPlan {
     // space-to-depth tensor's twin; decoder layers: ONE tensor holding [skip residual | up residual] per pixel
     bool comp;
     SrcDesc lo_src;
+    // decoder layers with 4 * cout <= 256: the four output parities fused into N = 4 * cout (column = phase * cout + channel), ONE
+    // k-block list over all 3 x 3 input offsets (a parity that does not use an offset gets zero weights).  An activation tile is then
+    // fetched once per offset instead of once per (parity, tap): 9 instead of 25 fetches, each feeding a 4x wider MMA - the
+    // phase-separated form of up3 (N = 64) took in 24 KB per 4 small MMAs and was bound by the SM's L2 intake at 40 % tensor use.
+    bool fused;
     // weights blob: [phase][n_tile_idx][kb][n_tile*32 floats], pre-swizzled (see pack_layer)
     size_t w_floats_per_stem;
     size_t w_phase_off[4];              // float offset of each phase inside the per-stem blob
@@ -104,7 +109,10 @@ CoeffLayout coeff_layout();
 // epilogue (as always), which also stores the residual a - tf32(a) as bf16; the layer then contracts tf32(a) with w (kind::tf32)
 // AND the residual with bf16(w) (kind::f16, 64 channels per 128-byte row, i.e. half the MMAs and half the bytes of the main
 // term).  Operand error drops from 2^-12 to ~2^-19 relative: fp32-grade results for 1.5x the tensor work.
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false, int n_stems = 1, int min_ctas = 0, unsigned comp_mask = 0);
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false, int n_stems = 1, int min_ctas = 0, unsigned comp_mask = 0,
+                                   bool fuse_phases = true);
+// transposed conv: the kernel row that serves output parity `par` at input offset d (o = 2h + kh - 1), or -1
+int dec_kh(int par, int d);
 
 // Pack one stem's weights for a layer into the k-block-major, 128B-swizzled layout the MMA
 // B operand is read from.  `coeff` is one spleeterCoeff blob.  Values are rounded to TF32

@@ -273,6 +273,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     return r;
 }
 
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2, two IEEE fp32 operations per lane and issue slot; each half rounds exactly
+// like the scalar instruction).  A pair built from one scalar twice compiles to a broadcast operand (R.F32), not to moves.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;\n" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 __device__ __forceinline__ float rna_tf32(float x)
 {
     uint32_t r;

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
                 for (int i = 0; i < 16; i++) acc[i] = fmaf(av, wb[swz128_index(c0 + i, j)], acc[i]);
             }
         }
-        if (valid) epilogue16(p, s, n, Y, X, phase, nt * p.n_tile + c0, acc);
+        const int col = nt * p.n_tile + c0;
+        if (valid) epilogue16(p, s, n, Y, X, p.fused ? col / p.cout : phase, p.fused ? col % p.cout : col, acc);
     }
 }
 
@@ -315,11 +316,14 @@ __global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Par
             *reinterpret_cast<float4*>(tile + r * U7_PITCH + 4 * c4) = v;
         }
         __syncthreads();
-        float acc[2][4][2];
+        // (mask L, mask R) of a pixel accumulate as one packed pair: acc += (w_L, w_R) * (x, x) is ONE FFMA2 (the weight pairs sit in
+        // uniform registers, x is a broadcast operand), 16 instead of 32 FMA issue slots per pixel; each half rounds like the scalar
+        // FFMA, so the result is bit-identical to the scalar loop
+        unsigned long long acc[2][4];
 #pragma unroll
         for (int a = 0; a < 2; a++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[a][j][0] = acc[a][j][1] = 0.0f;
+            for (int j = 0; j < 4; j++) acc[a][j] = 0ull;
 #pragma unroll
         for (int q = 0; q < 5; q++) {
             // tile row r0 + 2q = input row of output row r0 for kh = q and of output row r0 + 2 for kh = q - 1
@@ -331,14 +335,9 @@ __global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Par
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const float x = v[1 + j + 2 * kw];   // input column f + 2 kw - 3
-                    if (q < 4) {
-                        acc[0][j][0] = fmaf(wk[q * 4 + kw], x, acc[0][j][0]);
-                        acc[0][j][1] = fmaf(wk[16 + q * 4 + kw], x, acc[0][j][1]);
-                    }
-                    if (q >= 1) {
-                        acc[1][j][0] = fmaf(wk[(q - 1) * 4 + kw], x, acc[1][j][0]);
-                        acc[1][j][1] = fmaf(wk[16 + (q - 1) * 4 + kw], x, acc[1][j][1]);
-                    }
+                    const unsigned long long xx = ptx::pack_f32x2(x, x);
+                    if (q < 4) acc[0][j] = ptx::fma_f32x2(ptx::pack_f32x2(wk[q * 4 + kw], wk[16 + q * 4 + kw]), xx, acc[0][j]);
+                    if (q >= 1) acc[1][j] = ptx::fma_f32x2(ptx::pack_f32x2(wk[(q - 1) * 4 + kw], wk[16 + (q - 1) * 4 + kw]), xx, acc[1][j]);
                 }
         }
         const int f = f0 + fx;
@@ -349,7 +348,8 @@ __global__ void __launch_bounds__(256) up7_kernel(const __grid_constant__ Up7Par
                 float m[8];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float a0 = acc[a][j][0] + wk[32], a1 = acc[a][j][1] + wk[33];
+                    const float2 av = ptx::unpack_f32x2(acc[a][j]);
+                    const float a0 = av.x + wk[32], a1 = av.y + wk[33];
                     if (p.lut) { m[2 * j] = sigmoid_lut(lut_s, a0); m[2 * j + 1] = sigmoid_lut(lut_s, a1); }
                     else { m[2 * j] = sigmoid_exact(a0); m[2 * j + 1] = sigmoid_exact(a1); }
                 }

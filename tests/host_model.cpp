@@ -16,6 +16,8 @@ extern "C" void srt_host_model_set_split(int on) { g_split = on != 0; }
 static bool g_comp = false;    // compensated precision: sources rounded to TF32 + bf16 residual tensors contracted by extra k-blocks
 static bool g_comp_drop = false;   // (control experiment) sources rounded, compensation blocks ignored
 extern "C" void srt_host_model_set_comp(int on) { g_comp = on != 0; g_comp_drop = on == 2; }
+static bool g_fuse = true;     // decoder layers with 4 * cout <= 256 fuse their four output parities into N (the product's default)
+extern "C" void srt_host_model_set_fuse(int on) { g_fuse = on != 0; }
 static int g_min_ctas = 0;      // build_plans(min_ctas): narrower N tiles for small grids (what a small-batch context uses)
 extern "C" void srt_host_model_set_min_ctas(int v) { g_min_ctas = v; }
 
@@ -58,7 +60,7 @@ static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const 
 extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
                                     float* out, int want_act)
 {
-    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split, 1, g_min_ctas, g_comp ? 0x3ffu : 0u);
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split, 1, g_min_ctas, g_comp ? 0x3ffu : 0u, g_fuse);
     if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
     const LayerPlan& L = plans[plan_index];
     if (L.comp != g_comp) return -5;
@@ -132,11 +134,13 @@ extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* c
                             }
                         }
                         for (int n = 0; n < L.n_tile; n++) {
-                            const int o = nt * L.n_tile + n;
+                            int o = nt * L.n_tile + n;
+                            int phase = ph;
+                            if (L.fused) { phase = o / L.cout; o %= L.cout; }      // column = parity * cout + channel
                             float v = acc[n] + bias[o];
                             if (L.transposed) {
                                 v = bn[L.cout + o] * act_apply(act, v) + bn[o];
-                                const int oy = 2 * Y + (ph >> 1), ox = 2 * X + (ph & 1);
+                                const int oy = 2 * Y + (phase >> 1), ox = 2 * X + (phase & 1);
                                 out[((size_t)o * Hout + oy) * Wout + ox] = v;
                             } else {
                                 if (want_act && has_bn) v = act_apply(act, bn[L.cout + o] * v + bn[o]);
@@ -150,7 +154,7 @@ extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* c
 
 extern "C" int srt_host_model_plan_info(int T, int F, int n_img, int plan_index, int* info /* tw,th,nb,n_tile,n_tiles,phases,nkb0..3 */)
 {
-    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, n_img, false, 1, g_min_ctas);
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, n_img, false, 1, g_min_ctas, 0u, g_fuse);
     if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
     const LayerPlan& L = plans[plan_index];
     info[0] = L.tw; info[1] = L.th; info[2] = L.nb; info[3] = L.n_tile; info[4] = L.n_tiles; info[5] = L.phases;

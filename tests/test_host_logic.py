@@ -53,15 +53,19 @@ def test_gather_gemm_model_matches_oracle(oracle, host_model, small_nets, T, F, 
             got = _run_layer(host_model, T, F, i - 1, coeff, a_enc, act_in, None, ref.shape, row=row)
             err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
             assert err < 2e-5, f"down{i+1} (row-patch={row}): rel err {err}"
-    # decoder up1..up5
+    # decoder up1..up5: the generic form with fused parities where 4 * cout <= 256 (up3..up5) and phase-separated, and the row-patch form
     for d in range(5):
         s0 = taps["skip6"] if d == 0 else taps[f"skip{6-d}"]
         s1 = None if d == 0 else taps[f"up{d}"]
         ref = taps[f"up{d+1}"]
-        for row in ([False, True] if 5 + d in (8, 9) else [False]):
-            got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, s0, s1, ref.shape, row=row)
+        for row, fuse in ([(False, 1), (False, 0), (True, 1)] if 5 + d in (8, 9) else [(False, 1), (False, 0)]):
+            host_model.srt_host_model_set_fuse(fuse)
+            try:
+                got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, s0, s1, ref.shape, row=row)
+            finally:
+                host_model.srt_host_model_set_fuse(1)
             err = np.abs(got - ref).max() / max(1e-6, np.abs(ref).max())
-            assert err < 2e-5, f"up{d+1} (row-patch={row}): rel err {err}"
+            assert err < 2e-5, f"up{d+1} (row-patch={row}, fused={fuse}): rel err {err}"
 
 
 def test_down1_tensor_core_plan(oracle, host_model, small_nets):
@@ -148,12 +152,21 @@ def test_compensated_precision_tables(oracle, host_model, small_nets, mode):
 def test_plan_shapes(host_model):
     info = (C.c_int * 10)()
     # shape A (T=512, F=1024), batch 32: tiles are full and the k-block counts match the design
-    expect_nkb = {0: [15], 1: [25], 2: [50], 3: [100], 4: [200], 5: [64, 96, 96, 144], 9: [8, 12, 12, 18]}
+    # up3 / up5 (4 * cout <= 256) fuse their four output parities: one list over the 3 x 3 input offsets x sources x 32-channel slabs
+    expect_nkb = {0: [15], 1: [25], 2: [50], 3: [100], 4: [200], 5: [64, 96, 96, 144], 6: [64, 96, 96, 144], 7: [72], 9: [18]}
     for idx, nkb in expect_nkb.items():
         assert host_model.srt_host_model_plan_info(512, 1024, 32, idx, info) == 0
         tw, th, nb, n_tile, n_tiles, phases = info[0:6]
         assert tw * th * nb == 128 and n_tile * n_tiles in (32, 64, 128, 256, 512, 16)
         assert list(info[6:6 + phases]) == nkb
+    assert host_model.srt_host_model_plan_info(512, 1024, 32, 7, info) == 0 and info[3] == 256 and info[5] == 1     # up3: N = 4 x 64
+    host_model.srt_host_model_set_fuse(0)
+    try:
+        for idx, nkb in {7: [32, 48, 48, 72], 9: [8, 12, 12, 18]}.items():
+            assert host_model.srt_host_model_plan_info(512, 1024, 32, idx, info) == 0
+            assert info[5] == 4 and list(info[6:10]) == nkb
+    finally:
+        host_model.srt_host_model_set_fuse(1)
     # tiny deep layers batch images into the tile
     host_model.srt_host_model_plan_info(64, 64, 32, 4, info)
     assert info[0] * info[1] == 1 and info[2] == 32 or info[0] * info[1] * info[2] == 128
@@ -363,8 +376,10 @@ def test_narrow_n_tiles_for_small_grids(oracle, host_model, small_nets):
         assert (info[3], info[4]) == (64, 4)
         host_model.srt_host_model_plan_info(512, 1024, 32, 4, info)      # 32 images: 32 x 2 = 64 CTAs < 148 -> 128-wide tiles
         assert info[3] * info[4] == 512 and info[3] >= 64
-        host_model.srt_host_model_plan_info(512, 1024, 32, 9, info)      # up5 at full batch: untouched
-        assert (info[3], info[4]) == (16, 1)
+        host_model.srt_host_model_plan_info(512, 1024, 32, 9, info)      # up5 at full batch: untouched (N = 4 x 16: parities fused)
+        assert (info[3], info[4], info[5]) == (64, 1, 1)
+        host_model.srt_host_model_plan_info(512, 1024, 1, 7, info)       # up3, one image: 16 fused CTAs would not fill the SMs -> 4 phases
+        assert info[5] == 4 and info[3] == 64
         T, F = 64, 128
         coeff = small_nets[0][0]
         x = (np.abs(np.random.default_rng(5).standard_normal((2, T, F))) * 3).astype(np.float32)
