@@ -169,27 +169,29 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
                         const uint32_t b_lo = ptx::umma_desc_lo(wring_base + (uint32_t)ws * kWBytes);
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
-                        if (p.dbg & 2) {}
-                        else if (KB == 32 && (kb.part & kPartLo)) {
-                            // compensation block: the patch holds 64 bf16 residuals per pixel in the same 128-byte rows; 4 x K = 16
+                        // K step outer, row inner: consecutive MMAs hit different accumulators (dependent MMAs on one accumulator cost
+                        // ~100 cycles each, independent ones ~45-60: tools/mma_probe.cu).  K steps whose weights are all zero (an
+                        // encoder slab spanning pixel parities the tap does not touch, kPartSkipShift) are not issued.  A compensation
+                        // block holds 64 bf16 residuals per pixel in the same 128-byte rows: 4 x K = 16, kind::f16.
+                        const int skip = KB == 32 ? kb_skip_mask(kb) : 0;
+                        const bool lo = KB == 32 && (kb.part & kPartLo);
+                        if (!(p.dbg & 2)) {
 #pragma unroll
-                            for (int kk = 0; kk < 4; kk++) {
+                            for (int kk = 0; kk < KB / 8; kk++) {
+                                if (skip & (1 << kk)) continue;
+                                const uint32_t accum = first ? 0u : 1u;
+                                first = false;
 #pragma unroll
-                                for (int r = 0; r < R; r++)
-                                    ptx::mma_bf16_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2),
-                                                        idesc_lo, (kk != 0) ? 1u : (first ? 0u : 1u), kDescHi);
+                                for (int r = 0; r < R; r++) {
+                                    if (lo)
+                                        ptx::mma_bf16_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2), idesc_lo,
+                                                            accum, kDescHi);
+                                    else
+                                        ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2), idesc,
+                                                            accum, kDescHi);
+                                }
                             }
-                        } else
-                        // K step outer, row inner: consecutive MMAs hit different accumulators (dependent MMAs on one
-                        // accumulator cost ~100 cycles each, independent ones ~60: tools/mma_probe.cu)
-#pragma unroll
-                        for (int kk = 0; kk < KB / 8; kk++) {
-#pragma unroll
-                            for (int r = 0; r < R; r++)
-                                ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2),
-                                                    idesc, (kk != 0) ? 1u : (first ? 0u : 1u), kDescHi);
                         }
-                        first = false;
                         ptx::mma_commit(&hdr->w_empty[ws]);
                         if (++ws == WS) { ws = 0; wph ^= 1; }
                     }

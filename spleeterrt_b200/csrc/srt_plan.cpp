@@ -472,6 +472,20 @@ RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp
         }
     }
     L.ke_off = kelem_offsets(L.kb);
+    // K steps without any weight (see kPartSkipShift): quarter q of k-block k = elements [q * width / 4, (q + 1) * width / 4)
+    for (size_t k = 0; k < L.kb.size(); k++) {
+        const int width = kb_channels(L.kb[k]), per = width / 4;
+        int skip = 0;
+        for (int q = 0; q < 4; q++) {
+            bool any = false;
+            for (int j = q * per; j < (q + 1) * per; j++) {
+                const KElemP& e = L.kelem[L.ke_off[k] + j];
+                for (int ph = 0; ph < 4; ph++) any = any || (e.cin >= 0 && e.kh[ph] >= 0);
+            }
+            if (!any) skip |= 1 << q;
+        }
+        if (skip != 0xf) L.kb[k].part = (int8_t)((L.kb[k].part & 0xf) | (skip << kPartSkipShift));
+    }
     L.R = row_plan_R(L.N);
     L.w_floats_per_stem = L.kb.size() * (size_t)L.N * kKB;
     return L;

@@ -44,6 +44,11 @@ struct KBlock {
     int32_t c_off;   // channel coordinate in the source tensor (multiple of 32, or of 16 for paired taps; of 64 for compensation blocks)
 };
 constexpr int kPartLo = 2;
+// bits 4-7 of KBlock::part (row-patch plans): K steps of the k-block (quarters of its 128-byte rows) whose weights are all zero -
+// an encoder slab that spans several pixel parities carries a tap only in the parities that match the tap's offset - and that
+// the MMA issuer therefore skips (down2: 75 of 96 K steps per row are left)
+constexpr int kPartSkipShift = 4;
+SRT_HD inline int kb_skip_mask(const KBlock& kb) { return ((unsigned char)kb.part >> kPartSkipShift) & 0xf; }
 constexpr int kSrcLo = 2;               // KBlock::src / RowChunk::src of the residual tensor
 SRT_HD inline int kb_channels(const KBlock& kb) { return (kb.part & kPartLo) ? kKBlo : kKB; }
 
@@ -124,7 +129,7 @@ float round_tf32(float x);
 uint16_t bf16_rn(float x);              // round to nearest even (cvt.rn.bf16.f32)
 float bf16_to_float(uint16_t h);
 // value stored for a weight in a k-block of the given part
-inline float weight_part(float w, int part) { const float hi = round_tf32(w); return part == 0 ? hi : round_tf32(w - hi); }
+inline float weight_part(float w, int part) { const float hi = round_tf32(w); return (part & 1) == 0 ? hi : round_tf32(w - hi); }   // bit 0 of KBlock::part
 bool weights_tf32_exact(const float* coeff);   // all tensor-core conv weights of one net representable in TF32?
 
 // ---------------------------------------------------------------------------------------

@@ -197,6 +197,19 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
     const float* bias = coeff + (L.transposed ? cl.up_b[L.index - 5] : cl.down_b[L.index + 1]);
     const float* bn = coeff + (L.transposed ? cl.up_bn[L.index - 5] : cl.down_bn[L.index + 1]);
     const int Hout = L.transposed ? 2 * H : H, Wout = L.transposed ? 2 * W : W;
+    // K steps the MMA issuer skips (kPartSkipShift) must hold nothing but zero weights, and the model below honours the mask
+    for (size_t k = 0; k < L.kb.size(); k++) {
+        const int width = kb_channels(L.kb[k]), per = width / 4, skip = kb_skip_mask(L.kb[k]);
+        const bool lo16 = (L.kb[k].part & kPartLo) != 0;
+        for (int q = 0; q < 4; q++)
+            if (skip & (1 << q))
+                for (int n = 0; n < L.N; n++)
+                    for (int j = q * per; j < (q + 1) * per; j++) {
+                        const float* wb = &wpk[k * (size_t)L.N * kKB];
+                        const float v = lo16 ? bf16_to_float(reinterpret_cast<const uint16_t*>(wb)[swz128_index16(n, j)]) : wb[swz128_index(n, j)];
+                        if (v != 0.0f) return -6;
+                    }
+    }
     std::vector<float> acc(L.N);
     // CTA tiles: R rows x 128 columns; the patch is rows y0-1 .. y0+R, columns x0-1 .. x0+134
     for (int y0 = 0; y0 < H; y0 += L.R)
@@ -222,7 +235,8 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                                 const uint16_t* wh = reinterpret_cast<const uint16_t*>(wb);
                                 for (int n = 0; n < L.N; n++) {
                                     float s = 0.f;
-                                    for (int j = 0; j < kKBlo; j++) s += bf16_to_float(a[j]) * bf16_to_float(wh[swz128_index16(n, j)]);
+                                    for (int j = 0; j < kKBlo; j++)
+                                        if (!(kb_skip_mask(kb) & (1 << (j / 16)))) s += bf16_to_float(a[j]) * bf16_to_float(wh[swz128_index16(n, j)]);
                                     acc[n] += s;
                                 }
                                 continue;
@@ -232,7 +246,8 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                             const float* a = &src[kb.src][((size_t)yy * W + xx) * C + kb.c_off];
                             for (int n = 0; n < L.N; n++) {
                                 float s = 0.f;
-                                for (int j = 0; j < kKB; j++) s += a[j] * wb[swz128_index(n, j)];
+                                for (int j = 0; j < kKB; j++)
+                                    if (!(kb_skip_mask(kb) & (1 << (j / 8)))) s += a[j] * wb[swz128_index(n, j)];
                                 acc[n] += s;
                             }
                         }
