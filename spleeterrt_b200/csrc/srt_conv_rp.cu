@@ -59,6 +59,46 @@ __device__ __forceinline__ RpTile rp_tile(const RowConvParams& p, int t, int R)
     return o;
 }
 
+// The MMAs of one k-block, straight-line: K step outer, row inner, so consecutive MMAs hit different accumulators (dependent MMAs on
+// one accumulator cost ~100 cycles each, independent ones ~45-60: tools/mma_probe.cu).  The issuing thread is bound by instruction
+// latency (~43 cycles per small-N MMA), so what is issued is decided at compile time: LO = compensation block (64 bf16 residuals per
+// pixel in the same 128-byte rows: K = 16 per step, kind::f16), SKIP = K steps whose weights are all zero (kPartSkipShift).
+// Returns with `first` cleared once something was issued.
+template <int N, int R, int KSTEPS, bool LO, int SKIP>
+__device__ __forceinline__ void rp_issue(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t row_pitch16, uint32_t idesc, uint32_t desc_hi, bool& first)
+{
+    bool fresh = first;
+#pragma unroll
+    for (int kk = 0; kk < KSTEPS; kk++) {
+        if (SKIP & (1 << kk)) continue;
+        const uint32_t accum = fresh ? 0u : 1u;
+        fresh = false;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (LO) ptx::mma_bf16_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)r * row_pitch16 + (uint32_t)(kk * 2), b_lo + (uint32_t)(kk * 2), idesc, accum, desc_hi);
+            else ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)r * row_pitch16 + (uint32_t)(kk * 2), b_lo + (uint32_t)(kk * 2), idesc, accum, desc_hi);
+        }
+    }
+    first = fresh;
+}
+template <int N, int R, int KSTEPS, bool LO>
+__device__ __forceinline__ void rp_issue_masked(int skip, uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t row_pitch16, uint32_t idesc, uint32_t desc_hi,
+                                                bool& first)
+{
+    switch (skip) {   // the masks the plans produce: a slab spanning both column parities loses its first or second half, or three quarters
+    case 0x0: rp_issue<N, R, KSTEPS, LO, 0x0>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0x3: rp_issue<N, R, KSTEPS, LO, 0x3>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0xc: rp_issue<N, R, KSTEPS, LO, 0xc>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0x5: rp_issue<N, R, KSTEPS, LO, 0x5>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0xa: rp_issue<N, R, KSTEPS, LO, 0xa>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0x7: rp_issue<N, R, KSTEPS, LO, 0x7>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0xb: rp_issue<N, R, KSTEPS, LO, 0xb>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0xd: rp_issue<N, R, KSTEPS, LO, 0xd>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    case 0xe: rp_issue<N, R, KSTEPS, LO, 0xe>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;
+    default:  rp_issue<N, R, KSTEPS, LO, 0x0>(acc, a_lo, b_lo, row_pitch16, idesc, desc_hi, first); break;   // any other mask: issue everything (zeros are harmless)
+    }
+}
+
 template <int N, int R, int WS, int KB, int EPW>
 __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid_constant__ RowConvParams p)
 {
@@ -169,28 +209,13 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
                         const uint32_t b_lo = ptx::umma_desc_lo(wring_base + (uint32_t)ws * kWBytes);
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
-                        // K step outer, row inner: consecutive MMAs hit different accumulators (dependent MMAs on one accumulator cost
-                        // ~100 cycles each, independent ones ~45-60: tools/mma_probe.cu).  K steps whose weights are all zero (an
-                        // encoder slab spanning pixel parities the tap does not touch, kPartSkipShift) are not issued.  A compensation
-                        // block holds 64 bf16 residuals per pixel in the same 128-byte rows: 4 x K = 16, kind::f16.
-                        const int skip = KB == 32 ? kb_skip_mask(kb) : 0;
-                        const bool lo = KB == 32 && (kb.part & kPartLo);
                         if (!(p.dbg & 2)) {
-#pragma unroll
-                            for (int kk = 0; kk < KB / 8; kk++) {
-                                if (skip & (1 << kk)) continue;
-                                const uint32_t accum = first ? 0u : 1u;
-                                first = false;
-#pragma unroll
-                                for (int r = 0; r < R; r++) {
-                                    if (lo)
-                                        ptx::mma_bf16_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2), idesc_lo,
-                                                            accum, kDescHi);
-                                    else
-                                        ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)(r * (kRowPitch >> 4) + kk * 2), b_lo + (uint32_t)(kk * 2), idesc,
-                                                            accum, kDescHi);
-                                }
-                            }
+                            if (KB == 32 && (kb.part & kPartLo))
+                                rp_issue_masked<N, R, 4, true>(kb_skip_mask(kb), acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                            else if (KB == 32)
+                                rp_issue_masked<N, R, 4, false>(kb_skip_mask(kb), acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                            else
+                                rp_issue<N, R, KB / 8, false, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
                         }
                         ptx::mma_commit(&hdr->w_empty[ws]);
                         if (++ws == WS) { ws = 0; wph ^= 1; }
