@@ -210,12 +210,15 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
                         if (!(p.dbg & 2)) {
-                            if (KB == 32 && (kb.part & kPartLo))
-                                rp_issue_masked<N, R, 4, true>(kb_skip_mask(kb), acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
-                            else if (KB == 32)
-                                rp_issue_masked<N, R, 4, false>(kb_skip_mask(kb), acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                            const int skip = KB == 32 ? kb_skip_mask(kb) : 0;
+                            const bool lo = KB == 32 && (kb.part & kPartLo);
+                            if (skip == 0 && !(p.dbg & 256)) {           // the common case without a jump table in the issuing thread's path
+                                if (lo) rp_issue<N, R, KB / 8, true, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                                else rp_issue<N, R, KB / 8, false, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                            } else if (lo)
+                                rp_issue_masked<N, R, KB / 8, true>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
                             else
-                                rp_issue<N, R, KB / 8, false, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                                rp_issue_masked<N, R, KB / 8, false>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
                         }
                         ptx::mma_commit(&hdr->w_empty[ws]);
                         if (++ws == WS) { ws = 0; wph ^= 1; }
