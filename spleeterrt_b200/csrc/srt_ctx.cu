@@ -1315,15 +1315,17 @@ static int batch_enqueue(srt_ctx* c, int slot, const float* const* pcmL, const f
         off += np;
     }
     // Groups shorten the latency of a lone call (the first download starts after 1/groups of the kernels) but
-    // cost batch efficiency; once other batches are in flight the overlap comes from them, so the batch goes
-    // through whole (r1 tools/e2e_probe.py: blocking 18.4 / 14.1 / 12.5 ms and pipelined 9.6 / 9.6 / 10.3 ms per
-    // 32-stream step for 1 / 2 / 4 groups).
+    // cost batch efficiency.  Once other batches are in flight most of the overlap comes from them; two groups still
+    // pay there when a step's kernels take about as long as its download (compensated precision: 8.3 ms of kernels
+    // against 7.9-8.7 ms of D2H): the copy engine then always has half a batch queued and never waits for the end of
+    // a whole step.  Measured per 32-stream step (r2, ceiling 57 GB/s = 7.9 ms): blocking 17.9 / 13.4 / 11.6 ms and
+    // pipelined 9.3-9.6 / 9.0 / 9.4 ms for 1 / 2 / 4 groups.
     bool others_in_flight = false;
     for (int i = 0; i < kBatchSlots; i++)
         if (i != slot && c->slot_busy[i] && cudaEventQuery(c->ev_d2h[i]) == cudaErrorNotReady) others_in_flight = true;
     (void)cudaGetLastError();   // cudaErrorNotReady is not sticky, but keep the error state clean
     const char* ge = getenv("SRT_E2E_GROUPS");
-    int groups = ge ? atoi(ge) : (others_in_flight ? 1 : 4);
+    int groups = ge ? atoi(ge) : (others_in_flight ? 2 : 4);
     groups = std::max(1, std::min(std::min(groups, 8), n_streams));
     const int per = (n_streams + groups - 1) / groups;
     CK(cudaStreamWaitEvent(c->s_in, c->ev_cdone[slot], 0));     // no-op until the slot has been used once
