@@ -276,8 +276,9 @@ def main():
     ap.add_argument("--stems", type=int, default=4, help="nets per stream (4 = the metric's configuration; 5 = BASELINE.json config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-objects (other configs, probes, sustained run)")
-    ap.add_argument("--precision", default="compensated", choices=["compensated", "tf32"],
-                    help="srt_config.precision: compensated = TF32 main term + bf16 residual term (default, fp32-grade), tf32 = single pass")
+    ap.add_argument("--precision", default="compensated", choices=["compensated", "compensated_bf16", "tf32"],
+                    help="srt_config.precision: compensated = TF32 main term + residual term in e5m2 (bf16 in two layers), the default; "
+                         "compensated_bf16 = all residuals in bf16; tf32 = single pass")
     ap.add_argument("--dispatch", default="none", choices=["none", "nccl", "peer", "both"],
                     help="rank 0 holds the PCM of ALL streams in its HBM (include/srt_dispatch.h).  nccl: grouped ncclSend / ncclRecv scatter and "
                          "gather; peer: every rank's kernels load / store rank 0's memory over NVLink (CUDA IPC), no copies; both: time both")
@@ -560,12 +561,14 @@ def main():
             peak_src = ("srt_probe_tensor_peak: every SM issuing N=256 kind::tf32 MMAs from shared memory for 0.15 s right after the timed region "
                         f"(kind::f16/bf16: {bf16_peak:.0f} TF/s; {pk['source']} cuBLAS bf16 burst {pk['bf16_tflops']} / sustained {pk['bf16_tflops_sustained']})")
         hbm_peak = pk["hbm_gbs"]
-        comp = args.precision == "compensated"
+        comp = args.precision != "tf32"
         tc_flop = W.FLOP_PER_PIXEL_TC * P * units
         tc_ms = sum(layer_ms[k] for k in W.LAYER_FLOP_PER_PIXEL)
         ach = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         # executed tensor work: the compensation term repeats every layer's contraction on bf16 operands (half the MMAs, bf16 rate)
-        t_at_peak = tc_flop / (tf32_peak * 1e12) + (tc_flop / ((bf16_peak or 2 * tf32_peak) * 1e12) if comp else 0.0)
+        # (the e5m2 blocks of the default mode run at twice the bf16 rate: their layers hold 79 % of the FLOPs)
+        lo_rate = (bf16_peak or 2 * tf32_peak) * (1.0 if args.precision == "compensated_bf16" else 1.0 / (0.21 + 0.79 / 2))
+        t_at_peak = tc_flop / (tf32_peak * 1e12) + (tc_flop / (lo_rate * 1e12) if comp else 0.0)
         traffic, traffic_src, dram = None, None, {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
@@ -595,13 +598,14 @@ def main():
             "metric": f"realtime_factor_{S}stem_44k1_stereo", "value": audio_s / (ms_step * 1e-3), "unit": "x_realtime",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32+bf16" if comp else "tf32", "data": "synthetic",
+            "dtype": {"compensated": "tf32+e5m2/bf16", "compensated_bf16": "tf32+bf16", "tf32": "tf32"}[args.precision], "data": "synthetic",
             "frames_per_sec": frames * ns * world / (ms_step * 1e-3),
             "config": {"workload": f"{S}-stem 44.1 kHz stereo, {ns} x 10 s streams per GPU per step, T=512 F=1024 (1 tile/stream), "
                                    f"STFT + {S} U-Nets + mask + iSTFT/OLA", "streams_per_gpu": ns, "time_step": T, "bin_limit": F,
                        "stems": S, "unet_tiles_per_pass": B,
-                       "precision": args.precision + (" (default: tf32(a) x w + bf16(a - tf32(a)) x bf16(w), fp32 accumulate)" if comp
-                                                      else " (single-pass TF32 operands, fp32 accumulate)"),
+                       "precision": args.precision + {"compensated": " (default: tf32(a) x w + residual (a - tf32(a)) x w in e5m2, bf16 where the residual tensor has 64 channels; fp32 accumulate)",
+                                                      "compensated_bf16": " (tf32(a) x w + bf16(a - tf32(a)) x bf16(w), fp32 accumulate)",
+                                                      "tf32": " (single-pass TF32 operands, fp32 accumulate)"}[args.precision],
                        "weights": wdesc, "l2": "per-step working set (activations, > 9 GB) >> 126 MB L2; no explicit flush",
                        "parallelism": f"streams sharded over {world} GPU(s), no data-path collective", "cpu_pinning": pin_info},
             "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "x_realtime", "ms_per_step": ms_e2e,
@@ -662,18 +666,21 @@ def main():
             line["single_stream"] = {"ms_device": ms1, "x_realtime_device": SECONDS / (ms1 * 1e-3), "ms_e2e": ms1e,
                                      "x_realtime_e2e": SECONDS / (ms1e * 1e-3), "note": f"BASELINE.json configs[1]: one 10 s stereo stream, {S} stems, batch of 1 tile"}
             sep1.close()
-            # ---- the other precision mode, same batch ----------------------------------------------------------------------------------------
-            other = "tf32" if comp else "compensated"
+            # ---- the other precision modes, same batch ---------------------------------------------------------------------------------------
             sep.close()
             sep = None
-            sep2 = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream, precision=other)
-            for _ in range(3):
-                step_device(sep2)
-            ms_other = timed_device(args.steps, sep2)
-            line["precision_modes"] = {args.precision: {"ms_per_step": ms_step, "value": audio_s / (ms_step * 1e-3)},
-                                       other: {"ms_per_step": ms_other, "value": audio_s / (ms_other * 1e-3)},
-                                       "note": "same batch, device-resident; parity of both modes: tests/test_gpu_headline.py"}
-            sep2.close()
+            modes = {args.precision: {"ms_per_step": ms_step, "value": audio_s / (ms_step * 1e-3)}}
+            for other in ("compensated", "compensated_bf16", "tf32"):
+                if other == args.precision:
+                    continue
+                sep2 = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream, precision=other)
+                for _ in range(3):
+                    step_device(sep2)
+                ms_other = timed_device(args.steps, sep2)
+                modes[other] = {"ms_per_step": ms_other, "value": audio_s / (ms_other * 1e-3)}
+                sep2.close()
+            modes["note"] = "same batch, device-resident; parity of every mode: tests/test_gpu_headline.py"
+            line["precision_modes"] = modes
             # ---- sustained: >= 5 s of back-to-back steps in the default configuration (power cap, clocks) -----------------------------------
             sep3 = srt.Separator(nets, T, F, max_images=B, max_batch_images=ns, device=local_rank, cuda_stream=stream.cuda_stream,
                                  precision=args.precision)

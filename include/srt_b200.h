@@ -53,12 +53,15 @@ typedef struct {
     int flavour;           /* 0 = Executable (LUT sigmoid, ELU clamp -15), 1 = VST (exact sigmoid) */
     int conv_impl;         /* 0 = tcgen05 tensor-core kernels (the product), 1 = SIMT verification kernels */
     void* cuda_stream;     /* optional cudaStream_t to enqueue on (NULL = context-owned stream) */
-    int precision;         /* arithmetic of the ten tensor-core layers (accumulation is fp32 in both):
-                            *   0 = SRT_PRECISION_COMPENSATED (default): activations feed the MMAs as tf32(a) PLUS the bf16
-                            *       residual a - tf32(a) (second, half-size contraction into the same accumulator):
-                            *       operand error ~2^-19, stems agree with the fp32 reference to ~1e-6 RMS at any level;
+    int precision;         /* arithmetic of the ten tensor-core layers (accumulation is fp32 in all):
+                            *   0 = SRT_PRECISION_COMPENSATED (default): activations feed the MMAs as tf32(a) PLUS the residual
+                            *       a - tf32(a) (a second, smaller contraction into the same accumulator).  The residual travels in
+                            *       8 bits (e5m2) where the layer's residual tensor has >= 128 channels per pixel and as bf16 in the
+                            *       two layers where it has 64: operand error 2^-12 -> ~2^-16, about what the tensor core's own
+                            *       accumulation adds; stems agree with the fp32 reference to a few 1e-6 RMS at any input level;
+                            *   2 = SRT_PRECISION_COMPENSATED_BF16: all residuals in bf16 (operand error ~2^-19; ~6 % slower);
                             *   1 = SRT_PRECISION_TF32: single-pass TF32 operands (2^-12): ~1.3x faster U-Net, stem error
-                            *       ~1e-4 of the stem's level (3e-5 RMS on the -12 dBFS test signal, above 1e-4 at full scale). */
+                            *       ~1e-4 of the stem's level (3e-5 RMS on the -12 dBFS test signal, 1e-4 at full scale). */
     int share_weights;     /* 1: contexts created on the same device with the same coeffs POINTERS, stem modes and configuration
                             * share one device copy of the packed weights and tables (created once, reference-counted) instead of
                             * packing and uploading per context.  The caller promises the blobs stay unchanged while any such
@@ -68,6 +71,7 @@ typedef struct {
 } srt_config;
 #define SRT_PRECISION_COMPENSATED 0
 #define SRT_PRECISION_TF32 1
+#define SRT_PRECISION_COMPENSATED_BF16 2
 
 /* coeffs[s]: one spleeterCoeff blob (SRT_COEFF_FLOATS floats, host memory) per stem;
  * stem_modes[s]: 0 = LeakyReLU(0.2)/ReLU, !=0 = ELU/ELU (spleeter.c:130-139).

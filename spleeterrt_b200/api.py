@@ -46,17 +46,19 @@ class _Config(C.Structure):
                 ("conv_impl", C.c_int), ("cuda_stream", C.c_void_p), ("precision", C.c_int), ("share_weights", C.c_int)]
 
 
-PRECISION_COMPENSATED, PRECISION_TF32 = 0, 1      # srt_config.precision (include/srt_b200.h)
+PRECISION_COMPENSATED, PRECISION_TF32, PRECISION_COMPENSATED_BF16 = 0, 1, 2      # srt_config.precision (include/srt_b200.h)
 
 
 def _precision(p):
     if p is None:
         return PRECISION_COMPENSATED
-    if p in ("compensated", "tf32+bf16", PRECISION_COMPENSATED):
+    if p in ("compensated", PRECISION_COMPENSATED):
         return PRECISION_COMPENSATED
-    if p in ("tf32", PRECISION_TF32):
+    if p in ("tf32", PRECISION_TF32) and p is not True:
         return PRECISION_TF32
-    raise SrtError(f"unknown precision {p!r} (compensated | tf32)")
+    if p in ("compensated_bf16", "tf32+bf16", PRECISION_COMPENSATED_BF16):
+        return PRECISION_COMPENSATED_BF16
+    raise SrtError(f"unknown precision {p!r} (compensated | compensated_bf16 | tf32)")
 
 
 def lib_path():

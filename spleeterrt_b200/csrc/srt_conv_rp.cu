@@ -64,7 +64,7 @@ __device__ __forceinline__ RpTile rp_tile(const RowConvParams& p, int t, int R)
 // latency (~43 cycles per small-N MMA), so what is issued is decided at compile time: LO = compensation block (64 bf16 residuals per
 // pixel in the same 128-byte rows: K = 16 per step, kind::f16), SKIP = K steps whose weights are all zero (kPartSkipShift).
 // Returns with `first` cleared once something was issued.
-template <int N, int R, int KSTEPS, bool LO, int SKIP>
+template <int N, int R, int KSTEPS, int LO, int SKIP>   // LO: 0 = TF32 main term, 1 = bf16 residuals, 2 = e5m2 residuals
 __device__ __forceinline__ void rp_issue(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t row_pitch16, uint32_t idesc, uint32_t desc_hi, bool& first)
 {
     bool fresh = first;
@@ -75,13 +75,14 @@ __device__ __forceinline__ void rp_issue(uint32_t acc, uint32_t a_lo, uint32_t b
         fresh = false;
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            if (LO) ptx::mma_bf16_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)r * row_pitch16 + (uint32_t)(kk * 2), b_lo + (uint32_t)(kk * 2), idesc, accum, desc_hi);
+            if (LO == 2) ptx::mma_f8_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)r * row_pitch16 + (uint32_t)(kk * 2), b_lo + (uint32_t)(kk * 2), idesc, accum, desc_hi);
+            else if (LO == 1) ptx::mma_bf16_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)r * row_pitch16 + (uint32_t)(kk * 2), b_lo + (uint32_t)(kk * 2), idesc, accum, desc_hi);
             else ptx::mma_tf32_ss_lo(acc + (uint32_t)(r * N), a_lo + (uint32_t)r * row_pitch16 + (uint32_t)(kk * 2), b_lo + (uint32_t)(kk * 2), idesc, accum, desc_hi);
         }
     }
     first = fresh;
 }
-template <int N, int R, int KSTEPS, bool LO>
+template <int N, int R, int KSTEPS, int LO>
 __device__ __forceinline__ void rp_issue_masked(int skip, uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t row_pitch16, uint32_t idesc, uint32_t desc_hi,
                                                 bool& first)
 {
@@ -211,14 +212,17 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
                         ptx::tc_fence_after();
                         if (!(p.dbg & 2)) {
                             const int skip = KB == 32 ? kb_skip_mask(kb) : 0;
-                            const bool lo = KB == 32 && (kb.part & kPartLo);
+                            const bool lo = KB == 32 && (kb.part & kPartLo), lo8 = lo && (kb.part & kPartLo8);
                             if (skip == 0 && !(p.dbg & 256)) {           // the common case without a jump table in the issuing thread's path
-                                if (lo) rp_issue<N, R, KB / 8, true, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
-                                else rp_issue<N, R, KB / 8, false, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
-                            } else if (lo)
-                                rp_issue_masked<N, R, KB / 8, true>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                                if (lo8) rp_issue<N, R, KB / 8, 2, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                                else if (lo) rp_issue<N, R, KB / 8, 1, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                                else rp_issue<N, R, KB / 8, 0, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                            } else if (lo8)
+                                rp_issue_masked<N, R, KB / 8, 2>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                            else if (lo)
+                                rp_issue_masked<N, R, KB / 8, 1>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
                             else
-                                rp_issue_masked<N, R, KB / 8, false>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                                rp_issue_masked<N, R, KB / 8, 0>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
                         }
                         ptx::mma_commit(&hdr->w_empty[ws]);
                         if (++ws == WS) { ws = 0; wph ^= 1; }

@@ -132,12 +132,19 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
             int stage = 0;
             uint32_t ph = 0;
             for (int k = 0; k < nkb; k++) {
-                const bool comp = (hdr->kb[k].part & kPartLo) != 0;   // compensation block: bf16 operands, 4 x K = 16 over the same 128-byte rows
+                const int part = hdr->kb[k].part;
+                const bool comp = (part & kPartLo) != 0;   // compensation block: bf16 (4 x K = 16) or e5m2 (4 x K = 32) operands over the same 128-byte rows
                 ptx::mbar_wait(&hdr->full[stage], ph);
                 ptx::tc_fence_after();
                 const uint32_t a_lo = ptx::umma_desc_lo(tiles_base + (uint32_t)stage * kStageBytes);
                 const uint32_t b_lo = a_lo + ((MT * kABytes) >> 4);
-                if (comp) {
+                if (comp && (part & kPartLo8)) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                        for (int m = 0; m < MT; m++)
+                            ptx::mma_f8_ss_lo(tmem_d + m * N_TILE, a_lo + m * (kABytes >> 4) + kk * 2, b_lo + kk * 2, idesc_lo, (kk != 0) ? 1u : (k != 0 ? 1u : 0u));
+                } else if (comp) {
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++)
 #pragma unroll

@@ -83,15 +83,16 @@ static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int
 }
 
 // bf16 residual tensor [n][H][W][C] of a compensated layer -> 4-D map, box {64, tw, th, nb} = the same 128-byte swizzled rows
-static int make_tmap_lo(CUtensorMap* m, const uint16_t* base, int C, int W, int H, int N, int tw, int th, int nb)
+static int make_tmap_lo(CUtensorMap* m, const void* base, int C, int W, int H, int N, int tw, int th, int nb, bool fp8)
 {
+    const int esize = fp8 ? 1 : 2;            // e5m2 bytes, 128 channels per box row - or bf16, 64
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kKBlo, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+    cuuint64_t strides[3] = {(cuuint64_t)C * esize, (cuuint64_t)W * C * esize, (cuuint64_t)H * W * C * esize};
+    cuuint32_t box[4] = {(cuuint32_t)(fp8 ? kKBlo8 : kKBlo), (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 residual) failed (%d) C=%d W=%d H=%d N=%d box=%d,%d,%d", (int)r, C, W, H, N, tw, th, nb);
     return 0;
@@ -176,8 +177,10 @@ struct srt_ctx {
     float* U[7]{};    // U[1..5] decoder outputs (NHWC), U[6] = up6 output [n][T][F]
     // compensated precision (srt_config.precision 0): bf16 residuals v - tf32(v) of the tensors above, per consumer layer
     unsigned comp_mask = 0;        // bit i: tensor-core layer i (0..4 = down2..down6, 5..9 = up1..up5) contracts the residuals too
-    uint16_t* Alo[6]{};            // Alo[i]: residual of A[i] (same S2D layout), read by down{i+1}
-    uint16_t* Clo[5]{};            // Clo[d], d = 1..4: [skip E{6-d} | up U{d}] residuals per pixel, read by up{d+1}; Clo[0]: E6's, read by up1
+    int lo_want = LO_BF16;         // residual format asked for; layer i uses layer_lo_format(i, lo_want)
+    uint8_t* Alo[6]{};             // Alo[i]: residual of A[i] (same S2D layout), read by down{i+1}: bf16 or e5m2 bytes (the consumer's format)
+    uint8_t* Clo[5]{};             // Clo[d], d = 1..4: [skip E{6-d} | up U{d}] residuals per pixel, read by up{d+1}; Clo[0]: E6's, read by up1
+    int lo_fmt_of(int layer) const { return ((comp_mask >> layer) & 1u) ? layer_lo_format(layer, lo_want) : LO_NONE; }
     // batch buffers
     float* d_mag = nullptr;       // [NB][T/2][F/2][(py,px)][c] space-to-depth, TF32-rounded
     float4* d_spec = nullptr;     // [NB][T][2049]
@@ -390,20 +393,24 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         if ((r = dalloc(c, &c->U[d], act_floats(c, 6 - d, kDecOut[d - 1])))) return r;
     if ((r = dalloc(c, &c->U[6], act_floats(c, 0, 1)))) return r;
     // ---- precision: which tensor-core layers also contract the bf16 residuals of their inputs
-    c->comp_mask = c->cfg.precision == SRT_PRECISION_TF32 ? 0u : 0x3ffu;
-    if (const char* pe = getenv("SRT_PRECISION")) c->comp_mask = atoi(pe) == SRT_PRECISION_TF32 ? 0u : 0x3ffu;
+    int prec = c->cfg.precision;
+    if (const char* pe = getenv("SRT_PRECISION")) prec = atoi(pe);
+    if (prec != SRT_PRECISION_COMPENSATED && prec != SRT_PRECISION_TF32 && prec != SRT_PRECISION_COMPENSATED_BF16)
+        return fail(SRT_ERR_ARG, "precision %d: 0 (compensated), 1 (TF32) or 2 (compensated, bf16 residuals)", prec);
+    c->comp_mask = prec == SRT_PRECISION_TF32 ? 0u : 0x3ffu;
+    c->lo_want = prec == SRT_PRECISION_COMPENSATED ? LO_FP8 : LO_BF16;
     if (const char* me = getenv("SRT_COMP_MASK")) c->comp_mask = (unsigned)strtoul(me, nullptr, 0) & 0x3ffu;   // experiments: per-layer selection
     for (int i = 1; i <= 5; i++)
-        if ((c->comp_mask >> (i - 1)) & 1u) {
-            const size_t n = act_floats(c, i, kEnc[i]);
-            if ((r = dalloc(c, &c->Alo[i], n))) return r;
-            CK(cudaMemset(c->Alo[i], 0, n * 2));
+        if (c->lo_fmt_of(i - 1) != LO_NONE) {
+            const size_t bytes = act_floats(c, i, kEnc[i]) * (c->lo_fmt_of(i - 1) == LO_FP8 ? 1 : 2);
+            if ((r = dalloc(c, &c->Alo[i], bytes))) return r;
+            CK(cudaMemset(c->Alo[i], 0, bytes));
         }
     for (int d = 0; d <= 4; d++)
-        if ((c->comp_mask >> (5 + d)) & 1u) {
-            const size_t n = act_floats(c, 6 - d, d == 0 ? 512 : 2 * kEnc[6 - d]);
-            if ((r = dalloc(c, &c->Clo[d], n))) return r;
-            CK(cudaMemset(c->Clo[d], 0, n * 2));
+        if (c->lo_fmt_of(5 + d) != LO_NONE) {
+            const size_t bytes = act_floats(c, 6 - d, d == 0 ? 512 : 2 * kEnc[6 - d]) * (c->lo_fmt_of(5 + d) == LO_FP8 ? 1 : 2);
+            if ((r = dalloc(c, &c->Clo[d], bytes))) return r;
+            CK(cudaMemset(c->Clo[d], 0, bytes));
         }
     // ---- weights
     const CoeffLayout cl = coeff_layout();
@@ -500,7 +507,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     // small batches: narrower N tiles so that the deep layers fill the SMs (SRT_TC_NARROW=0 keeps the wide tiles)
     const char* nwe = getenv("SRT_TC_NARROW");
     const char* fze = getenv("SRT_TC_FUSE");      // "0": decoder layers stay phase-separated (A/B timing)
-    c->plans = build_plans(NetGeom{T, F}, c->B, split, S, (nwe && atoi(nwe) == 0) ? 0 : c->sm_count, c->comp_mask, !(fze && atoi(fze) == 0));
+    c->plans = build_plans(NetGeom{T, F}, c->B, split, S, (nwe && atoi(nwe) == 0) ? 0 : c->sm_count, c->comp_mask, !(fze && atoi(fze) == 0), c->lo_want);
     c->conv.resize(c->plans.size());
     for (size_t li = 0; li < c->plans.size(); li++) {
         const LayerPlan& L = c->plans[li];
@@ -568,9 +575,12 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             // residuals for compensated consumers: the raw skip E{i+1} is read by up{6-i} (its [skip | up] residual tensor;
             // E6 by up1), the activation A{i+1} by down{i+2}
             const int dcons = 5 - i;            // Clo index of the decoder layer that reads E{i+1}
-            if (c->Clo[dcons]) { p.lo_raw = c->Clo[dcons]; p.lo_raw_C = dcons == 0 ? 512 : 2 * L.cout; p.lo_raw_coff = 0; }
-            if (L.index < 4 && c->Alo[i + 1]) p.lo_act = c->Alo[i + 1];
-            if (L.comp) { p.lo_ptr = c->Alo[i]; p.lo_C = 4 * L.cin; }
+            if (c->Clo[dcons]) {
+                p.lo_raw = c->Clo[dcons]; p.lo_raw_C = dcons == 0 ? 512 : 2 * L.cout; p.lo_raw_coff = 0;
+                p.lo_raw_fp8 = c->lo_fmt_of(5 + dcons) == LO_FP8;
+            }
+            if (L.index < 4 && c->Alo[i + 1]) { p.lo_act = c->Alo[i + 1]; p.lo_act_fp8 = c->lo_fmt_of(L.index + 1) == LO_FP8; }
+            if (L.comp) { p.lo_ptr = c->Alo[i]; p.lo_C = 4 * L.cin; p.lo_fp8 = L.lo_fmt == LO_FP8; }
         } else {
             const int d = L.index - 5;          // up{d+1}
             if (d == 0) src[0] = c->E[6];
@@ -578,8 +588,11 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             p.mode = 2;
             p.out_dec = c->U[d + 1];
             p.round_act = (d < 4) ? 1 : 0;      // up5 feeds the SIMT up6 kernel: keep fp32
-            if (d < 4 && c->Clo[d + 1]) { p.lo_dec = c->Clo[d + 1]; p.lo_dec_C = 2 * L.cout; p.lo_dec_coff = L.cout; }   // U{d+1}: second half of up{d+2}'s residuals
-            if (L.comp) { p.lo_ptr = c->Clo[d]; p.lo_C = L.cin; }
+            if (d < 4 && c->Clo[d + 1]) {       // U{d+1}: second half of up{d+2}'s residuals
+                p.lo_dec = c->Clo[d + 1]; p.lo_dec_C = 2 * L.cout; p.lo_dec_coff = L.cout;
+                p.lo_dec_fp8 = c->lo_fmt_of(5 + d + 1) == LO_FP8;
+            }
+            if (L.comp) { p.lo_ptr = c->Clo[d]; p.lo_C = L.cin; p.lo_fp8 = L.lo_fmt == LO_FP8; }
         }
         for (int q = 0; q < L.nsrc; q++) {
             p.src_ptr[q] = src[q];
@@ -588,7 +601,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         }
         if (L.nsrc == 1) p.tmap[1] = p.tmap[0];
         p.tmap[2] = p.tmap[0];                  // always a valid descriptor (the kernels prefetch all three)
-        if (L.comp && (r = make_tmap_lo(&p.tmap[2], p.lo_ptr, L.lo_src.C, L.lo_src.W, L.lo_src.H, S * c->B, L.tw, L.th, L.nb))) return r;
+        if (L.comp && (r = make_tmap_lo(&p.tmap[2], p.lo_ptr, L.lo_src.C, L.lo_src.W, L.lo_src.H, S * c->B, L.tw, L.th, L.nb, L.lo_fmt == LO_FP8))) return r;
     }
     // ---- row-patch variants of the small-N layers ------------------------------------------
     // SRT_CONV_RP: "0" = never, "1" = whenever supported, unset = when the tile row is wide enough to pay
@@ -596,7 +609,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     const char* boe = getenv("SRT_RP_BO");
     for (size_t li = 0; li < c->plans.size(); li++) {
         if (!row_plan_supported((int)li) || c->cfg.conv_impl == 1) continue;
-        const RowPlan rpl = build_row_plan(NetGeom{T, F}, (int)li, c->split_weights, c->plans[li].comp);
+        const RowPlan rpl = build_row_plan(NetGeom{T, F}, (int)li, c->split_weights, c->plans[li].comp, c->lo_want);
         const bool want = rpe ? atoi(rpe) != 0 : rpl.Ws >= 96;
         if (!want || !conv_rp_fits((int)rpl.chunks.size(), (int)rpl.kb.size())) continue;
         RowConvParams& q = c->rp[li];
@@ -621,7 +634,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             if (make_tmap(&q.tmap[k], c->conv[li].src_ptr[k], rpl.src[k].C, rpl.src[k].W, rpl.src[k].H, S * c->B, kPatchW, rpl.R + 2, 1)) ok = false;
         if (rpl.nsrc == 1) q.tmap[1] = q.tmap[0];
         q.tmap[2] = q.tmap[0];
-        if (ok && rpl.comp && make_tmap_lo(&q.tmap[2], c->conv[li].lo_ptr, rpl.lo_src.C, rpl.lo_src.W, rpl.lo_src.H, S * c->B, kPatchW, rpl.R + 2, 1)) ok = false;
+        if (ok && rpl.comp && make_tmap_lo(&q.tmap[2], c->conv[li].lo_ptr, rpl.lo_src.C, rpl.lo_src.W, rpl.lo_src.H, S * c->B, kPatchW, rpl.R + 2, 1, rpl.lo_fmt == LO_FP8)) ok = false;
         if (!ok) { fprintf(stderr, "[spleeterrt_b200] row-patch tensor map rejected for layer %zu (%s); using the generic kernel\n", li, g_err.c_str()); continue; }
         c->use_rp[li] = true;
     }
@@ -659,6 +672,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             e.round_raw = 0;            // the skip feeds the fp32 SIMT up6 kernel
             e.round_act = 1;
             e.lo_act = c->Alo[1];       // residual of A1 for a compensated down2 (nullptr otherwise)
+            e.lo_act_fp8 = c->lo_fmt_of(0) == LO_FP8;
             if (make_tmap(&q.tmap[0], c->d_mag, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1) ||
                 make_tmap(&q.tmap[1], c->d_mag + (size_t)c->NB * T * F * 2, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1)) {
                 fprintf(stderr, "[spleeterrt_b200] down1 tensor map rejected (%s); using the SIMT kernel\n", g_err.c_str());
@@ -766,7 +780,7 @@ static int run_unet_launches(srt_ctx* c, int mag_img0, int Bv, float* mask_base,
             p.mag = c->d_mag + (size_t)mag_img0 * c->T * c->F * 2;
             p.mag_lo = p.mag + (size_t)c->NB * c->T * c->F * 2;
             p.w = c->d_w1; p.bias = c->d_b1; p.bn_scale = c->d_s1; p.bn_offset = c->d_o1;
-            p.out_raw = c->E[1]; p.out_act = c->A[1]; p.lo_act = c->Alo[1];
+            p.out_raw = c->E[1]; p.out_act = c->A[1]; p.lo_act = reinterpret_cast<uint16_t*>(c->Alo[1]);   // down2's residuals are always bf16 (64 channels)
             p.T = c->T; p.F = c->F; p.B = c->B; p.Bv = Bv; p.S = S;
             for (int s = 0; s < S; s++) {
                 p.stem = s;

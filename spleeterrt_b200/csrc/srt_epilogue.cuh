@@ -68,6 +68,21 @@ __device__ __forceinline__ void store16_lo(uint16_t* dst, const float* lo)
     }
 }
 
+// The same residuals in the 8-bit format: e5m2(4 lo), 16 bytes per pixel and chunk, one store.
+__device__ __forceinline__ void store16_lo8(uint8_t* dst, const float* lo)
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = ptx::pack_e5m2x4(4.0f * lo[4 * i], 4.0f * lo[4 * i + 1], 4.0f * lo[4 * i + 2], 4.0f * lo[4 * i + 3]);
+    if (dst) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// residual store in the destination's format; `elem` = element index of the pixel's first channel of this chunk
+__device__ __forceinline__ void store16_residual(void* base, size_t elem, int fp8, bool valid, const float* lo)
+{
+    if (fp8) store16_lo8(valid ? reinterpret_cast<uint8_t*>(base) + elem : nullptr, lo);
+    else store16_lo(valid ? reinterpret_cast<uint16_t*>(base) + elem : nullptr, lo);
+}
+
 // Branch-free activations for the tensor-core epilogues.  The epilogue warps are instruction-latency
 // bound (ncu / tools/stage_sweep.py: the epilogue, not the MMAs, dominates down1 and costs as much as the
 // MMAs of the small-N layers), so the activation kind is resolved once per 16-channel chunk and ELU is
@@ -137,7 +152,7 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
         float* dst = p.out_dec + opix * p.cout + c0;
         if (stage) store16_warp(valid ? dst : nullptr, o, stage);
         else store16(dst, o);
-        if (p.lo_dec) store16_lo(valid ? p.lo_dec + opix * p.lo_dec_C + p.lo_dec_coff + c0 : nullptr, l);
+        if (p.lo_dec) store16_residual(p.lo_dec, opix * p.lo_dec_C + p.lo_dec_coff + c0, p.lo_dec_fp8, valid, l);
         return;
     }
     float raw[16];
@@ -154,7 +169,7 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
         float* dst = p.out_act + apix * p.cout + c0;
         if (stage) store16_warp(valid ? dst : nullptr, a, stage);
         else store16(dst, a);
-        if (p.lo_act) store16_lo(valid ? p.lo_act + apix * p.cout + c0 : nullptr, l);
+        if (p.lo_act) store16_residual(p.lo_act, apix * p.cout + c0, p.lo_act_fp8, valid, l);
     }
     const size_t rpix = ((size_t)n * p.Hs + Y) * p.Ws + X;
     if (p.round_raw) {
@@ -165,7 +180,7 @@ __device__ __forceinline__ void epilogue16(const ConvParams& p, int s, int n, in
             l[i] = raw[i] - hi;
             raw[i] = hi;
         }
-        if (p.lo_raw) store16_lo(valid ? p.lo_raw + rpix * p.lo_raw_C + p.lo_raw_coff + c0 : nullptr, l);
+        if (p.lo_raw) store16_residual(p.lo_raw, rpix * p.lo_raw_C + p.lo_raw_coff + c0, p.lo_raw_fp8, valid, l);
     }
     float* dst = p.out_raw + rpix * p.cout + c0;
     if (stage) store16_warp(valid ? dst : nullptr, raw, stage);

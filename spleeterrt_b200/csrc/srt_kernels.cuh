@@ -45,8 +45,9 @@ struct LaunchState {
 struct alignas(64) ConvParams {
     CUtensorMap tmap[3];          // source activation tensors, dims {C, W, H, S*B}, box {32, tw, th, nb}, SW128; [2] = the bf16 residual
                                   // tensor of compensated layers (box {64, tw, th, nb}: the same 128-byte rows)
-    const uint16_t* lo_ptr;       // the residual tensor as a raw pointer (SIMT verification path), lo_C channels per pixel
-    int lo_C;
+    const void* lo_ptr;           // the residual tensor as a raw pointer (SIMT verification path), lo_C channels per pixel,
+    int lo_C;                     // bf16 or (lo_fp8) e5m2 bytes
+    int lo_fp8;
     const float* src_ptr[2];      // same tensors as raw pointers (SIMT verification path)
     int src_C[2];
     const KBlock* kb;             // all phases back to back
@@ -75,10 +76,12 @@ struct alignas(64) ConvParams {
     int round_raw, round_act;     // round stored values to TF32 (consumer is a tensor-core layer)
     // compensated precision: next to every TF32-rounded value hi = tf32(v) the epilogue stores bf16(v - hi) for the
     // consumer's compensation k-blocks (srt_plan.h build_plans).  nullptr = the consumer runs single-pass TF32.
-    uint16_t* lo_raw;             // residual of out_raw:  [n][Hs][Ws][lo_raw_C], this layer's channels at lo_raw_coff
-    uint16_t* lo_act;             // residual of out_act:  same space-to-depth layout as out_act
-    uint16_t* lo_dec;             // residual of out_dec:  [n][2Hs][2Ws][lo_dec_C], this layer's channels at lo_dec_coff
+    // Each residual tensor is in its CONSUMER's format: bf16, or e5m2 bytes holding 4 (v - hi) (srt_plan.h kPartLo8).
+    void* lo_raw;                 // residual of out_raw:  [n][Hs][Ws][lo_raw_C], this layer's channels at lo_raw_coff
+    void* lo_act;                 // residual of out_act:  same space-to-depth layout as out_act
+    void* lo_dec;                 // residual of out_dec:  [n][2Hs][2Ws][lo_dec_C], this layer's channels at lo_dec_coff
     int lo_raw_C, lo_raw_coff, lo_dec_C, lo_dec_coff;
+    int lo_raw_fp8, lo_act_fp8, lo_dec_fp8;
 };
 
 // Row-patch tensor-core kernel (srt_conv_rp.cu): small-N layers, see srt_plan.h RowPlan.
@@ -115,7 +118,7 @@ struct Down1Params {              // 5x5 s2 conv 2->16 on the magnitude image, s
     const float* bn_offset;       // [S][16]
     float* out_raw;               // [S*B][T/2][F/2][16]
     float* out_act;               // S2D [S*B][T/4][F/4][64], TF32-rounded
-    uint16_t* lo_act;             // bf16 residual of out_act (compensated down2) or nullptr
+    uint16_t* lo_act;             // bf16 residual of out_act (compensated down2: its 64 residual channels are always bf16) or nullptr
     int T, F, B, Bv, S;
     int act[8];
     int stem;                     // one launch per stem: weights / bias / BN ride in the constant bank

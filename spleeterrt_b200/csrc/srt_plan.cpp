@@ -1,6 +1,7 @@
 // srt_plan.cpp — see srt_plan.h.  Plain host C++.
 #include "srt_plan.h"
 
+#include <cmath>
 #include <cstring>
 
 namespace srt {
@@ -54,6 +55,53 @@ float bf16_to_float(uint16_t h)
     float r;
     std::memcpy(&r, &u, 4);
     return r;
+}
+
+// float -> e5m2 = the top byte of the IEEE half, rounded to nearest even on the dropped 8 bits; saturates to the largest finite value
+uint8_t e5m2_rn(float x)
+{
+    if (x != x) return 0x7f;
+    const float ax = x < 0 ? -x : x;
+    const uint8_t sign = x < 0 || (x == 0 && 1.0f / x < 0) ? 0x80 : 0x00;
+    if (ax >= 57344.0f) return sign | 0x7b;                  // max finite e5m2 (satfinite)
+    // scale into the half format by hand: e5m2 has exponent bias 15, 2 mantissa bits, subnormals down to 2^-16
+    if (ax < 7.62939453125e-06f) return sign;                 // < 2^-17: rounds to zero (2^-17 itself ties to even = 0)
+    int e;
+    const float m = std::frexp(ax, &e);                       // ax = m 2^e, m in [0.5, 1)
+    int exp = e - 1;                                          // ax = (2m) 2^(e-1), 2m in [1, 2)
+    float frac = 2.0f * m;
+    int q;                                                    // quantised magnitude in units of the format's ulp
+    if (exp < -14) {                                          // subnormal: ulp 2^-16
+        const float u = ax * 65536.0f;                        // in units of 2^-16: < 4
+        q = (int)u;
+        const float r = u - (float)q;
+        if (r > 0.5f || (r == 0.5f && (q & 1))) q++;
+        return sign | (uint8_t)q;                             // q == 4 becomes the smallest normal (0x04): correct carry
+    }
+    const float u = (frac - 1.0f) * 4.0f;                     // mantissa in quarters: [0, 4)
+    q = (int)u;
+    const float r = u - (float)q;
+    if (r > 0.5f || (r == 0.5f && (q & 1))) q++;
+    if (q == 4) { q = 0; exp++; }
+    if (exp > 15) return sign | 0x7b;
+    return sign | (uint8_t)(((exp + 15) << 2) | q);
+}
+float e5m2_to_float(uint8_t b)
+{
+    const int e = (b >> 2) & 0x1f, m = b & 3;
+    float v;
+    if (e == 0) v = (float)m * 1.52587890625e-05f;            // m 2^-16
+    else if (e == 31) v = m ? NAN : INFINITY;
+    else v = std::ldexp(1.0f + 0.25f * (float)m, e - 15);
+    return (b & 0x80) ? -v : v;
+}
+
+int layer_lo_format(int index, int want)
+{
+    if (want != LO_FP8) return want;
+    // residual channels per pixel: encoder 4 * cin (space-to-depth), decoder cin ([skip | up]); down2 = 64, up5 = 64
+    const int C = index < 5 ? 4 * kEnc[index + 1] : kDecIn[index - 5];
+    return (C % kKBlo8 == 0) ? LO_FP8 : LO_BF16;
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -149,7 +197,7 @@ bool weights_tf32_exact(const float* coeff)
     return true;
 }
 
-std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int n_stems, int min_ctas, unsigned comp_mask, bool fuse_phases)
+std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int n_stems, int min_ctas, unsigned comp_mask, bool fuse_phases, int lo_fmt)
 {
     std::vector<LayerPlan> plans;
     auto narrow = [&](LayerPlan& L) {
@@ -268,7 +316,10 @@ std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights, int
     // ---- compensation blocks (after the main term: small contributions are added last) ------------
     for (auto& L : plans) {
         L.comp = (comp_mask >> L.index) & 1u;
+        L.lo_fmt = L.comp ? layer_lo_format(L.index, lo_fmt) : LO_NONE;
         if (!L.comp) continue;
+        const int kKBlo = L.lo_fmt == LO_FP8 ? kKBlo8 : srt::kKBlo;                 // channels per compensation block
+        const int8_t kPartLo = (int8_t)(L.lo_fmt == LO_FP8 ? (srt::kPartLo | kPartLo8) : srt::kPartLo);
         if (!L.transposed) {
             L.lo_src = SrcDesc{4 * L.cin, L.Ws, L.Hs};
             for (int c_off = 0; c_off < 4 * L.cin; c_off += kKBlo)
@@ -329,7 +380,8 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
         for (int nt = 0; nt < L.n_tiles; nt++)
             for (size_t kb = 0; kb < nkb; kb++) {
                 float* blk = out + L.w_phase_off[p] + ((size_t)nt * nkb + kb) * L.n_tile * kKB;
-                const bool lo = (L.kb[p][kb].part & kPartLo) != 0;     // [n_tile][64] bf16 in the same bytes
+                const bool lo = (L.kb[p][kb].part & kPartLo) != 0;     // [n_tile][64] bf16 in the same bytes ...
+                const bool lo8 = (L.kb[p][kb].part & kPartLo8) != 0;   // ... or [n_tile][128] e5m2
                 const int width = kb_channels(L.kb[p][kb]);
                 for (int n = 0; n < L.n_tile; n++) {
                     int o = nt * L.n_tile + n;
@@ -353,7 +405,8 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
                                 : (((size_t)o * L.cin + e.cin) * 5 + e.kh) * 5 + e.kw;     // [O][I][kh][kw]
                             v = lo ? w[idx] : weight_part(w[idx], L.kb[p][kb].part);
                         }
-                        if (lo) reinterpret_cast<uint16_t*>(blk)[swz128_index16(n, j)] = bf16_rn(v);
+                        if (lo8) reinterpret_cast<uint8_t*>(blk)[swz128_index8(n, j)] = e5m2_rn(0.25f * v);
+                        else if (lo) reinterpret_cast<uint16_t*>(blk)[swz128_index16(n, j)] = bf16_rn(v);
                         else blk[swz128_index(n, j)] = v;
                     }
                 }
@@ -367,7 +420,7 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out)
 bool row_plan_supported(int layer_index) { return layer_index == 0 || layer_index == 1 || layer_index == 8 || layer_index == 9; }
 
 
-RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp)
+RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp, int lo_fmt)
 {
     RowPlan L{};
     L.index = layer_index;
@@ -441,9 +494,12 @@ RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp
     }
     // compensation chunks: 64-channel slabs of the bf16 residual tensor, same taps, bf16 weights (see build_plans)
     L.comp = comp;
+    L.lo_fmt = comp ? layer_lo_format(layer_index, lo_fmt) : LO_NONE;
     if (comp) {
         const int Clo = L.transposed ? L.cin : 4 * L.cin;
         L.lo_src = SrcDesc{Clo, L.Ws, L.Hs};
+        const int kKBlo = L.lo_fmt == LO_FP8 ? kKBlo8 : srt::kKBlo;
+        const int8_t kPartLo = (int8_t)(L.lo_fmt == LO_FP8 ? (srt::kPartLo | kPartLo8) : srt::kPartLo);
         for (int c_off = 0; c_off < Clo; c_off += kKBlo) {
             RowChunk ch{(int8_t)kSrcLo, c_off, (int32_t)L.kb.size(), 0};
             for (int dy = -1; dy <= 1; dy++)
@@ -497,7 +553,7 @@ void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
     const float* w = coeff + (L.transposed ? cl.up_w[L.index - 5] : cl.down_w[L.index + 1]);
     for (size_t kb = 0; kb < L.kb.size(); kb++) {
         float* blk = out + kb * (size_t)L.N * kKB;
-        const bool lo = (L.kb[kb].part & kPartLo) != 0;
+        const bool lo = (L.kb[kb].part & kPartLo) != 0, lo8 = (L.kb[kb].part & kPartLo8) != 0;
         const int width = kb_channels(L.kb[kb]);
         for (int n = 0; n < L.N; n++) {
             const int ph = L.transposed ? n / L.cout : 0, o = L.transposed ? n % L.cout : n;
@@ -509,7 +565,8 @@ void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
                                                     : (((size_t)o * L.cin + e.cin) * 5 + e.kh[ph]) * 5 + e.kw[ph];
                     v = lo ? w[idx] : weight_part(w[idx], L.kb[kb].part);
                 }
-                if (lo) reinterpret_cast<uint16_t*>(blk)[swz128_index16(n, j)] = bf16_rn(v);
+                if (lo8) reinterpret_cast<uint8_t*>(blk)[swz128_index8(n, j)] = e5m2_rn(0.25f * v);
+                else if (lo) reinterpret_cast<uint16_t*>(blk)[swz128_index16(n, j)] = bf16_rn(v);
                 else blk[swz128_index(n, j)] = v;
             }
         }

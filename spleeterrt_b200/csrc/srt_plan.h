@@ -49,8 +49,15 @@ constexpr int kPartLo = 2;
 // the MMA issuer therefore skips (down2: 75 of 96 K steps per row are left)
 constexpr int kPartSkipShift = 4;
 SRT_HD inline int kb_skip_mask(const KBlock& kb) { return ((unsigned char)kb.part >> kPartSkipShift) & 0xf; }
+// bit 2 (with bit 1): the compensation block is in the 8-bit format: A = e5m2(4 (a - tf32(a))), W = e5m2(w / 4), 128 channels per
+// 128-byte row, kind::f8f6f4 MMAs (K = 32).  Two mantissa bits on either side leave ~6 % of the rounding error (bf16: 0.4 %),
+// about what the tensor core's own accumulation adds; half the MMAs and half the bytes of the bf16 form.  The factors 4 and
+// 1/4 keep both operands inside e5m2's normal range (residuals of |a| >= 2^-4, weights >= 2^-12); smaller ones fade out.
+constexpr int kPartLo8 = 4;
+constexpr int kKBlo8 = 128;
 constexpr int kSrcLo = 2;               // KBlock::src / RowChunk::src of the residual tensor
-SRT_HD inline int kb_channels(const KBlock& kb) { return (kb.part & kPartLo) ? kKBlo : kKB; }
+SRT_HD inline int kb_channels(const KBlock& kb) { return (kb.part & kPartLo) ? ((kb.part & kPartLo8) ? kKBlo8 : kKBlo) : kKB; }
+enum LoFormat : int { LO_NONE = 0, LO_BF16 = 1, LO_FP8 = 2 };
 
 // For the weight packer: where k-element j of a k-block comes from.
 struct KElem {
@@ -81,6 +88,7 @@ struct LayerPlan {
     // compensated precision (see build_plans): the residual source, bf16, same pixel grid as src[]; encoder layers: the
     // space-to-depth tensor's twin; decoder layers: ONE tensor holding [skip residual | up residual] per pixel
     bool comp;
+    int lo_fmt;           // LoFormat of this layer's residual tensor (LO_FP8 needs a channel count that is a multiple of 128)
     SrcDesc lo_src;
     // decoder layers with 4 * cout <= 256: the four output parities fused into N = 4 * cout (column = phase * cout + channel), ONE
     // k-block list over all 3 x 3 input offsets (a parity that does not use an offset gets zero weights).  An activation tile is then
@@ -115,7 +123,10 @@ CoeffLayout coeff_layout();
 // AND the residual with bf16(w) (kind::f16, 64 channels per 128-byte row, i.e. half the MMAs and half the bytes of the main
 // term).  Operand error drops from 2^-12 to ~2^-19 relative: fp32-grade results for 1.5x the tensor work.
 std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false, int n_stems = 1, int min_ctas = 0, unsigned comp_mask = 0,
-                                   bool fuse_phases = true);
+                                   bool fuse_phases = true, int lo_fmt = LO_BF16);
+// the residual format layer `index` (0..9) uses when `want` is asked for: LO_FP8 only where the residual tensor has a multiple of 128
+// channels per pixel (everything but down2 and up5, whose 64 channels stay bf16)
+int layer_lo_format(int index, int want);
 // transposed conv: the kernel row that serves output parity `par` at input offset d (o = 2h + kh - 1), or -1
 int dec_kh(int par, int d);
 
@@ -128,6 +139,8 @@ void pack_layer(const LayerPlan& L, const float* coeff, float* out);
 float round_tf32(float x);
 uint16_t bf16_rn(float x);              // round to nearest even (cvt.rn.bf16.f32)
 float bf16_to_float(uint16_t h);
+uint8_t e5m2_rn(float x);               // round to nearest even, saturating (cvt.rn.satfinite.e5m2x2.f32)
+float e5m2_to_float(uint8_t b);
 // value stored for a weight in a k-block of the given part
 inline float weight_part(float w, int part) { const float hi = round_tf32(w); return (part & 1) == 0 ? hi : round_tf32(w - hi); }   // bit 0 of KBlock::part
 bool weights_tf32_exact(const float* coeff);   // all tensor-core conv weights of one net representable in TF32?
@@ -165,6 +178,7 @@ struct RowPlan {
     std::vector<KElemP> kelem;          // kb_channels() per k-block, k-block k starts at ke_off[k]
     std::vector<int32_t> ke_off;
     bool comp;                          // compensated precision: extra chunks with src = kSrcLo (see build_plans)
+    int lo_fmt;
     SrcDesc lo_src;
     size_t w_floats_per_stem;           // kb.size() * N * 32
 };
@@ -189,12 +203,14 @@ SRT_HD inline int swz32_index(int row, int j) { return row * 8 + ((((j >> 2) ^ (
 SRT_HD inline size_t mag_s2d_index(int T, int F, int t, int f) { return (((size_t)(t >> 1) * (F >> 1) + (f >> 1)) << 2) + ((t & 1) << 1) + (f & 1); }
 
 bool row_plan_supported(int layer_index);                 // down2, down3, up4, up5
-RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights = false, bool comp = false);
+RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights = false, bool comp = false, int lo_fmt = LO_BF16);
 void pack_row_layer(const RowPlan& L, const float* coeff, float* out);
 
 // index of (row n, k-element j) inside a swizzled [rows][32] fp32 block
 SRT_HD inline int swz128_index(int row, int j) { return row * 32 + ((((j >> 2) ^ (row & 7)) << 2) | (j & 3)); }
 // same for a [rows][64] block of 2-byte elements (16-byte chunks of 8 elements)
 SRT_HD inline int swz128_index16(int row, int j) { return row * 64 + ((((j >> 3) ^ (row & 7)) << 3) | (j & 7)); }
+// and for a [rows][128] block of bytes (16-byte chunks of 16 elements)
+SRT_HD inline int swz128_index8(int row, int j) { return row * 128 + ((((j >> 4) ^ (row & 7)) << 4) | (j & 15)); }
 
 }  // namespace srt

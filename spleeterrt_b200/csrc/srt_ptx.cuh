@@ -178,6 +178,21 @@ __device__ __forceinline__ void mma_bf16_ss_lo(uint32_t tmem_d, uint32_t a_lo, u
         : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
         : "memory");
 }
+// The 8-bit form of the compensation blocks (kPartLo8): A and W are e5m2 bytes, 128 per 128-byte row, K = 32 per MMA (again a
+// 32-byte descriptor advance).  The instruction descriptor is the bf16 one (format code 1 = E5M2 for this kind).
+__device__ __forceinline__ void mma_f8_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                             uint32_t desc_hi = kDescHiSw128)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %3, p;\n\t}\n"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+        : "memory");
+}
 // same, with separate descriptor high words for A and B (operands in different swizzle modes)
 __device__ __forceinline__ void mma_tf32_ss_ab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                                uint32_t accumulate)
@@ -271,6 +286,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+
+// four floats -> four e5m2 bytes (round to nearest even, saturating), a in bits 0-7 ... d in bits 24-31
+__device__ __forceinline__ uint32_t pack_e5m2x4(float a, float b, float c, float d)
+{
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;\n" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;\n" : "=h"(hi) : "f"(d), "f"(c));
+    return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
 // Packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2, two IEEE fp32 operations per lane and issue slot; each half rounds exactly

@@ -2,6 +2,8 @@
 // plus a slow SIMT evaluation of the gather-GEMM layers that consumes exactly the same
 // tables / packed weights / activation layouts as the tcgen05 kernel.  The latter is a
 // verification aid (SRT_CONV_IMPL=simt), not a CPU fallback: everything here runs on the GPU.
+#include <cuda_fp16.h>
+
 #include "srt_epilogue.cuh"
 #include "srt_kernels.cuh"
 #include "srt_ptx.cuh"
@@ -33,8 +35,19 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(const __grid_constant__ 
             const int yy = Y + kb.dy, xx = X + kb.dx;
             if (!valid || yy < 0 || yy >= p.Hs || xx < 0 || xx >= p.Ws) continue;   // zero padding
             const float* wb = wbase + (size_t)k * p.n_tile * kKB;
+            if (kb.part & kPartLo8) {   // compensation block, 8-bit form: e5m2(4 lo) x e5m2(w / 4), 128 channels
+                const uint8_t* a = reinterpret_cast<const uint8_t*>(p.lo_ptr) + (((size_t)n * p.Hs + yy) * p.Ws + xx) * p.lo_C + kb.c_off;
+                const uint8_t* wh = reinterpret_cast<const uint8_t*>(wb);
+                for (int j = 0; j < kKBlo8; j++) {
+                    const float av = __half2float(__ushort_as_half((unsigned short)((unsigned)a[j] << 8)));   // e5m2 = the top byte of a half
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        acc[i] = fmaf(av, __half2float(__ushort_as_half((unsigned short)((unsigned)wh[swz128_index8(c0 + i, j)] << 8))), acc[i]);
+                }
+                continue;
+            }
             if (kb.part & kPartLo) {   // compensation block: bf16 residuals x bf16 weights, 64 channels
-                const uint16_t* a = p.lo_ptr + (((size_t)n * p.Hs + yy) * p.Ws + xx) * p.lo_C + kb.c_off;
+                const uint16_t* a = reinterpret_cast<const uint16_t*>(p.lo_ptr) + (((size_t)n * p.Hs + yy) * p.Ws + xx) * p.lo_C + kb.c_off;
                 const uint16_t* wh = reinterpret_cast<const uint16_t*>(wb);
                 for (int j = 0; j < kKBlo; j++) {
                     const float av = __uint_as_float((uint32_t)a[j] << 16);

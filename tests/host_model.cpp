@@ -15,7 +15,8 @@ static bool g_split = false;   // two-term weights (weights not exactly represen
 extern "C" void srt_host_model_set_split(int on) { g_split = on != 0; }
 static bool g_comp = false;    // compensated precision: sources rounded to TF32 + bf16 residual tensors contracted by extra k-blocks
 static bool g_comp_drop = false;   // (control experiment) sources rounded, compensation blocks ignored
-extern "C" void srt_host_model_set_comp(int on) { g_comp = on != 0; g_comp_drop = on == 2; }
+static int g_lo_fmt = LO_BF16;     // residual format asked for: LO_BF16, or LO_FP8 (layers with 64 residual channels stay bf16)
+extern "C" void srt_host_model_set_comp(int on) { g_comp = on != 0; g_comp_drop = on == 2; g_lo_fmt = on == 3 ? LO_FP8 : LO_BF16; }
 static bool g_fuse = true;     // decoder layers with 4 * cout <= 256 fuse their four output parities into N (the product's default)
 extern "C" void srt_host_model_set_fuse(int on) { g_fuse = on != 0; }
 static int g_min_ctas = 0;      // build_plans(min_ctas): narrower N tiles for small grids (what a small-batch context uses)
@@ -35,9 +36,11 @@ static float act_apply(int act, float x)
 
 // What the producing epilogue stores in compensated mode: hi = tf32(a) in place, residual bf16(a - hi) in the layer's
 // residual tensor (encoder: same layout; decoder: channel q's block of the concatenated [skip | up] tensor).
-static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const SrcDesc* sd, int H, int W, const SrcDesc& lo_sd, std::vector<uint16_t>& lo)
+// `lo` holds the operand values the compensation MMAs read: bf16(a - hi), or e5m2(4 (a - hi)) in the 8-bit format.
+static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const SrcDesc* sd, int H, int W, const SrcDesc& lo_sd, int lo_fmt,
+                          std::vector<float>& lo)
 {
-    lo.assign((size_t)H * W * lo_sd.C, 0);
+    lo.assign((size_t)H * W * lo_sd.C, 0.f);
     int coff = 0;
     for (int q = 0; q < nsrc; q++) {
         const int C = sd[q].C;
@@ -45,11 +48,17 @@ static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const 
             for (int c = 0; c < C; c++) {
                 float& a = src[q][px * C + c];
                 const float hi = round_tf32(a);
-                lo[px * lo_sd.C + coff + c] = bf16_rn(a - hi);
+                lo[px * lo_sd.C + coff + c] = lo_fmt == LO_FP8 ? e5m2_to_float(e5m2_rn(4.0f * (a - hi))) : bf16_to_float(bf16_rn(a - hi));
                 a = hi;
             }
         coff += C;
     }
+}
+// weight of a compensation block as the MMA reads it
+static float lo_weight(const KBlock& kb, const float* wb, int n, int j)
+{
+    if (kb.part & kPartLo8) return e5m2_to_float(reinterpret_cast<const uint8_t*>(wb)[swz128_index8(n, j)]);
+    return bf16_to_float(reinterpret_cast<const uint16_t*>(wb)[swz128_index16(n, j)]);
 }
 
 // src0/src1: planar [C][H][W] fp32 in the *reference's* layout:
@@ -60,7 +69,7 @@ static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const 
 extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
                                     float* out, int want_act)
 {
-    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split, 1, g_min_ctas, g_comp ? 0x3ffu : 0u, g_fuse);
+    std::vector<LayerPlan> plans = build_plans(NetGeom{T, F}, 1, g_split, 1, g_min_ctas, g_comp ? 0x3ffu : 0u, g_fuse, g_lo_fmt);
     if (plan_index < 0 || plan_index >= (int)plans.size()) return -1;
     const LayerPlan& L = plans[plan_index];
     if (L.comp != g_comp) return -5;
@@ -85,8 +94,8 @@ extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* c
                     for (int x = 0; x < W; x++) src[q][((size_t)y * W + x) * C + c] = in[q][((size_t)c * H + y) * W + x];
         }
     }
-    std::vector<uint16_t> lo;
-    if (L.comp) split_sources(src, L.nsrc, L.src, H, W, L.lo_src, lo);
+    std::vector<float> lo;
+    if (L.comp) split_sources(src, L.nsrc, L.src, H, W, L.lo_src, L.lo_fmt, lo);
     // ---- weights and epilogue vectors ----------------------------------------------------
     std::vector<float> wpk(L.w_floats_per_stem);
     pack_layer(L, coeff, wpk.data());
@@ -113,13 +122,14 @@ extern "C" int srt_host_model_layer(int T, int F, int plan_index, const float* c
                             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;   // TMA zero fill
                             const float* wb = &wpk[L.w_phase_off[ph] + ((size_t)nt * nkb + k) * L.n_tile * kKB];
                             if (kb.part & kPartLo) {                                // compensation block: bf16 residuals x bf16 weights
-                                if (!L.comp || kb.src != kSrcLo || kb.c_off < 0 || kb.c_off + kKBlo > L.lo_src.C) return -2;
+                                const int width = kb_channels(kb);
+                                if (!L.comp || kb.src != kSrcLo || kb.c_off < 0 || kb.c_off + width > L.lo_src.C) return -2;
+                                if (((kb.part & kPartLo8) != 0) != (L.lo_fmt == LO_FP8)) return -7;
                                 if (g_comp_drop) continue;
-                                const uint16_t* a = &lo[((size_t)yy * W + xx) * L.lo_src.C + kb.c_off];
-                                const uint16_t* wh = reinterpret_cast<const uint16_t*>(wb);
+                                const float* a = &lo[((size_t)yy * W + xx) * L.lo_src.C + kb.c_off];
                                 for (int n = 0; n < L.n_tile; n++) {
                                     float s = 0.f;
-                                    for (int j = 0; j < kKBlo; j++) s += bf16_to_float(a[j]) * bf16_to_float(wh[swz128_index16(n, j)]);
+                                    for (int j = 0; j < width; j++) s += a[j] * lo_weight(kb, wb, n, j);
                                     acc[n] += s;
                                 }
                                 continue;
@@ -163,13 +173,15 @@ extern "C" int srt_host_model_plan_info(int T, int F, int n_img, int plan_index,
 }
 
 extern "C" float srt_host_model_round_tf32(float x) { return round_tf32(x); }
+extern "C" int srt_host_model_e5m2(float x) { return e5m2_rn(x); }
+extern "C" float srt_host_model_e5m2_value(int b) { return e5m2_to_float((uint8_t)b); }
 
 // ---- row-patch ("v2") form of down2 / down3 / up4 / up5 --------------------------------------
 extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const float* coeff, int act, const float* src0, const float* src1,
                                         float* out, int want_act)
 {
     if (!row_plan_supported(plan_index)) return -1;
-    const RowPlan L = build_row_plan(NetGeom{T, F}, plan_index, g_split, g_comp);
+    const RowPlan L = build_row_plan(NetGeom{T, F}, plan_index, g_split, g_comp, g_lo_fmt);
     const CoeffLayout cl = coeff_layout();
     const int H = L.Hs, W = L.Ws;
     std::vector<std::vector<float>> src(L.nsrc);
@@ -190,8 +202,8 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                     for (int x = 0; x < W; x++) src[q][((size_t)y * W + x) * C + c] = in[q][((size_t)c * H + y) * W + x];
         }
     }
-    std::vector<uint16_t> lo;
-    if (L.comp) split_sources(src, L.nsrc, L.src, H, W, L.lo_src, lo);
+    std::vector<float> lo;
+    if (L.comp) split_sources(src, L.nsrc, L.src, H, W, L.lo_src, L.lo_fmt, lo);
     std::vector<float> wpk(L.w_floats_per_stem);
     pack_row_layer(L, coeff, wpk.data());
     const float* bias = coeff + (L.transposed ? cl.up_b[L.index - 5] : cl.down_b[L.index + 1]);
@@ -200,13 +212,13 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
     // K steps the MMA issuer skips (kPartSkipShift) must hold nothing but zero weights, and the model below honours the mask
     for (size_t k = 0; k < L.kb.size(); k++) {
         const int width = kb_channels(L.kb[k]), per = width / 4, skip = kb_skip_mask(L.kb[k]);
-        const bool lo16 = (L.kb[k].part & kPartLo) != 0;
+        const bool is_lo = (L.kb[k].part & kPartLo) != 0;
         for (int q = 0; q < 4; q++)
             if (skip & (1 << q))
                 for (int n = 0; n < L.N; n++)
                     for (int j = q * per; j < (q + 1) * per; j++) {
                         const float* wb = &wpk[k * (size_t)L.N * kKB];
-                        const float v = lo16 ? bf16_to_float(reinterpret_cast<const uint16_t*>(wb)[swz128_index16(n, j)]) : wb[swz128_index(n, j)];
+                        const float v = is_lo ? lo_weight(L.kb[k], wb, n, j) : wb[swz128_index(n, j)];
                         if (v != 0.0f) return -6;
                     }
     }
@@ -229,14 +241,15 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                             if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
                             const float* wb = &wpk[(size_t)k * L.N * kKB];
                             if (kb.part & kPartLo) {
-                                if (!L.comp || ch.src != kSrcLo || kb.c_off + kKBlo > L.lo_src.C) return -2;
+                                const int width = kb_channels(kb);
+                                if (!L.comp || ch.src != kSrcLo || kb.c_off + width > L.lo_src.C) return -2;
+                                if (((kb.part & kPartLo8) != 0) != (L.lo_fmt == LO_FP8)) return -7;
                                 if (g_comp_drop) continue;
-                                const uint16_t* a = &lo[((size_t)yy * W + xx) * L.lo_src.C + kb.c_off];
-                                const uint16_t* wh = reinterpret_cast<const uint16_t*>(wb);
+                                const float* a = &lo[((size_t)yy * W + xx) * L.lo_src.C + kb.c_off];
                                 for (int n = 0; n < L.N; n++) {
                                     float s = 0.f;
-                                    for (int j = 0; j < kKBlo; j++)
-                                        if (!(kb_skip_mask(kb) & (1 << (j / 16)))) s += bf16_to_float(a[j]) * bf16_to_float(wh[swz128_index16(n, j)]);
+                                    for (int j = 0; j < width; j++)
+                                        if (!(kb_skip_mask(kb) & (1 << (j / (width / 4))))) s += a[j] * lo_weight(kb, wb, n, j);
                                     acc[n] += s;
                                 }
                                 continue;

@@ -149,6 +149,70 @@ def test_compensated_precision_tables(oracle, host_model, small_nets, mode):
         host_model.srt_host_model_set_comp(0)
 
 
+def test_e5m2_conversion(host_model):
+    """e5m2_rn (the host's statement of cvt.rn.satfinite.e5m2x2.f32, used to pack the 8-bit compensation weights): every one of the
+    256 codes round-trips, values round to the nearest code (ties to even), and out-of-range values saturate."""
+    host_model.srt_host_model_e5m2_value.restype = C.c_float
+    host_model.srt_host_model_e5m2.argtypes = [C.c_float]
+    codes = [b for b in range(256) if (b >> 2) & 31 != 31]
+    vals = {b: host_model.srt_host_model_e5m2_value(b) for b in codes}
+    for b, v in vals.items():
+        if v == 0.0:
+            continue
+        assert host_model.srt_host_model_e5m2(v) == b, (b, v)
+    pos = sorted(v for v in vals.values() if v > 0)
+    rng = np.random.default_rng(0)
+    for x in np.exp(rng.uniform(np.log(1e-6), np.log(7e4), 4000)).astype(np.float32):
+        got = host_model.srt_host_model_e5m2_value(host_model.srt_host_model_e5m2(float(x)))
+        best = min([0.0] + pos, key=lambda v: abs(v - float(x)))
+        assert abs(got - float(x)) <= abs(best - float(x)) * (1 + 1e-6), (x, got, best)
+    assert host_model.srt_host_model_e5m2_value(host_model.srt_host_model_e5m2(1e9)) == 57344.0
+    assert host_model.srt_host_model_e5m2_value(host_model.srt_host_model_e5m2(-1e9)) == -57344.0
+    assert host_model.srt_host_model_e5m2(1.25 + 0.125) == host_model.srt_host_model_e5m2(1.5)       # tie 1.375 -> even mantissa (1.5 = 0b10)
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_fp8_compensation_tables(oracle, host_model, small_nets, mode):
+    """The 8-bit residual format (e5m2(4 lo) x e5m2(w / 4), 128 channels per block; down2 and up5 keep bf16 because their
+    residual tensors have 64 channels): tables, packing and scaling reproduce the oracle to ~1e-5, between the bf16 form
+    (~1e-6) and uncompensated TF32 (~2e-4)."""
+    T, F = 64, 128
+    coeff = small_nets[0][0] if mode else small_nets[1][0]
+    rng = np.random.default_rng(9 + mode)
+    x = (np.abs(rng.standard_normal((2, T, F))) * 3).astype(np.float32)
+    _, tp = oracle.unet(coeff, x, mode, taps=True)
+    taps = oracle.split_taps(tp, T, F)
+    v = oracle.coeff_views(coeff)
+    a_enc, a_dec = (3, 3) if mode else (1, 2)
+    errs = {}
+    for fmt in (3, 1, 2):                     # fp8, bf16, rounded without compensation
+        host_model.srt_host_model_set_comp(fmt)
+        try:
+            for i in (2, 3):                  # down3 (row-patch and generic), down4
+                bn = v[f"down{i}.bn"]
+                act_in = _act(a_enc, bn[1][:, None, None] * taps[f"skip{i}"] + bn[0][:, None, None]).astype(np.float32)
+                ref = taps[f"skip{i+1}"]
+                for row in ([False, True] if i == 2 else [False]):
+                    got = _run_layer(host_model, T, F, i - 1, coeff, a_enc, act_in, None, ref.shape, row=row)
+                    errs[(f"down{i+1}", row, fmt)] = rms_rel(got, ref)
+            for d, rows in ((1, [False]), (2, [False]), (3, [False, True])):      # up2, up3 (fused parities), up4 (both forms)
+                ref = taps[f"up{d+1}"]
+                for row in rows:
+                    got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, taps[f"skip{6-d}"], taps[f"up{d}"], ref.shape, row=row)
+                    errs[(f"up{d+1}", row, fmt)] = rms_rel(got, ref)
+        finally:
+            host_model.srt_host_model_set_comp(0)
+    for (name, row, fmt), e in errs.items():
+        if fmt == 3:
+            assert e < 4e-5, (name, row, e)
+            assert e < errs[(name, row, 2)] / 4, (name, row, e, errs[(name, row, 2)])      # clearly better than no compensation
+            assert e > errs[(name, row, 1)], (name, row)                                      # and coarser than bf16
+
+
+def rms_rel(a, b):
+    return float(np.sqrt(np.mean((a.astype(np.float64) - b) ** 2)) / np.sqrt(np.mean(b.astype(np.float64) ** 2)))
+
+
 def test_plan_shapes(host_model):
     info = (C.c_int * 10)()
     # shape A (T=512, F=1024), batch 32: tiles are full and the k-block counts match the design
