@@ -43,22 +43,47 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML through pynvml when it is
+    importable (a query takes ~0.1 ms, so a 100 ms timed region still gets dozens of samples), else one nvidia-smi call per sample."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+        self.index, self.rows, self.stop_flag, self.th, self.via = index, [], False, None, "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.via = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]     # HW slowdown, HW thermal, SW thermal, SW power cap
+        return [str(sm), str(mx), f"{pw:.2f}"] + ["Active" if f else "Not Active" for f in flags]
 
     def _run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                               "--format=csv,noheader,nounits"], text=True, timeout=5)
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                if self.nvml:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                                   "--format=csv,noheader,nounits"], text=True, timeout=5)
+                    self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.005 if self.nvml else 0.1)
 
     def start(self):
         self.th = threading.Thread(target=self._run, daemon=True)
@@ -71,14 +96,13 @@ class ClockSampler:
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
-            for k, nm in enumerate(names):
+            for k, nm in enumerate(self.NAMES):
                 if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         mx = max((int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()), default=0)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_mhz_min": sm[0] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(self.rows), "power_w_max": max(pw) if pw else None, "via": self.via}
 
 
 def host_threads():
