@@ -51,6 +51,8 @@ typedef struct _spleeter* spleeter;
 size_t getCoeffSize(void);
 void* allocateSpleeterStr(void);
 /* width = analyseBinLimit (F), height = timeStep (T); stemMode 0: LeakyReLU/ReLU, else ELU.
+ * Callers compiled against the VST flavour's prototype (int width, int height: VST/Source/spleeter.h:4) bind to the same symbol:
+ * only the low 32 bits of the two sizes are used.
  * Both must be multiples of 64 (six halvings), 64 <= width <= 2048: other sizes - which the reference CLI merely warns
  * about, main.c:739-742 - end the process with exit status 2 and a message naming the restriction.  CUDA failures
  * (there is no error channel in this API) print the reason and abort().

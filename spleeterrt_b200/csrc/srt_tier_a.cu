@@ -27,6 +27,11 @@ extern "C" void* allocateSpleeterStr(void) { return calloc(1, sizeof(struct _spl
 
 extern "C" void initSpleeter(struct _spleeter* nn, size_t width, size_t height, int stemMode, void* coeff)
 {
+    // One symbol for both of the reference's ABIs: Executable/spleeter.h:66 declares the sizes as size_t, VST/Source/spleeter.h:4 as
+    // int.  An int caller leaves the upper halves of the two 64-bit argument registers undefined (SysV x86-64), so only the low 32
+    // bits are looked at; no valid size needs more.
+    width &= 0xffffffffu;
+    height &= 0xffffffffu;
     srt_config cfg;
     memset(&cfg, 0, sizeof cfg);
     const char* dev = getenv("SRT_DEVICE");

@@ -146,10 +146,11 @@ def test_unet_golden(srt, oracle):
 
 
 def test_tier_a_process_spleeter(srt, oracle, small_nets):
-    """The reference's own entry points (spleeter.h) through the shared library."""
+    """The reference's own entry points (spleeter.h) through the shared library.  The sizes are passed with garbage in their upper
+    32 bits, as a caller compiled against the VST flavour's `int width, int height` prototype may leave them."""
     lib = srt.load_library()
     lib.allocateSpleeterStr.restype = C.c_void_p
-    lib.initSpleeter.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p]
+    lib.initSpleeter.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     lib.getMaskPtr.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_float))]
     lib.processSpleeter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.freeSpleeter.argtypes = [C.c_void_p]
@@ -157,7 +158,7 @@ def test_tier_a_process_spleeter(srt, oracle, small_nets):
     coeff, mode = small_nets[1]
     x = (np.abs(np.random.default_rng(1).standard_normal((2, T, F))) * 3).astype(np.float32)
     nn = lib.allocateSpleeterStr()
-    lib.initSpleeter(nn, F, T, mode, coeff.ctypes.data)
+    lib.initSpleeter(nn, F | (0xdeadbeef << 32), T | (0x7fff1234 << 32), mode, coeff.ctypes.data)
     mp = C.POINTER(C.c_float)()
     lib.getMaskPtr(nn, C.byref(mp))
     lib.processSpleeter(nn, x.ctypes.data, C.cast(mp, C.c_void_p))
@@ -443,9 +444,13 @@ def test_unet_vst_flavour(srt, oracle, small_nets):
     y = sep.process_spleeter(x)[0, 0]
     sep.close()
     ref = oracle.unet(coeff, x, 1, flavour=1)
-    # white-noise input, no LUT clipping of the tails: a float64 emulation of TF32 operand rounding on this very
-    # input gives 6.0e-4 mask RMS against the oracle, so the bound is 1e-3 here (5e-4 elsewhere)
-    assert rms(y - ref) < 1e-3 and np.abs(y - ref).max() < 3e-2
+    # white-noise input, no LUT clipping of the tails: single-pass TF32 operands gave 6.0e-4 mask RMS here (float64 emulation and
+    # round 1's GPU path); the default compensated precision has to stay an order of magnitude under that
+    assert rms(y - ref) < 1e-4 and np.abs(y - ref).max() < 5e-3
+    fast = srt.Separator([(coeff, 1)], T, F, max_images=1, flavour=1, precision="tf32")
+    yf = fast.process_spleeter(x)[0, 0]
+    fast.close()
+    assert rms(yf - ref) < 1e-3 and np.abs(yf - ref).max() < 3e-2
 
 
 @pytest.mark.parametrize("block", [1024, 512, 300])
