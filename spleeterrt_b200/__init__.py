@@ -8,4 +8,4 @@ PyTorch fallback — if the library or a B200 is missing, calls raise.
 from .api import (COEFF_FLOATS, FFTSIZE, HOPSIZE, BINS, Separator, CliSeparator, Streamer, SrtError, half_to_float,  # noqa: F401
                   load_coeff_dat, save_coeff_dat, load_model_fp16, pack_layer, resample_plan,
                   lib_path, load_library, exported_symbols, HEADER_SYMBOLS, DISPATCH_SYMBOLS, dispatch_lib_path, load_dispatch_library,
-                  dispatch_schedule, NcclDispatcher, probe_tensor_peak, probe_copy_bandwidth)
+                  dispatch_schedule, NcclDispatcher, probe_tensor_peak, probe_copy_bandwidth, pinned_empty)

@@ -269,6 +269,33 @@ def probe_copy_bandwidth(nbytes=1 << 30, device=0):
     return out.value
 
 
+def pinned_empty(shape, dtype=np.float32):
+    """A numpy array in page-locked host memory (srt_host_alloc).  Hand such arrays to separate_async() / separate_raw_async():
+    cudaMemcpyAsync from pageable memory is staged synchronously by the driver, which silently turns the three-batch
+    pipeline into blocking copies.  The memory is released when the array (and every view of it) is garbage-collected."""
+    lib = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    lib.srt_host_alloc.restype = C.c_void_p
+    lib.srt_host_alloc.argtypes = [C.c_size_t]
+    lib.srt_host_free.argtypes = [C.c_void_p]
+    p = lib.srt_host_alloc(max(n, 1))
+    if not p:
+        raise SrtError("srt_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.srt_host_free(self.ptr)
+            except Exception:
+                pass
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    buf._owner = _Owner(p)                      # the ctypes buffer keeps the allocation alive; numpy keeps the buffer
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 def half_to_float(halves):
     """fp16 model blob -> fp32, denormals as zero (f32Decompress, main.c:423-434)."""
     h = np.ascontiguousarray(halves, dtype=np.uint16)
@@ -451,13 +478,15 @@ class Separator:
 
     def separate_async(self, streams, unaffected=None):
         """Like separate(), but only enqueues the batch (srt_separate_batch_async).  Returns a pending handle;
-        result(handle) waits and returns the stems.  Up to three batches are in flight per Separator; a fourth submit first drains the oldest."""
+        result(handle) waits and returns the stems.  Up to three batches are in flight per Separator; a fourth submit first drains the oldest.
+        The copies overlap the kernels only for page-locked buffers: pass streams allocated with pinned_empty() (outputs are
+        allocated that way here); pageable numpy arrays still work but their H2D copies are staged synchronously."""
         ns = len(streams)
         Ls, Rs = self._channels(streams)
         n = (C.c_size_t * ns)(*[l.size for l in Ls])
         pl = (C.c_void_p * ns)(*[l.ctypes.data for l in Ls])
         pr = (C.c_void_p * ns)(*[r.ctypes.data for r in Rs])
-        outs = [np.empty((self.S, 2, l.size), np.float32) for l in Ls]
+        outs = [pinned_empty((self.S, 2, l.size), np.float32) for l in Ls]
         po = (C.c_void_p * (ns * self.S * 2))(*[o[s, c].ctypes.data for o in outs for s in range(self.S) for c in range(2)])
         uw = (C.c_float * self.S)(*[float(u) for u in unaffected]) if unaffected is not None else None
         ticket = self.separate_raw_async(pl, pr, n, ns, uw, po)
