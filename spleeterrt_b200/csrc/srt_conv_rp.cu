@@ -162,7 +162,9 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
                     ptx::mbar_wait(&hdr->patch_empty[ps], pph ^ 1);
                     if (p.dbg & 4) { ptx::mbar_arrive(&hdr->patch_full[ps]); }
                     else {
-                    ptx::mbar_arrive_expect_tx(&hdr->patch_full[ps], kPatchBytes);
+                    // a chunk of 64-channel e5m2 residuals (kPartLo8n) has 64-byte rows: half the patch bytes
+                    const bool narrow = KB == 32 && (hdr->kb[ch.kb0].part & kPartLo8n);
+                    ptx::mbar_arrive_expect_tx(&hdr->patch_full[ps], narrow ? kPatchBytes / 2 : kPatchBytes);
                     ptx::tma_load_4d(patch + (size_t)ps * kPatchBytes, &p.tmap[ch.src], &hdr->patch_full[ps], ch.c_off, tl.x0 - 1, tl.y0 - 1, p.src_img0 + tl.n);
                     }
                     if (++ps == 2) { ps = 0; pph ^= 1; }
@@ -205,24 +207,30 @@ __global__ void __launch_bounds__((EPW + 3) * 32, 1) conv_rp_kernel(const __grid
                     const uint32_t p_lo = ptx::umma_desc_lo(patch_base + (uint32_t)ps * kPatchBytes);
                     for (int k = ch.kb0; k < ch.kb0 + ch.nkb; k++) {
                         const KBlock kb = hdr->kb[k];
-                        // descriptor low word of the tap's window for row r = 0, K step 0 (16-byte units)
-                        const uint32_t a_lo = p_lo + (uint32_t)((kb.dy + 1) * (kRowPitch >> 4) + (kb.dx + 1) * (kRowBytes >> 4));
+                        // descriptor low word of the tap's window for row r = 0, K step 0 (16-byte units); rows of a narrow chunk are 64 bytes
+                        const bool narrow = KB == 32 && (kb.part & kPartLo8n);
+                        const uint32_t pitch16 = narrow ? (uint32_t)(kRowPitch >> 5) : (uint32_t)(kRowPitch >> 4);
+                        const uint32_t a_lo = p_lo + (uint32_t)(kb.dy + 1) * pitch16 + (uint32_t)(kb.dx + 1) * (narrow ? (uint32_t)(kRowBytes >> 5) : (uint32_t)(kRowBytes >> 4));
                         const uint32_t b_lo = ptx::umma_desc_lo(wring_base + (uint32_t)ws * kWBytes);
                         ptx::mbar_wait(&hdr->w_full[ws], wph);
                         ptx::tc_fence_after();
                         if (!(p.dbg & 2)) {
                             const int skip = KB == 32 ? kb_skip_mask(kb) : 0;
                             const bool lo = KB == 32 && (kb.part & kPartLo), lo8 = lo && (kb.part & kPartLo8);
-                            if (skip == 0 && !(p.dbg & 256)) {           // the common case without a jump table in the issuing thread's path
-                                if (lo8) rp_issue<N, R, KB / 8, 2, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
-                                else if (lo) rp_issue<N, R, KB / 8, 1, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
-                                else rp_issue<N, R, KB / 8, 0, 0>(acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                            if (narrow) {                                // 64 e5m2 residuals per pixel: two K = 32 steps over 64-byte rows (SWIZZLE_64B)
+                                if (skip == 0) rp_issue<N, R, 2, 2, 0>(acc, a_lo, b_lo, pitch16, idesc_lo, ptx::kDescHiSw64, first);
+                                else if (skip == 1) rp_issue<N, R, 2, 2, 1>(acc, a_lo, b_lo, pitch16, idesc_lo, ptx::kDescHiSw64, first);
+                                else rp_issue<N, R, 2, 2, 2>(acc, a_lo, b_lo, pitch16, idesc_lo, ptx::kDescHiSw64, first);
+                            } else if (skip == 0 && !(p.dbg & 256)) {    // the common case without a jump table in the issuing thread's path
+                                if (lo8) rp_issue<N, R, KB / 8, 2, 0>(acc, a_lo, b_lo, pitch16, idesc_lo, kDescHi, first);
+                                else if (lo) rp_issue<N, R, KB / 8, 1, 0>(acc, a_lo, b_lo, pitch16, idesc_lo, kDescHi, first);
+                                else rp_issue<N, R, KB / 8, 0, 0>(acc, a_lo, b_lo, pitch16, idesc, kDescHi, first);
                             } else if (lo8)
-                                rp_issue_masked<N, R, KB / 8, 2>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                                rp_issue_masked<N, R, KB / 8, 2>(skip, acc, a_lo, b_lo, pitch16, idesc_lo, kDescHi, first);
                             else if (lo)
-                                rp_issue_masked<N, R, KB / 8, 1>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc_lo, kDescHi, first);
+                                rp_issue_masked<N, R, KB / 8, 1>(skip, acc, a_lo, b_lo, pitch16, idesc_lo, kDescHi, first);
                             else
-                                rp_issue_masked<N, R, KB / 8, 0>(skip, acc, a_lo, b_lo, (uint32_t)(kRowPitch >> 4), idesc, kDescHi, first);
+                                rp_issue_masked<N, R, KB / 8, 0>(skip, acc, a_lo, b_lo, pitch16, idesc, kDescHi, first);
                         }
                         ptx::mma_commit(&hdr->w_empty[ws]);
                         if (++ws == WS) { ws = 0; wph ^= 1; }

@@ -83,17 +83,18 @@ static int make_tmap(CUtensorMap* m, const float* base, int C, int W, int H, int
 }
 
 // bf16 residual tensor [n][H][W][C] of a compensated layer -> 4-D map, box {64, tw, th, nb} = the same 128-byte swizzled rows
-static int make_tmap_lo(CUtensorMap* m, const void* base, int C, int W, int H, int N, int tw, int th, int nb, bool fp8)
+static int make_tmap_lo(CUtensorMap* m, const void* base, int C, int W, int H, int N, int tw, int th, int nb, int lo_fmt)
 {
-    const int esize = fp8 ? 1 : 2;            // e5m2 bytes, 128 channels per box row - or bf16, 64
+    const bool fp8 = lo_fmt == LO_FP8 || lo_fmt == LO_FP8N, narrow = lo_fmt == LO_FP8N;
+    const int esize = fp8 ? 1 : 2;            // e5m2 bytes, 128 (narrow: 64, in 64-byte rows) channels per box row - or bf16, 64
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * esize, (cuuint64_t)W * C * esize, (cuuint64_t)H * W * C * esize};
-    cuuint32_t box[4] = {(cuuint32_t)(fp8 ? kKBlo8 : kKBlo), (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
+    cuuint32_t box[4] = {(cuuint32_t)(narrow ? 64 : fp8 ? kKBlo8 : kKBlo), (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, fp8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     narrow ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SRT_ERR_CUDA, "cuTensorMapEncodeTiled (bf16 residual) failed (%d) C=%d W=%d H=%d N=%d box=%d,%d,%d", (int)r, C, W, H, N, tw, th, nb);
     return 0;
 }
@@ -180,7 +181,10 @@ struct srt_ctx {
     int lo_want = LO_BF16;         // residual format asked for; layer i uses layer_lo_format(i, lo_want)
     uint8_t* Alo[6]{};             // Alo[i]: residual of A[i] (same S2D layout), read by down{i+1}: bf16 or e5m2 bytes (the consumer's format)
     uint8_t* Clo[5]{};             // Clo[d], d = 1..4: [skip E{6-d} | up U{d}] residuals per pixel, read by up{d+1}; Clo[0]: E6's, read by up1
-    int lo_fmt_of(int layer) const { return ((comp_mask >> layer) & 1u) ? layer_lo_format(layer, lo_want) : LO_NONE; }
+    bool will_rp[10]{};            // the layer runs in the row-patch kernel (decided before anything is allocated: it selects the format)
+    bool lo_narrow_off = false;    // SRT_LO_NARROW=0: down2 / up5 keep bf16 residuals (A/B timing)
+    int lo_fmt_of(int layer) const { return ((comp_mask >> layer) & 1u) ? layer_lo_format(layer, lo_want, will_rp[layer] && !lo_narrow_off) : LO_NONE; }
+    bool lo_is_fp8(int layer) const { const int f = lo_fmt_of(layer); return f == LO_FP8 || f == LO_FP8N; }
     // batch buffers
     float* d_mag = nullptr;       // [NB][T/2][F/2][(py,px)][c] space-to-depth, TF32-rounded
     float4* d_spec = nullptr;     // [NB][T][2049]
@@ -400,15 +404,25 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     c->comp_mask = prec == SRT_PRECISION_TF32 ? 0u : 0x3ffu;
     c->lo_want = prec == SRT_PRECISION_COMPENSATED ? LO_FP8 : LO_BF16;
     if (const char* me = getenv("SRT_COMP_MASK")) c->comp_mask = (unsigned)strtoul(me, nullptr, 0) & 0x3ffu;   // experiments: per-layer selection
+    // which layers run in the row-patch kernel (SRT_CONV_RP: "0" = never, "1" = whenever supported, unset = when the tile row is wide enough to pay)
+    {
+        const char* rpe = getenv("SRT_CONV_RP");
+        c->lo_narrow_off = getenv("SRT_LO_NARROW") && atoi(getenv("SRT_LO_NARROW")) == 0;
+        for (int li = 0; li < 10; li++) {
+            if (!row_plan_supported(li) || c->cfg.conv_impl == 1) continue;
+            const RowPlan rpl = build_row_plan(NetGeom{T, F}, li, false, false);
+            c->will_rp[li] = (rpe ? atoi(rpe) != 0 : rpl.Ws >= 96);
+        }
+    }
     for (int i = 1; i <= 5; i++)
         if (c->lo_fmt_of(i - 1) != LO_NONE) {
-            const size_t bytes = act_floats(c, i, kEnc[i]) * (c->lo_fmt_of(i - 1) == LO_FP8 ? 1 : 2);
+            const size_t bytes = act_floats(c, i, kEnc[i]) * (c->lo_is_fp8(i - 1) ? 1 : 2);
             if ((r = dalloc(c, &c->Alo[i], bytes))) return r;
             CK(cudaMemset(c->Alo[i], 0, bytes));
         }
     for (int d = 0; d <= 4; d++)
         if (c->lo_fmt_of(5 + d) != LO_NONE) {
-            const size_t bytes = act_floats(c, 6 - d, d == 0 ? 512 : 2 * kEnc[6 - d]) * (c->lo_fmt_of(5 + d) == LO_FP8 ? 1 : 2);
+            const size_t bytes = act_floats(c, 6 - d, d == 0 ? 512 : 2 * kEnc[6 - d]) * (c->lo_is_fp8(5 + d) ? 1 : 2);
             if ((r = dalloc(c, &c->Clo[d], bytes))) return r;
             CK(cudaMemset(c->Clo[d], 0, bytes));
         }
@@ -577,9 +591,9 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             const int dcons = 5 - i;            // Clo index of the decoder layer that reads E{i+1}
             if (c->Clo[dcons]) {
                 p.lo_raw = c->Clo[dcons]; p.lo_raw_C = dcons == 0 ? 512 : 2 * L.cout; p.lo_raw_coff = 0;
-                p.lo_raw_fp8 = c->lo_fmt_of(5 + dcons) == LO_FP8;
+                p.lo_raw_fp8 = c->lo_is_fp8(5 + dcons);
             }
-            if (L.index < 4 && c->Alo[i + 1]) { p.lo_act = c->Alo[i + 1]; p.lo_act_fp8 = c->lo_fmt_of(L.index + 1) == LO_FP8; }
+            if (L.index < 4 && c->Alo[i + 1]) { p.lo_act = c->Alo[i + 1]; p.lo_act_fp8 = c->lo_is_fp8(L.index + 1); }
             if (L.comp) { p.lo_ptr = c->Alo[i]; p.lo_C = 4 * L.cin; p.lo_fp8 = L.lo_fmt == LO_FP8; }
         } else {
             const int d = L.index - 5;          // up{d+1}
@@ -590,7 +604,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             p.round_act = (d < 4) ? 1 : 0;      // up5 feeds the SIMT up6 kernel: keep fp32
             if (d < 4 && c->Clo[d + 1]) {       // U{d+1}: second half of up{d+2}'s residuals
                 p.lo_dec = c->Clo[d + 1]; p.lo_dec_C = 2 * L.cout; p.lo_dec_coff = L.cout;
-                p.lo_dec_fp8 = c->lo_fmt_of(5 + d + 1) == LO_FP8;
+                p.lo_dec_fp8 = c->lo_is_fp8(5 + d + 1);
             }
             if (L.comp) { p.lo_ptr = c->Clo[d]; p.lo_C = L.cin; p.lo_fp8 = L.lo_fmt == LO_FP8; }
         }
@@ -601,7 +615,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
         }
         if (L.nsrc == 1) p.tmap[1] = p.tmap[0];
         p.tmap[2] = p.tmap[0];                  // always a valid descriptor (the kernels prefetch all three)
-        if (L.comp && (r = make_tmap_lo(&p.tmap[2], p.lo_ptr, L.lo_src.C, L.lo_src.W, L.lo_src.H, S * c->B, L.tw, L.th, L.nb, L.lo_fmt == LO_FP8))) return r;
+        if (L.comp && (r = make_tmap_lo(&p.tmap[2], p.lo_ptr, L.lo_src.C, L.lo_src.W, L.lo_src.H, S * c->B, L.tw, L.th, L.nb, L.lo_fmt))) return r;
     }
     // ---- row-patch variants of the small-N layers ------------------------------------------
     // SRT_CONV_RP: "0" = never, "1" = whenever supported, unset = when the tile row is wide enough to pay
@@ -609,9 +623,16 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
     const char* boe = getenv("SRT_RP_BO");
     for (size_t li = 0; li < c->plans.size(); li++) {
         if (!row_plan_supported((int)li) || c->cfg.conv_impl == 1) continue;
-        const RowPlan rpl = build_row_plan(NetGeom{T, F}, (int)li, c->split_weights, c->plans[li].comp, c->lo_want);
-        const bool want = rpe ? atoi(rpe) != 0 : rpl.Ws >= 96;
-        if (!want || !conv_rp_fits((int)rpl.chunks.size(), (int)rpl.kb.size())) continue;
+        if (!c->will_rp[li]) continue;
+        // the residual format was fixed when the tensors were allocated: the row-patch plan has to agree with it
+        const int lf = c->lo_fmt_of((int)li);
+        const RowPlan rpl = build_row_plan(NetGeom{T, F}, (int)li, c->split_weights, c->plans[li].comp, lf == LO_BF16 ? LO_BF16 : LO_FP8);
+        const bool narrow = rpl.comp && rpl.lo_fmt == LO_FP8N;
+        if (rpl.comp && rpl.lo_fmt != lf) return fail(SRT_ERR_STATE, "layer %zu: residual format mismatch (%d vs %d)", li, rpl.lo_fmt, lf);
+        if (!conv_rp_fits((int)rpl.chunks.size(), (int)rpl.kb.size())) {
+            if (narrow) return fail(SRT_ERR_STATE, "layer %zu: row-patch tables do not fit and its residuals are in the row-patch-only format", li);
+            continue;
+        }
         RowConvParams& q = c->rp[li];
         std::memset(&q, 0, sizeof q);
         std::vector<float> wpk((size_t)S * rpl.w_floats_per_stem);
@@ -634,7 +655,8 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             if (make_tmap(&q.tmap[k], c->conv[li].src_ptr[k], rpl.src[k].C, rpl.src[k].W, rpl.src[k].H, S * c->B, kPatchW, rpl.R + 2, 1)) ok = false;
         if (rpl.nsrc == 1) q.tmap[1] = q.tmap[0];
         q.tmap[2] = q.tmap[0];
-        if (ok && rpl.comp && make_tmap_lo(&q.tmap[2], c->conv[li].lo_ptr, rpl.lo_src.C, rpl.lo_src.W, rpl.lo_src.H, S * c->B, kPatchW, rpl.R + 2, 1, rpl.lo_fmt == LO_FP8)) ok = false;
+        if (ok && rpl.comp && make_tmap_lo(&q.tmap[2], c->conv[li].lo_ptr, rpl.lo_src.C, rpl.lo_src.W, rpl.lo_src.H, S * c->B, kPatchW, rpl.R + 2, 1, rpl.lo_fmt)) ok = false;
+        if (!ok && narrow) return fail(SRT_ERR_CUDA, "layer %zu: row-patch tensor map rejected (%s)", li, g_err.c_str());
         if (!ok) { fprintf(stderr, "[spleeterrt_b200] row-patch tensor map rejected for layer %zu (%s); using the generic kernel\n", li, g_err.c_str()); continue; }
         c->use_rp[li] = true;
     }
@@ -672,7 +694,7 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             e.round_raw = 0;            // the skip feeds the fp32 SIMT up6 kernel
             e.round_act = 1;
             e.lo_act = c->Alo[1];       // residual of A1 for a compensated down2 (nullptr otherwise)
-            e.lo_act_fp8 = c->lo_fmt_of(0) == LO_FP8;
+            e.lo_act_fp8 = c->lo_is_fp8(0);
             if (make_tmap(&q.tmap[0], c->d_mag, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1) ||
                 make_tmap(&q.tmap[1], c->d_mag + (size_t)c->NB * T * F * 2, 8, F / 2, T / 2, c->NB, kPatchW, q.R + 2, 1, kKB1)) {
                 fprintf(stderr, "[spleeterrt_b200] down1 tensor map rejected (%s); using the SIMT kernel\n", g_err.c_str());

@@ -96,12 +96,13 @@ float e5m2_to_float(uint8_t b)
     return (b & 0x80) ? -v : v;
 }
 
-int layer_lo_format(int index, int want)
+int layer_lo_format(int index, int want, bool row_patch)
 {
     if (want != LO_FP8) return want;
     // residual channels per pixel: encoder 4 * cin (space-to-depth), decoder cin ([skip | up]); down2 = 64, up5 = 64
     const int C = index < 5 ? 4 * kEnc[index + 1] : kDecIn[index - 5];
-    return (C % kKBlo8 == 0) ? LO_FP8 : LO_BF16;
+    if (C % kKBlo8 == 0) return LO_FP8;
+    return (row_patch && C == 64) ? LO_FP8N : LO_BF16;
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -494,12 +495,13 @@ RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp
     }
     // compensation chunks: 64-channel slabs of the bf16 residual tensor, same taps, bf16 weights (see build_plans)
     L.comp = comp;
-    L.lo_fmt = comp ? layer_lo_format(layer_index, lo_fmt) : LO_NONE;
+    L.lo_fmt = comp ? layer_lo_format(layer_index, lo_fmt, true) : LO_NONE;
     if (comp) {
         const int Clo = L.transposed ? L.cin : 4 * L.cin;
         L.lo_src = SrcDesc{Clo, L.Ws, L.Hs};
-        const int kKBlo = L.lo_fmt == LO_FP8 ? kKBlo8 : srt::kKBlo;
-        const int8_t kPartLo = (int8_t)(L.lo_fmt == LO_FP8 ? (srt::kPartLo | kPartLo8) : srt::kPartLo);
+        const int kKBlo = L.lo_fmt == LO_FP8 ? kKBlo8 : srt::kKBlo;                     // LO_FP8N and bf16: 64 channels per block
+        const int8_t kPartLo = (int8_t)(L.lo_fmt == LO_FP8 ? (srt::kPartLo | kPartLo8)
+                                        : L.lo_fmt == LO_FP8N ? (srt::kPartLo | kPartLo8 | kPartLo8n) : srt::kPartLo);
         for (int c_off = 0; c_off < Clo; c_off += kKBlo) {
             RowChunk ch{(int8_t)kSrcLo, c_off, (int32_t)L.kb.size(), 0};
             for (int dy = -1; dy <= 1; dy++)
@@ -530,9 +532,9 @@ RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp
     L.ke_off = kelem_offsets(L.kb);
     // K steps without any weight (see kPartSkipShift): quarter q of k-block k = elements [q * width / 4, (q + 1) * width / 4)
     for (size_t k = 0; k < L.kb.size(); k++) {
-        const int width = kb_channels(L.kb[k]), per = width / 4;
+        const int steps = kb_ksteps(L.kb[k]), width = kb_channels(L.kb[k]), per = width / steps;
         int skip = 0;
-        for (int q = 0; q < 4; q++) {
+        for (int q = 0; q < steps; q++) {
             bool any = false;
             for (int j = q * per; j < (q + 1) * per; j++) {
                 const KElemP& e = L.kelem[L.ke_off[k] + j];
@@ -540,7 +542,7 @@ RowPlan build_row_plan(NetGeom g, int layer_index, bool split_weights, bool comp
             }
             if (!any) skip |= 1 << q;
         }
-        if (skip != 0xf) L.kb[k].part = (int8_t)((L.kb[k].part & 0xf) | (skip << kPartSkipShift));
+        if (skip != (1 << steps) - 1) L.kb[k].part = (int8_t)((L.kb[k].part & 0xf) | (skip << kPartSkipShift));
     }
     L.R = row_plan_R(L.N);
     L.w_floats_per_stem = L.kb.size() * (size_t)L.N * kKB;
@@ -565,7 +567,8 @@ void pack_row_layer(const RowPlan& L, const float* coeff, float* out)
                                                     : (((size_t)o * L.cin + e.cin) * 5 + e.kh[ph]) * 5 + e.kw[ph];
                     v = lo ? w[idx] : weight_part(w[idx], L.kb[kb].part);
                 }
-                if (lo8) reinterpret_cast<uint8_t*>(blk)[swz128_index8(n, j)] = e5m2_rn(0.25f * v);
+                if (lo8 && (L.kb[kb].part & kPartLo8n)) reinterpret_cast<uint8_t*>(blk)[swz64_index8(n, j)] = e5m2_rn(0.25f * v);
+                else if (lo8) reinterpret_cast<uint8_t*>(blk)[swz128_index8(n, j)] = e5m2_rn(0.25f * v);
                 else if (lo) reinterpret_cast<uint16_t*>(blk)[swz128_index16(n, j)] = bf16_rn(v);
                 else blk[swz128_index(n, j)] = v;
             }

@@ -55,9 +55,13 @@ SRT_HD inline int kb_skip_mask(const KBlock& kb) { return ((unsigned char)kb.par
 // 1/4 keep both operands inside e5m2's normal range (residuals of |a| >= 2^-4, weights >= 2^-12); smaller ones fade out.
 constexpr int kPartLo8 = 4;
 constexpr int kKBlo8 = 128;
+// bit 3 (with bits 1, 2; row-patch plans only): the 8-bit block is 64 channels wide - a residual tensor with 64 channels per pixel
+// (down2's, up5's) - in 64-byte rows (SWIZZLE_64B), two K = 32 steps.
+constexpr int kPartLo8n = 8;
 constexpr int kSrcLo = 2;               // KBlock::src / RowChunk::src of the residual tensor
-SRT_HD inline int kb_channels(const KBlock& kb) { return (kb.part & kPartLo) ? ((kb.part & kPartLo8) ? kKBlo8 : kKBlo) : kKB; }
-enum LoFormat : int { LO_NONE = 0, LO_BF16 = 1, LO_FP8 = 2 };
+SRT_HD inline int kb_channels(const KBlock& kb) { return (kb.part & kPartLo) ? ((kb.part & kPartLo8n) ? 64 : (kb.part & kPartLo8) ? kKBlo8 : kKBlo) : kKB; }
+SRT_HD inline int kb_ksteps(const KBlock& kb) { return (kb.part & kPartLo8n) ? 2 : 4; }     // MMAs (K steps) per k-block and accumulator row
+enum LoFormat : int { LO_NONE = 0, LO_BF16 = 1, LO_FP8 = 2, LO_FP8N = 3 };
 
 // For the weight packer: where k-element j of a k-block comes from.
 struct KElem {
@@ -124,9 +128,9 @@ CoeffLayout coeff_layout();
 // term).  Operand error drops from 2^-12 to ~2^-19 relative: fp32-grade results for 1.5x the tensor work.
 std::vector<LayerPlan> build_plans(NetGeom g, int n_img, bool split_weights = false, int n_stems = 1, int min_ctas = 0, unsigned comp_mask = 0,
                                    bool fuse_phases = true, int lo_fmt = LO_BF16);
-// the residual format layer `index` (0..9) uses when `want` is asked for: LO_FP8 only where the residual tensor has a multiple of 128
-// channels per pixel (everything but down2 and up5, whose 64 channels stay bf16)
-int layer_lo_format(int index, int want);
+// the residual format layer `index` (0..9) uses when `want` is asked for: LO_FP8 where the residual tensor has a multiple of 128
+// channels per pixel; down2's and up5's have 64: LO_FP8N (64-byte rows) in the row-patch kernel, bf16 in the generic one
+int layer_lo_format(int index, int want, bool row_patch = false);
 // transposed conv: the kernel row that serves output parity `par` at input offset d (o = 2h + kh - 1), or -1
 int dec_kh(int par, int d);
 
@@ -212,5 +216,7 @@ SRT_HD inline int swz128_index(int row, int j) { return row * 32 + ((((j >> 2) ^
 SRT_HD inline int swz128_index16(int row, int j) { return row * 64 + ((((j >> 3) ^ (row & 7)) << 3) | (j & 7)); }
 // and for a [rows][128] block of bytes (16-byte chunks of 16 elements)
 SRT_HD inline int swz128_index8(int row, int j) { return row * 128 + ((((j >> 4) ^ (row & 7)) << 4) | (j & 15)); }
+// a [rows][64] block of bytes in SWIZZLE_64B (chunk index ^= address bits 7-8 = (row >> 1) & 3)
+SRT_HD inline int swz64_index8(int row, int j) { return row * 64 + ((((j >> 4) ^ ((row >> 1) & 3)) << 4) | (j & 15)); }
 
 }  // namespace srt

@@ -48,7 +48,7 @@ static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const 
             for (int c = 0; c < C; c++) {
                 float& a = src[q][px * C + c];
                 const float hi = round_tf32(a);
-                lo[px * lo_sd.C + coff + c] = lo_fmt == LO_FP8 ? e5m2_to_float(e5m2_rn(4.0f * (a - hi))) : bf16_to_float(bf16_rn(a - hi));
+                lo[px * lo_sd.C + coff + c] = (lo_fmt == LO_FP8 || lo_fmt == LO_FP8N) ? e5m2_to_float(e5m2_rn(4.0f * (a - hi))) : bf16_to_float(bf16_rn(a - hi));
                 a = hi;
             }
         coff += C;
@@ -57,6 +57,7 @@ static void split_sources(std::vector<std::vector<float>>& src, int nsrc, const 
 // weight of a compensation block as the MMA reads it
 static float lo_weight(const KBlock& kb, const float* wb, int n, int j)
 {
+    if (kb.part & kPartLo8n) return e5m2_to_float(reinterpret_cast<const uint8_t*>(wb)[swz64_index8(n, j)]);
     if (kb.part & kPartLo8) return e5m2_to_float(reinterpret_cast<const uint8_t*>(wb)[swz128_index8(n, j)]);
     return bf16_to_float(reinterpret_cast<const uint16_t*>(wb)[swz128_index16(n, j)]);
 }
@@ -211,9 +212,9 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
     const int Hout = L.transposed ? 2 * H : H, Wout = L.transposed ? 2 * W : W;
     // K steps the MMA issuer skips (kPartSkipShift) must hold nothing but zero weights, and the model below honours the mask
     for (size_t k = 0; k < L.kb.size(); k++) {
-        const int width = kb_channels(L.kb[k]), per = width / 4, skip = kb_skip_mask(L.kb[k]);
+        const int steps = kb_ksteps(L.kb[k]), width = kb_channels(L.kb[k]), per = width / steps, skip = kb_skip_mask(L.kb[k]);
         const bool is_lo = (L.kb[k].part & kPartLo) != 0;
-        for (int q = 0; q < 4; q++)
+        for (int q = 0; q < steps; q++)
             if (skip & (1 << q))
                 for (int n = 0; n < L.N; n++)
                     for (int j = q * per; j < (q + 1) * per; j++) {
@@ -243,13 +244,14 @@ extern "C" int srt_host_model_row_layer(int T, int F, int plan_index, const floa
                             if (kb.part & kPartLo) {
                                 const int width = kb_channels(kb);
                                 if (!L.comp || ch.src != kSrcLo || kb.c_off + width > L.lo_src.C) return -2;
-                                if (((kb.part & kPartLo8) != 0) != (L.lo_fmt == LO_FP8)) return -7;
+                                if (((kb.part & kPartLo8) != 0) != (L.lo_fmt == LO_FP8 || L.lo_fmt == LO_FP8N)) return -7;
+                                if (((kb.part & kPartLo8n) != 0) != (L.lo_fmt == LO_FP8N)) return -7;
                                 if (g_comp_drop) continue;
                                 const float* a = &lo[((size_t)yy * W + xx) * L.lo_src.C + kb.c_off];
                                 for (int n = 0; n < L.N; n++) {
                                     float s = 0.f;
                                     for (int j = 0; j < width; j++)
-                                        if (!(kb_skip_mask(kb) & (1 << (j / (width / 4))))) s += a[j] * lo_weight(kb, wb, n, j);
+                                        if (!(kb_skip_mask(kb) & (1 << (j / (width / kb_ksteps(kb)))))) s += a[j] * lo_weight(kb, wb, n, j);
                                     acc[n] += s;
                                 }
                                 continue;

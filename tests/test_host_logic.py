@@ -188,14 +188,14 @@ def test_fp8_compensation_tables(oracle, host_model, small_nets, mode):
     for fmt in (3, 1, 2):                     # fp8, bf16, rounded without compensation
         host_model.srt_host_model_set_comp(fmt)
         try:
-            for i in (2, 3):                  # down3 (row-patch and generic), down4
+            for i in (1, 2, 3):               # down2 (row-patch: 64-channel e5m2 blocks in 64-byte rows), down3 (both forms), down4
                 bn = v[f"down{i}.bn"]
                 act_in = _act(a_enc, bn[1][:, None, None] * taps[f"skip{i}"] + bn[0][:, None, None]).astype(np.float32)
                 ref = taps[f"skip{i+1}"]
-                for row in ([False, True] if i == 2 else [False]):
+                for row in ([True] if i == 1 else [False, True] if i == 2 else [False]):
                     got = _run_layer(host_model, T, F, i - 1, coeff, a_enc, act_in, None, ref.shape, row=row)
                     errs[(f"down{i+1}", row, fmt)] = rms_rel(got, ref)
-            for d, rows in ((1, [False]), (2, [False]), (3, [False, True])):      # up2, up3 (fused parities), up4 (both forms)
+            for d, rows in ((1, [False]), (2, [False]), (3, [False, True]), (4, [True])):      # up2, up3 (fused parities), up4 (both forms), up5 (row-patch, narrow blocks)
                 ref = taps[f"up{d+1}"]
                 for row in rows:
                     got = _run_layer(host_model, T, F, 5 + d, coeff, a_dec, taps[f"skip{6-d}"], taps[f"up{d}"], ref.shape, row=row)
