@@ -56,8 +56,7 @@ typedef struct {
     int precision;         /* arithmetic of the ten tensor-core layers (accumulation is fp32 in all):
                             *   0 = SRT_PRECISION_COMPENSATED (default): activations feed the MMAs as tf32(a) PLUS the residual
                             *       a - tf32(a) (a second, smaller contraction into the same accumulator).  The residual travels in
-                            *       8 bits (e5m2) where the layer's residual tensor has >= 128 channels per pixel and as bf16 in the
-                            *       two layers where it has 64: operand error 2^-12 -> ~2^-16, about what the tensor core's own
+                            *       8 bits (e5m2, scaled by 4): operand error 2^-12 -> ~2^-16, about what the tensor core's own
                             *       accumulation adds; stems agree with the fp32 reference to a few 1e-6 RMS at any input level;
                             *   2 = SRT_PRECISION_COMPENSATED_BF16: all residuals in bf16 (operand error ~2^-19; ~6 % slower);
                             *   1 = SRT_PRECISION_TF32: single-pass TF32 operands (2^-12): ~1.3x faster U-Net, stem error
