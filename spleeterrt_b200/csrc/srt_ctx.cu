@@ -486,6 +486,13 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
                                 wpk[(size_t)s * kUp6TcWFloatsPerStem + (b * 2 + term) * 256 + swz32_index(tap, j)] =
                                     weight_part(w6[(size_t)s * 800 + cin * 25 + tap], term);
                             }
+            // the 8-bit residual term's weights: [32 taps][32 channels = skip1 16 | up5 16] e5m2(w / 4), SWIZZLE_32B
+            for (int s = 0; s < S; s++) {
+                uint8_t* blk = reinterpret_cast<uint8_t*>(&wpk[(size_t)s * kUp6TcWFloatsPerStem + 8 * 256]);
+                for (int tap = 0; tap < 25; tap++)
+                    for (int j = 0; j < 32; j++)
+                        blk[tap * 32 + ((((j >> 4) ^ ((tap >> 2) & 1)) << 4) | (j & 15))] = e5m2_rn(0.25f * w6[(size_t)s * 800 + j * 25 + tap]);
+            }
             float* dw;
             if ((r = upload(c, &dw, wpk))) return r;
             q.w = dw;
@@ -497,7 +504,10 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             q.dbg = dbe ? atoi(dbe) : 0;
             const char* ste = getenv("SRT_UP6_STAGES");
             const char* ace = getenv("SRT_UP6_ACC");
-            q.stages = ste ? std::max(2, std::min(5, atoi(ste))) : 5;
+            const char* l8e = getenv("SRT_UP6_LO8");
+            q.lo8 = l8e ? atoi(l8e) != 0 : (c->cfg.precision == SRT_PRECISION_COMPENSATED && !(getenv("SRT_PRECISION") && atoi(getenv("SRT_PRECISION")) != 0));
+            const int max_stages = q.lo8 ? 8 : 5;
+            q.stages = ste ? std::max(2, std::min(max_stages, atoi(ste))) : max_stages;
             q.acc_slots = ace ? std::max(2, std::min(8, atoi(ace))) : 4;
             const int W = F / 2;
             q.blocks_x = (W + 125) / 126;

@@ -142,7 +142,7 @@ struct Up6Params {                // 5x5 s2 transposed conv 32->1 + act + BN, sp
 
 // Tensor-core up6 (srt_up6_tc.cu).  Weights: per stem [box = src*2 + channel half][term: 0 = tf32(w), 1 = tf32(w - tf32(w))]
 // [32 rows = taps (25 used)][8 channels], SWIZZLE_32B pre-swizzled (swz32_index): 8 blocks of 256 floats.
-constexpr int kUp6TcWFloatsPerStem = 8 * 256;
+constexpr int kUp6TcWFloatsPerStem = 9 * 256;   // 8 TF32 blocks + one [32 taps][32 channels] e5m2(w / 4) block (SWIZZLE_32B) for the 8-bit residual term
 struct Up6TcParams {
     CUtensorMap tmap[2];          // skip1, up5: {16, F/2, T/2, S*B}, box {8, 128, 1, 1}, SWIZZLE_32B
     const float* w;               // [S][kUp6TcWFloatsPerStem]
@@ -152,7 +152,9 @@ struct Up6TcParams {
     int chunks, rows_per_unit;    // row chunks per image, input rows per chunk (even)
     int w_terms;                  // 1: weights TF32-exact; 2: also the residual term
     int prefetch_rows;            // L2 prefetch distance in rows (0 = off)
-    int stages, acc_slots;        // ring depths in use (<= 4 input rows, <= 8 TMEM accumulators)
+    int stages, acc_slots;        // ring depths in use (<= 8 input rows (5 with fp32 residuals), <= 8 TMEM accumulators)
+    int lo8;                      // residual term in 8 bits: the split warps write e5m2(4 (a - trunc(a))) as ONE [128 px][32 ch] tile per row
+                                  // (4 KB instead of 16 KB) that a single K = 32 MMA contracts; 0 = fp32 residual tile, four TF32 MMAs
     int dbg;                      // SRT_UP6_DBG stage-skip bits (1 gather, 2 MMA, 4 TMA, 8 split): timing experiments only
     float bias[8], bn_scale[8], bn_offset[8];
     int act[8];

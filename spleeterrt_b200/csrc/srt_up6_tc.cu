@@ -33,8 +33,10 @@
 namespace srt {
 
 constexpr int kU6Threads = 448;            // 8 epilogue + 4 split + TMA + MMA warps
-constexpr int kU6Stages = 5;               // input rows in flight (the kernel is bound by the TMA -> split -> MMA -> release
-                                           // latency chain per ring slot: 2 / 3 / 4 stages ran 1.40 / 1.16 / 0.85 ms, profiles/r1m_up6_stage_sweep.txt)
+constexpr int kU6Stages = 8;               // input rows in flight (the kernel is bound by the TMA -> split -> MMA -> release
+                                           // latency chain per ring slot: 2 / 3 / 4 stages ran 1.40 / 1.16 / 0.85 ms, profiles/r1m_up6_stage_sweep.txt).
+                                           // 5 fit with fp32 residual tiles (2 x 16 KB per row), 8 with the 8-bit ones (16 + 4 KB)
+constexpr int kU6Lo8Bytes = 128 * 32;      // residual tile of a row in the 8-bit form: [128 px][E1 16 ch | U5 16 ch] e5m2, SWIZZLE_32B
 constexpr int kU6AccSlots = 8;             // TMEM accumulators (32 columns each)
 constexpr int kU6RowBytes = 2 * 128 * 64;  // 2 boxes x 128 pixels x 16 channels fp32 = 16 KB
 constexpr int kU6BoxBytes = 128 * 64;
@@ -49,8 +51,9 @@ struct U6Header {
 
 static size_t up6_tc_smem_bytes(int S)
 {
-    (void)S;   // only the current stem's weights are resident (8 KB): the space of the other stems buys the fifth ring stage
-    return sizeof(U6Header) + 1024 + (size_t)2 * kU6Stages * kU6RowBytes + (size_t)kUp6TcWFloatsPerStem * 4 + (size_t)4 * kU6GSlot * 4;
+    (void)S;   // only the current stem's weights are resident (9 KB): the space of the other stems buys ring stages
+    // 5 stages x (16 + 16 KB) = 8 stages x (16 + 4 KB) = 160 KB of operand rings in either form
+    return sizeof(U6Header) + 1024 + (size_t)160 * 1024 + (size_t)kUp6TcWFloatsPerStem * 4 + (size_t)4 * kU6GSlot * 4;
 }
 
 struct U6Unit {
@@ -78,10 +81,11 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
     U6Header* hdr = reinterpret_cast<U6Header*>(smem_raw);
     const uint32_t a_base = (ptx::smem_u32(smem_raw) + (uint32_t)sizeof(U6Header) + 1023u) & ~1023u;
     uint8_t* a_raw = smem_raw + (a_base - ptx::smem_u32(smem_raw));   // [stage][source][128][16] fp32, hi after the split
-    uint8_t* a_lo = a_raw + kU6Stages * kU6RowBytes;                  // same layout, residuals
-    const uint32_t lo_base = a_base + kU6Stages * kU6RowBytes;
-    float* wsm = reinterpret_cast<float*>(a_lo + kU6Stages * kU6RowBytes);   // [box][term][32][8] pre-swizzled, current stem
-    const uint32_t w_base = lo_base + kU6Stages * kU6RowBytes;
+    const uint32_t lo_stage = p.lo8 ? (uint32_t)kU6Lo8Bytes : (uint32_t)kU6RowBytes;
+    uint8_t* a_lo = a_raw + p.stages * kU6RowBytes;                   // residuals: same layout in fp32, or one [128][32] e5m2 tile per row
+    const uint32_t lo_base = a_base + p.stages * kU6RowBytes;
+    float* wsm = reinterpret_cast<float*>(a_raw + 160 * 1024);       // [box][term][32][8] pre-swizzled (+ the e5m2 block), current stem
+    const uint32_t w_base = a_base + 160 * 1024;
     float* G = wsm + (size_t)kUp6TcWFloatsPerStem;                           // [4][25][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,8 +152,22 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                 if (p.dbg & 16) ptx::mbar_wait_warp(&hdr->a_full[st], ph);
                 else ptx::mbar_wait(&hdr->a_full[st], ph);
                 float4* raw = reinterpret_cast<float4*>(a_raw + (size_t)st * kU6RowBytes);
-                float4* lo = reinterpret_cast<float4*>(a_lo + (size_t)st * kU6RowBytes);
-                if (p.dbg & 32) {   // A/B switch: round-to-nearest hi, rewritten in place
+                float4* lo = reinterpret_cast<float4*>(a_lo + (size_t)st * lo_stage);
+                if (p.lo8 && !(p.dbg & 8)) {
+                    // 8-bit residuals: element e of the raw stage is (source e >> 9, pixel (e & 511) >> 2, 16-byte chunk e & 3 of the pixel's
+                    // 64-byte SWIZZLE_64B row, i.e. channels 4 c .. 4 c + 3 with c = chunk ^ ((px >> 1) & 3)); its four residuals go, as e5m2(4 x),
+                    // to bytes 16 source + 4 c of the pixel's 32-byte row of the SWIZZLE_32B tile (16-byte chunk index ^ ((px >> 2) & 1))
+                    uint32_t* lo8 = reinterpret_cast<uint32_t*>(lo);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int e = ts + 128 * i;
+                        const float4 a = raw[e];
+                        const int box = e >> 9, px = (e & 511) >> 2, c = (e & 3) ^ ((px >> 1) & 3);
+                        const uint32_t w = ptx::pack_e5m2x4(4.0f * (a.x - ptx::trunc_tf32(a.x)), 4.0f * (a.y - ptx::trunc_tf32(a.y)),
+                                                            4.0f * (a.z - ptx::trunc_tf32(a.z)), 4.0f * (a.w - ptx::trunc_tf32(a.w)));
+                        lo8[px * 8 + ((box ^ ((px >> 2) & 1)) << 2) + c] = w;
+                    }
+                } else if (p.dbg & 32) {   // A/B switch: round-to-nearest hi, rewritten in place
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const float4 a = raw[ts + 128 * i];
@@ -209,6 +227,15 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                     ptx::tc_fence_after();
                     // terms: (A_hi, W_hi), (A_lo, W_hi), and (A_hi, W_lo) when the weights carry a residual
                     for (int term = 0; term < ((p.dbg & 2) ? 0 : 1 + p.w_terms); term++) {
+                        if (term == 1 && p.lo8) {
+                            // the residual term in 8 bits: one K = 32 MMA per row over [E1 | U5] (both operands SWIZZLE_32B, e5m2)
+                            const uint32_t b8 = w_lo + (uint32_t)((8 * 1024) >> 4);
+#pragma unroll
+                            for (int j = 0; j < 2; j++)
+                                ptx::mma_f8_ss_lo(tmem_d + (uint32_t)(asj[j] * 32), ptx::umma_desc_lo(lo_base + (uint32_t)stj[j] * kU6Lo8Bytes), b8,
+                                                  ptx::umma_idesc_bf16(kTileM, 32), 1u, ptx::kDescHiSw32);
+                            continue;
+                        }
                         const uint32_t abase = (term == 1) ? lo_base : a_base;
                         const uint32_t wterm = (term == 2) ? 1u : 0u;
 #pragma unroll
