@@ -449,7 +449,8 @@ def main():
     e2e_check = {"slots_identical": bool(torch.equal(houts[0][0], houts[1][0])) if args.steps >= 2 else None,
                  "max_abs_diff_vs_device_path": float((hout[ns - 1] - dout[ns - 1].cpu()).abs().max())}
     if e2e_check["max_abs_diff_vs_device_path"] > 1e-3 or e2e_check["slots_identical"] is False:
-        raise SystemExit(f"bench: host-pointer results are wrong: {e2e_check}")
+        if not os.environ.get("SRT_BENCH_STAGE_SKIPS"):   # tools/up6_sweep.sh: kernels with pipeline stages switched off put out garbage by design
+            raise SystemExit(f"bench: host-pointer results are wrong: {e2e_check}")
     # the ceiling of that loop: the same D2H bytes as plain cudaMemcpyAsync, nothing else running (per rank, all ranks at once)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -505,10 +505,12 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             const char* ste = getenv("SRT_UP6_STAGES");
             const char* ace = getenv("SRT_UP6_ACC");
             const char* l8e = getenv("SRT_UP6_LO8");
-            q.lo8 = l8e ? atoi(l8e) != 0 : (c->cfg.precision == SRT_PRECISION_COMPENSATED && !(getenv("SRT_PRECISION") && atoi(getenv("SRT_PRECISION")) != 0));
-            const int max_stages = q.lo8 ? 8 : 5;
+            q.lo8 = l8e ? atoi(l8e) != 0 : 1;   // every precision mode ("0": the fp32 residual tile, four rows in flight)
+            const char* pre = getenv("SRT_UP6_PAIR");
+            q.pair = pre ? atoi(pre) != 0 : 1;   // the two forms time the same (profiles/r2_up6_sweep.txt)
+            const int max_stages = q.pair ? (q.lo8 ? 6 : 4) : (q.lo8 ? 8 : 5);
             q.stages = ste ? std::max(2, std::min(max_stages, atoi(ste))) : max_stages;
-            q.acc_slots = ace ? std::max(2, std::min(8, atoi(ace))) : 4;
+            q.acc_slots = ace ? std::max(2, std::min(8, atoi(ace) & ~1)) : 4;   // even: the rows go through in pairs
             const int W = F / 2;
             q.blocks_x = (W + 125) / 126;
             q.bw = (W + q.blocks_x - 1) / q.blocks_x;

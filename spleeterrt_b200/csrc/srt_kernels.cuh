@@ -152,7 +152,8 @@ struct Up6TcParams {
     int chunks, rows_per_unit;    // row chunks per image, input rows per chunk (even)
     int w_terms;                  // 1: weights TF32-exact; 2: also the residual term
     int prefetch_rows;            // L2 prefetch distance in rows (0 = off)
-    int stages, acc_slots;        // ring depths in use (<= 8 input rows (5 with fp32 residuals), <= 8 TMEM accumulators)
+    int stages, acc_slots;        // ring depths in use (input rows: see `pair`; <= 8 TMEM accumulators, an even number)
+    int pair;                     // epilogue loop over row pairs (6 G rows, <= 6 / 4 input rows in flight) instead of single rows (4 G rows, <= 8 / 5)
     int lo8;                      // residual term in 8 bits: the split warps write e5m2(4 (a - trunc(a))) as ONE [128 px][32 ch] tile per row
                                   // (4 KB instead of 16 KB) that a single K = 32 MMA contracts; 0 = fp32 residual tile, four TF32 MMAs
     int dbg;                      // SRT_UP6_DBG stage-skip bits (1 gather, 2 MMA, 4 TMA, 8 split): timing experiments only

@@ -16,7 +16,7 @@
 //                (4 boxes of 32-byte rows) was fetch-bound: with everything but the TMA switched off the kernel
 //                still took 0.77 of its 0.85 ms (profiles/r1m_up6_stage_sweep.txt) - the copy engine works per
 //                contiguous fragment, and 64-byte fragments halve their number.
-//   warps 8-11   split: hi = the tile as loaded (the MMA sees a truncated to TF32), lo = a - trunc_tf32(a)
+//   warps 8-11   split, one warp per row: hi = the tile as loaded (the MMA sees a truncated to TF32), lo = a - trunc_tf32(a)
 //                (second tile).  The two inputs are fp32 and this layer feeds the mask almost directly, so
 //                plain TF32 operands would double the stem error of small nets (oracle emulation,
 //                DESIGN.md); hi + lo keeps fp32 accuracy.
@@ -35,12 +35,18 @@ namespace srt {
 constexpr int kU6Threads = 448;            // 8 epilogue + 4 split + TMA + MMA warps
 constexpr int kU6Stages = 8;               // input rows in flight (the kernel is bound by the TMA -> split -> MMA -> release
                                            // latency chain per ring slot: 2 / 3 / 4 stages ran 1.40 / 1.16 / 0.85 ms, profiles/r1m_up6_stage_sweep.txt).
-                                           // 5 fit with fp32 residual tiles (2 x 16 KB per row), 8 with the 8-bit ones (16 + 4 KB)
+                                           // 4 fit with fp32 residual tiles (2 x 16 KB per row), 6 with the 8-bit ones (16 + 4 KB); beyond 6 nothing moves
+                                           // (profiles/r2_up6_sweep.txt)
 constexpr int kU6Lo8Bytes = 128 * 32;      // residual tile of a row in the 8-bit form: [128 px][E1 16 ch | U5 16 ch] e5m2, SWIZZLE_32B
 constexpr int kU6AccSlots = 8;             // TMEM accumulators (32 columns each)
 constexpr int kU6RowBytes = 2 * 128 * 64;  // 2 boxes x 128 pixels x 16 channels fp32 = 16 KB
 constexpr int kU6BoxBytes = 128 * 64;
 constexpr int kU6GSlot = 25 * 128;         // floats per G row
+// Two forms of the epilogue loop share the shared memory differently (Up6TcParams.pair):
+//   single rows: 4 G rows (3 gathered from + 1 written), 160 KB of operand rings = 8 stages x (16 + 4 KB) or 5 x (16 + 16 KB)
+//   row pairs:   6 G rows (4 + 2),                      128 KB                  = 6 stages             or 4
+__host__ __device__ constexpr int u6_g_slots(int pair) { return pair ? 6 : 4; }
+__host__ __device__ constexpr int u6_ring_bytes(int pair) { return (pair ? 128 : 160) * 1024; }
 
 struct U6Header {
     uint64_t a_full[kU6Stages], a_ready[kU6Stages], a_empty[kU6Stages];
@@ -49,11 +55,10 @@ struct U6Header {
     uint32_t tmem_base, pad;
 };
 
-static size_t up6_tc_smem_bytes(int S)
+static size_t up6_tc_smem_bytes(int S, int pair)
 {
     (void)S;   // only the current stem's weights are resident (9 KB): the space of the other stems buys ring stages
-    // 5 stages x (16 + 16 KB) = 8 stages x (16 + 4 KB) = 160 KB of operand rings in either form
-    return sizeof(U6Header) + 1024 + (size_t)160 * 1024 + (size_t)kUp6TcWFloatsPerStem * 4 + (size_t)4 * kU6GSlot * 4;
+    return sizeof(U6Header) + 1024 + (size_t)u6_ring_bytes(pair) + (size_t)kUp6TcWFloatsPerStem * 4 + (size_t)u6_g_slots(pair) * kU6GSlot * 4;
 }
 
 struct U6Unit {
@@ -84,9 +89,9 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
     const uint32_t lo_stage = p.lo8 ? (uint32_t)kU6Lo8Bytes : (uint32_t)kU6RowBytes;
     uint8_t* a_lo = a_raw + p.stages * kU6RowBytes;                   // residuals: same layout in fp32, or one [128][32] e5m2 tile per row
     const uint32_t lo_base = a_base + p.stages * kU6RowBytes;
-    float* wsm = reinterpret_cast<float*>(a_raw + 160 * 1024);       // [box][term][32][8] pre-swizzled (+ the e5m2 block), current stem
-    const uint32_t w_base = a_base + 160 * 1024;
-    float* G = wsm + (size_t)kUp6TcWFloatsPerStem;                           // [4][25][128]
+    float* wsm = reinterpret_cast<float*>(a_raw + u6_ring_bytes(p.pair));       // [box][term][32][8] pre-swizzled (+ the e5m2 block), current stem
+    const uint32_t w_base = a_base + u6_ring_bytes(p.pair);
+    float* G = wsm + (size_t)kUp6TcWFloatsPerStem;                           // [u6_g_slots][25][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = p.T / 2, W = p.F / 2;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
         ptx::tma_prefetch_desc(&p.tmap[1]);
         for (int i = 0; i < kU6Stages; i++) {
             ptx::mbar_init(&hdr->a_full[i], 1);
-            ptx::mbar_init(&hdr->a_ready[i], 4);    // one arrival per split warp
+            ptx::mbar_init(&hdr->a_ready[i], 1);    // the split warp that owns the row
             ptx::mbar_init(&hdr->a_empty[i], 1);
         }
         for (int i = 0; i < kU6AccSlots; i++) {
@@ -143,52 +148,48 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
         }
     } else if (warp >= 8 && warp < 12) {
         // ===== split: hi (in place) / lo ============================================================
-        const int ts = threadIdx.x - 256;   // 0..127
-        int st = 0;
+        // One warp per ROW (row k of this CTA goes to split warp k & 3): the fixed latencies of a row - the wait for the TMA, the
+        // proxy fence, the arrival - then overlap across four rows instead of adding up once per row (with the four warps sharing
+        // every row this stage alone took 0.26 ms of the kernel's 0.73: profiles/r2_up6_sweep.txt).
+        const int wsplit = warp - 8;
+        int st = 0, k = 0;
         uint32_t ph = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const U6Unit t = u6_unit(p, u);
-            for (int y = t.r0 - 1; y <= t.r1; y++) {
-                if (p.dbg & 16) ptx::mbar_wait_warp(&hdr->a_full[st], ph);
-                else ptx::mbar_wait(&hdr->a_full[st], ph);
-                float4* raw = reinterpret_cast<float4*>(a_raw + (size_t)st * kU6RowBytes);
-                float4* lo = reinterpret_cast<float4*>(a_lo + (size_t)st * lo_stage);
-                if (p.lo8 && !(p.dbg & 8)) {
-                    // 8-bit residuals: element e of the raw stage is (source e >> 9, pixel (e & 511) >> 2, 16-byte chunk e & 3 of the pixel's
-                    // 64-byte SWIZZLE_64B row, i.e. channels 4 c .. 4 c + 3 with c = chunk ^ ((px >> 1) & 3)); its four residuals go, as e5m2(4 x),
-                    // to bytes 16 source + 4 c of the pixel's 32-byte row of the SWIZZLE_32B tile (16-byte chunk index ^ ((px >> 2) & 1))
-                    uint32_t* lo8 = reinterpret_cast<uint32_t*>(lo);
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int e = ts + 128 * i;
-                        const float4 a = raw[e];
-                        const int box = e >> 9, px = (e & 511) >> 2, c = (e & 3) ^ ((px >> 1) & 3);
-                        const uint32_t w = ptx::pack_e5m2x4(4.0f * (a.x - ptx::trunc_tf32(a.x)), 4.0f * (a.y - ptx::trunc_tf32(a.y)),
-                                                            4.0f * (a.z - ptx::trunc_tf32(a.z)), 4.0f * (a.w - ptx::trunc_tf32(a.w)));
-                        lo8[px * 8 + ((box ^ ((px >> 2) & 1)) << 2) + c] = w;
+            for (int y = t.r0 - 1; y <= t.r1; y++, k++) {
+                if ((k & 3) == wsplit) {
+                    ptx::mbar_wait(&hdr->a_full[st], ph);
+                    float4* raw = reinterpret_cast<float4*>(a_raw + (size_t)st * kU6RowBytes);
+                    float4* lo = reinterpret_cast<float4*>(a_lo + (size_t)st * lo_stage);
+                    if (p.lo8 && !(p.dbg & 8)) {
+                        // 8-bit residuals: element e of the raw stage is (source e >> 9, pixel (e & 511) >> 2, 16-byte chunk e & 3 of the pixel's
+                        // 64-byte SWIZZLE_64B row, i.e. channels 4 c .. 4 c + 3 with c = chunk ^ ((px >> 1) & 3)); its four residuals go, as
+                        // e5m2(4 x), to bytes 16 source + 4 c of the pixel's 32-byte row of the SWIZZLE_32B tile (16-byte chunk ^ ((px >> 2) & 1))
+                        uint32_t* lo8 = reinterpret_cast<uint32_t*>(lo);
+#pragma unroll 8
+                        for (int i = 0; i < 32; i++) {
+                            const int e = lane + 32 * i;
+                            const float4 a = raw[e];
+                            const int box = e >> 9, px = (e & 511) >> 2, c = (e & 3) ^ ((px >> 1) & 3);
+                            const uint32_t w = ptx::pack_e5m2x4(4.0f * (a.x - ptx::trunc_tf32(a.x)), 4.0f * (a.y - ptx::trunc_tf32(a.y)),
+                                                                4.0f * (a.z - ptx::trunc_tf32(a.z)), 4.0f * (a.w - ptx::trunc_tf32(a.w)));
+                            lo8[px * 8 + ((box ^ ((px >> 2) & 1)) << 2) + c] = w;
+                        }
+                    } else if (!(p.dbg & 8)) {
+                        // fp32 residuals.  hi = the raw tile itself: the tensor core reads only the TF32 bits of an fp32 operand (sign,
+                        // exponent, 10 mantissa bits), i.e. a truncated to TF32.  lo = a - trunc(a) is exact in fp32 and < 2^-10 |a|, so
+                        // hi + tf32(lo) carries >= 20 mantissa bits.  Not rewriting hi saves a third of this stage's shared-memory traffic.
+#pragma unroll 8
+                        for (int i = 0; i < 32; i++) {
+                            const float4 a = raw[lane + 32 * i];
+                            lo[lane + 32 * i] = make_float4(a.x - ptx::trunc_tf32(a.x), a.y - ptx::trunc_tf32(a.y), a.z - ptx::trunc_tf32(a.z),
+                                                            a.w - ptx::trunc_tf32(a.w));
+                        }
                     }
-                } else if (p.dbg & 32) {   // A/B switch: round-to-nearest hi, rewritten in place
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float4 a = raw[ts + 128 * i];
-                        const float4 h = make_float4(ptx::rna_tf32(a.x), ptx::rna_tf32(a.y), ptx::rna_tf32(a.z), ptx::rna_tf32(a.w));
-                        raw[ts + 128 * i] = h;
-                        lo[ts + 128 * i] = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
-                    }
-                } else if (!(p.dbg & 8))
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    // hi = the raw tile itself: the tensor core reads only the TF32 bits of an fp32 operand (sign, exponent,
-                    // 10 mantissa bits), i.e. a truncated to TF32.  lo = a - trunc(a) is exact in fp32 and < 2^-10 |a|, so
-                    // hi + tf32(lo) carries >= 20 mantissa bits.  Not rewriting hi saves a third of this warp group's
-                    // shared-memory traffic (the kernel's bound).
-                    const float4 a = raw[ts + 128 * i];
-                    lo[ts + 128 * i] = make_float4(a.x - ptx::trunc_tf32(a.x), a.y - ptx::trunc_tf32(a.y), a.z - ptx::trunc_tf32(a.z),
-                                                   a.w - ptx::trunc_tf32(a.w));
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&hdr->a_ready[st]);
                 }
-                ptx::fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&hdr->a_ready[st]);
                 if (++st == p.stages) { st = 0; ph ^= 1; }
             }
         }
@@ -258,10 +259,11 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
         }
     } else {
         // ===== epilogue warps 0..7 =================================================================
-        // Software-pipelined per input row y:  issue the TMEM load of row y  |  gather + store the output rows of
-        // input row y - 2 from G rows y-3, y-2, y-1 (complete and published by the previous barrier) while that load
-        // is in flight  |  wait for the load, write G[y]  |  barrier.  The gather reads three ring slots and the
-        // store goes to the fourth, so one 256-thread barrier per row is enough.
+        // Software-pipelined per PAIR of input rows (y, y + 1):  issue the TMEM loads of both rows  |  gather + store the output
+        // rows of input rows y - 3 and y - 2 from G rows y-4 .. y-1 (complete and published by the previous barrier) while the
+        // loads are in flight  |  wait for the loads, write G[y], G[y + 1]  |  barrier.  The gathers read four ring slots and the
+        // stores go to the other two, so one 256-thread barrier per row pair is enough.  (The eight warps run in lockstep, so the
+        // loop period is the latency of one iteration, ~550 cycles with every other stage switched off: profiles/r2_up6_sweep.txt.)
         const int q = warp & 3, half = warp >> 2;
         const int m = q * 32 + lane;              // TMEM lane = pixel of the tile
         const int gm = threadIdx.x & 127;         // gather: pixel
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                 for (int dy = -1; dy <= 1; dy++) {
                     if (po == 0 && dy == 1) continue;      // kh = -1
                     const int kh = po + 1 - 2 * dy;
-                    const float* gr = G + (size_t)((c + dy) & 3) * kU6GSlot + (kh * 5) * 128 + gm;
+                    const float* gr = G + (size_t)(p.pair ? (unsigned)(c + dy) % 6u : (unsigned)(c + dy) & 3u) * kU6GSlot + (kh * 5) * 128 + gm;
                     o0 += gr[1 * 128] + gr[3 * 128 - 1];                       // qo = 0: kw = 1 (dx 0), 3 (dx -1)
                     o1 += gr[0 * 128 + 1] + gr[2 * 128] + gr[4 * 128 - 1];     // qo = 1: kw = 0 (dx +1), 2 (dx 0), 4 (dx -1)
                 }
@@ -298,25 +300,67 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
                 r.y = sc * r.y + of;
                 *reinterpret_cast<float2*>(p.out + ((size_t)t.n * p.T + 2 * yo + po) * p.F + 2 * X) = r;
             };
-            for (int y = t.r0 - 1; y <= t.r1; y++, grow++) {
-                if (p.dbg & 16) ptx::mbar_wait_warp(&hdr->acc_full[as], aph);
-                else ptx::mbar_wait(&hdr->acc_full[as], aph);
-                ptx::tc_fence_after();
-                uint32_t v[16];
-                ptx::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 32 + half * 16), v);
-                if (y - 2 >= t.r0 && col_ok) gather(y - 2, grow - 2);
-                ptx::tmem_ld16_wait(v);
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&hdr->acc_empty[as]);
-                if (++as == p.acc_slots) { as = 0; aph ^= 1; }
-                float* gs = G + (size_t)(grow & 3) * kU6GSlot;
+            if (p.pair) {
+                // two input rows per iteration (the MMA warp issues them as a pair): both accumulators are loaded at once, the gathers of
+                // output-row pairs y - 3 and y - 2 (G rows y-4 .. y-1) run under the loads, and ONE 256-thread barrier publishes G[y], G[y+1]
+                for (int y = t.r0 - 1; y <= t.r1; y += 2, grow += 2) {   // the row count r1 - r0 + 2 is even
+                    const int as1 = as + 1;                               // acc_slots is even: a pair never wraps
+                    ptx::mbar_wait(&hdr->acc_full[as], aph);
+                    ptx::mbar_wait(&hdr->acc_full[as1], aph);
+                    ptx::tc_fence_after();
+                    uint32_t v0[16], v1[16];
+                    ptx::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 32 + half * 16), v0);
+                    ptx::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as1 * 32 + half * 16), v1);
+                    if (col_ok) {
+                        if (y - 3 >= t.r0) gather(y - 3, grow - 3);
+                        if (y - 2 >= t.r0) gather(y - 2, grow - 2);
+                    }
+                    ptx::tmem_ld16_wait(v0);
+                    ptx::tmem_ld16_wait(v1);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::mbar_arrive(&hdr->acc_empty[as]);
+                        ptx::mbar_arrive(&hdr->acc_empty[as1]);
+                    }
+                    as += 2;
+                    if (as == p.acc_slots) { as = 0; aph ^= 1; }
+                    float* gs0 = G + (size_t)((unsigned)grow % 6u) * kU6GSlot;
+                    float* gs1 = G + (size_t)((unsigned)(grow + 1) % 6u) * kU6GSlot;
 #pragma unroll
-                for (int i = 0; i < 16; i++)
-                    if (half * 16 + i < 25) gs[(half * 16 + i) * 128 + m] = __uint_as_float(v[i]);
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                    for (int i = 0; i < 16; i++)
+                        if (half * 16 + i < 25) {
+                            gs0[(half * 16 + i) * 128 + m] = __uint_as_float(v0[i]);
+                            gs1[(half * 16 + i) * 128 + m] = __uint_as_float(v1[i]);
+                        }
+                    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                }
+                if (col_ok) {   // flush: the last output rows of the unit (G rows r1-3 .. r1)
+                    if (t.r1 - 2 >= t.r0) gather(t.r1 - 2, grow - 3);
+                    if (t.r1 - 1 >= t.r0) gather(t.r1 - 1, grow - 2);
+                }
+            } else {
+                // one input row per iteration: issue the TMEM load of row y  |  gather + store the output rows of input row y - 2 from G rows
+                // y-3, y-2, y-1 while that load is in flight  |  wait for the load, write G[y]  |  barrier
+                for (int y = t.r0 - 1; y <= t.r1; y++, grow++) {
+                    ptx::mbar_wait(&hdr->acc_full[as], aph);
+                    ptx::tc_fence_after();
+                    uint32_t v[16];
+                    ptx::tmem_ld16_issue(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 32 + half * 16), v);
+                    if (y - 2 >= t.r0 && col_ok) gather(y - 2, grow - 2);
+                    ptx::tmem_ld16_wait(v);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&hdr->acc_empty[as]);
+                    if (++as == p.acc_slots) { as = 0; aph ^= 1; }
+                    float* gs = G + (size_t)(grow & 3) * kU6GSlot;
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (half * 16 + i < 25) gs[(half * 16 + i) * 128 + m] = __uint_as_float(v[i]);
+                    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                }
+                if (col_ok) gather(t.r1 - 1, grow - 2);   // flush: the last output rows of the unit (G rows r1-2, r1-1, r1)
             }
-            if (col_ok) gather(t.r1 - 1, grow - 2);   // flush: the last output rows of the unit (G rows r1-2, r1-1, r1)
         }
     }
     ptx::tc_fence_before();
@@ -329,13 +373,13 @@ __global__ void __launch_bounds__(kU6Threads, 1) up6_tc_kernel(const __grid_cons
 
 void launch_up6_tc(const Up6TcParams& p, cudaStream_t st)
 {
-    const size_t smem = up6_tc_smem_bytes(p.S);
+    const size_t smem = up6_tc_smem_bytes(p.S, 0);   // the larger of the two forms
     static LaunchState state;
     const int sms = state.prepare(up6_tc_kernel, smem);
     const int n_units = p.blocks_x * p.chunks * p.Bv * p.S;
     up6_tc_kernel<<<n_units < sms ? n_units : sms, kU6Threads, smem, st>>>(p);
 }
 
-bool up6_tc_fits(int S) { return up6_tc_smem_bytes(S) <= 232448; }
+bool up6_tc_fits(int S) { return up6_tc_smem_bytes(S, 0) <= 232448 && up6_tc_smem_bytes(S, 1) <= 232448; }
 
 }  // namespace srt
