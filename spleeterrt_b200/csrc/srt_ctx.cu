@@ -476,23 +476,9 @@ static int build(srt_ctx* c, const float* const* coeffs, const int* modes)
             bool exact = true;
             for (float v : w6) exact = exact && round_tf32(v) == v;
             q.w_terms = exact ? 1 : 2;
+            static_assert(kUp6TcWFloatsPerStem == kUp6PackFloats, "up6 weight block");
             std::vector<float> wpk((size_t)S * kUp6TcWFloatsPerStem, 0.0f);
-            for (int s = 0; s < S; s++)
-                for (int b = 0; b < 4; b++)
-                    for (int term = 0; term < 2; term++)
-                        for (int tap = 0; tap < 25; tap++)
-                            for (int j = 0; j < 8; j++) {
-                                const int cin = (b >> 1) * 16 + (b & 1) * 8 + j;   // [skip1 | up5] (spleeter.c:289)
-                                wpk[(size_t)s * kUp6TcWFloatsPerStem + (b * 2 + term) * 256 + swz32_index(tap, j)] =
-                                    weight_part(w6[(size_t)s * 800 + cin * 25 + tap], term);
-                            }
-            // the 8-bit residual term's weights: [32 taps][32 channels = skip1 16 | up5 16] e5m2(w / 4), SWIZZLE_32B
-            for (int s = 0; s < S; s++) {
-                uint8_t* blk = reinterpret_cast<uint8_t*>(&wpk[(size_t)s * kUp6TcWFloatsPerStem + 8 * 256]);
-                for (int tap = 0; tap < 25; tap++)
-                    for (int j = 0; j < 32; j++)
-                        blk[tap * 32 + ((((j >> 4) ^ ((tap >> 2) & 1)) << 4) | (j & 15))] = e5m2_rn(0.25f * w6[(size_t)s * 800 + j * 25 + tap]);
-            }
+            for (int s = 0; s < S; s++) pack_up6_weights(&w6[(size_t)s * 800], &wpk[(size_t)s * kUp6TcWFloatsPerStem]);
             float* dw;
             if ((r = upload(c, &dw, wpk))) return r;
             q.w = dw;

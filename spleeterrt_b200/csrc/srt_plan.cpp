@@ -626,4 +626,19 @@ void pack_down1(const Down1Plan& L, const float* const* coeffs, int nstems, floa
         }
 }
 
+void pack_up6_weights(const float* w6, float* out)
+{
+    for (int i = 0; i < kUp6PackFloats; i++) out[i] = 0.0f;
+    for (int b = 0; b < 4; b++)
+        for (int term = 0; term < 2; term++)
+            for (int tap = 0; tap < 25; tap++)
+                for (int j = 0; j < 8; j++) {
+                    const int cin = (b >> 1) * 16 + (b & 1) * 8 + j;
+                    out[(b * 2 + term) * 256 + swz32_index(tap, j)] = weight_part(w6[cin * 25 + tap], term);
+                }
+    uint8_t* blk = reinterpret_cast<uint8_t*>(out + 8 * 256);
+    for (int tap = 0; tap < 25; tap++)
+        for (int j = 0; j < 32; j++) blk[swz32_index8(tap, j)] = e5m2_rn(0.25f * w6[j * 25 + tap]);
+}
+
 }  // namespace srt

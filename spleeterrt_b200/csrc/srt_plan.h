@@ -218,5 +218,15 @@ SRT_HD inline int swz128_index16(int row, int j) { return row * 64 + ((((j >> 3)
 SRT_HD inline int swz128_index8(int row, int j) { return row * 128 + ((((j >> 4) ^ (row & 7)) << 4) | (j & 15)); }
 // a [rows][64] block of bytes in SWIZZLE_64B (chunk index ^= address bits 7-8 = (row >> 1) & 3)
 SRT_HD inline int swz64_index8(int row, int j) { return row * 64 + ((((j >> 4) ^ ((row >> 1) & 3)) << 4) | (j & 15)); }
+// byte j of row `row` of a [rows][32] byte tile in the SWIZZLE_32B layout (16-byte chunk ^= bit 2 of the row: address bit 4 ^= bit 7)
+SRT_HD inline int swz32_index8(int row, int j) { return row * 32 + ((((j >> 4) ^ ((row >> 2) & 1)) << 4) | (j & 15)); }
+
+// ---- up6 (transposed 5x5, 32 -> 1) for up6_tc_kernel: per stem kUp6PackFloats floats =
+//   8 blocks [box b = source * 2 + channel half][term: tf32(w), tf32(w - tf32(w))][32 taps][8 channels] fp32, rows in the SWIZZLE_32B layout
+//   (B operand of the K = 8 TF32 MMAs; taps 25..31 zero), then ONE block [32 taps][32 channels = skip1 16 | up5 16] of e5m2(w / 4) bytes,
+//   SWIZZLE_32B (B operand of the K = 32 MMA that contracts the 8-bit residual tile).  w6 = the layer's [32 cin][25 taps] weights
+//   (spleeter.c:289: channels [skip1 | up5]).
+constexpr int kUp6PackFloats = 9 * 256;
+void pack_up6_weights(const float* w6, float* out);
 
 }  // namespace srt

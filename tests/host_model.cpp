@@ -312,3 +312,72 @@ extern "C" int srt_host_model_down1(int T, int F, const float* const* coeffs, in
             }
     return 0;
 }
+
+// ---- up6 as up6_tc_kernel computes it: GEMM over the PACKED weights, then the 25-value gather ---------------------------
+// e1, u5: planar [16][H][W] (H = T/2, W = F/2); out: [T][F] = scale * act(tconv + bias) + offset.  lo8 = the residual term
+// through e5m2 operands (one K = 32 contraction), else through fp32 residuals (TF32 operands).  The packed blocks are read back
+// through the hardware's definition of SWIZZLE_32B (byte address bit 4 ^= bit 7), not through the packer's index helpers.
+static inline size_t unswz32(size_t byte) { return byte ^ (((byte >> 7) & 1) << 4); }
+static inline float trunc_tf32_host(float x)
+{
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u &= 0xffffe000u;
+    std::memcpy(&x, &u, 4);
+    return x;
+}
+extern "C" int srt_host_model_up6(int T, int F, const float* coeff, int act, const float* e1, const float* u5, float* out, int lo8)
+{
+    const CoeffLayout cl = coeff_layout();
+    const int H = T / 2, W = F / 2;
+    std::vector<float> pk(kUp6PackFloats);
+    pack_up6_weights(coeff + cl.up_w[5], pk.data());
+    const uint8_t* bytes = reinterpret_cast<const uint8_t*>(pk.data());
+    auto w_tf32 = [&](int b, int term, int tap, int j) {
+        float v;
+        std::memcpy(&v, bytes + (size_t)(b * 2 + term) * 1024 + unswz32((size_t)tap * 32 + j * 4), 4);
+        return v;
+    };
+    auto w_e5m2 = [&](int tap, int ch) { return e5m2_to_float(bytes[(size_t)8 * 1024 + unswz32((size_t)tap * 32 + ch)]); };
+    std::vector<float> G((size_t)H * W * 32, 0.f);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            float a[32];
+            for (int c = 0; c < 16; c++) {
+                a[c] = e1[((size_t)c * H + y) * W + x];
+                a[16 + c] = u5[((size_t)c * H + y) * W + x];
+            }
+            for (int tap = 0; tap < 32; tap++) {
+                double acc = 0.0;
+                for (int cin = 0; cin < 32; cin++) {
+                    const int b = (cin >> 4) * 2 + ((cin >> 3) & 1), j = cin & 7;
+                    const float hi = trunc_tf32_host(a[cin]), lo = a[cin] - hi;
+                    acc += (double)hi * w_tf32(b, 0, tap, j);
+                    if (g_split) acc += (double)hi * w_tf32(b, 1, tap, j);
+                    if (lo8) acc += (double)e5m2_to_float(e5m2_rn(4.0f * lo)) * w_e5m2(tap, cin);
+                    else acc += (double)trunc_tf32_host(lo) * w_tf32(b, 0, tap, j);
+                }
+                G[((size_t)y * W + x) * 32 + tap] = (float)acc;
+            }
+        }
+    for (int tap = 25; tap < 32; tap++)
+        for (size_t px = 0; px < (size_t)H * W; px++)
+            if (G[px * 32 + tap] != 0.f) return -2;   // the padding taps must stay zero
+    const float bias = coeff[cl.up_b[5]], offset = coeff[cl.up_bn[5]], scale = coeff[cl.up_bn[5] + 1];
+    for (int yo = 0; yo < H; yo++)
+        for (int X = 0; X < W; X++)
+            for (int po = 0; po < 2; po++)
+                for (int qo = 0; qo < 2; qo++) {
+                    float o = 0.f;
+                    for (int dy = -1; dy <= 1; dy++)
+                        for (int dx = -1; dx <= 1; dx++) {
+                            const int kh = po + 1 - 2 * dy, kw = qo + 1 - 2 * dx;
+                            if (kh < 0 || kh > 4 || kw < 0 || kw > 4) continue;
+                            const int yy = yo + dy, xx = X + dx;
+                            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                            o += G[((size_t)yy * W + xx) * 32 + kh * 5 + kw];
+                        }
+                    out[(size_t)(2 * yo + po) * F + 2 * X + qo] = scale * act_apply(act, o + bias) + offset;
+                }
+    return 0;
+}

@@ -464,3 +464,31 @@ def test_narrow_n_tiles_for_small_grids(oracle, host_model, small_nets):
             assert np.abs(got - ref).max() / max(1e-6, np.abs(ref).max()) < 2e-5
     finally:
         host_model.srt_host_model_set_min_ctas(0)
+
+
+@pytest.mark.parametrize("T,F,mode", [(64, 128, 1), (64, 192, 0)])
+def test_up6_packed_weights_and_8bit_residual_term(oracle, host_model, small_nets, T, F, mode):
+    """up6 as up6_tc_kernel contracts it - the packed weight block of srt_plan.cpp read back through the hardware's SWIZZLE_32B
+    definition, operands truncated to TF32, residual term through e5m2 (default) or TF32 operands - then the 25-value gather,
+    against the oracle's up6 tensor (spleeter.c:289-295)."""
+    coeff = small_nets[0][0] if mode else small_nets[1][0]
+    rng = np.random.default_rng(7 * T + F)
+    x = (np.abs(rng.standard_normal((2, T, F))) * 3).astype(np.float32)
+    _, tp = oracle.unet(coeff, x, mode, taps=True)
+    taps = oracle.split_taps(tp, T, F)
+    ref = taps["up6"][0]
+    e1 = np.ascontiguousarray(taps["skip1"], np.float32)
+    u5 = np.ascontiguousarray(taps["up5"], np.float32)
+    a_dec = 3 if mode else 2
+    errs = {}
+    for lo8 in (1, 0):
+        out = np.zeros((T, F), np.float32)
+        rc = host_model.srt_host_model_up6(T, F, np.ascontiguousarray(coeff).ctypes.data_as(C.c_void_p), a_dec, e1.ctypes.data_as(C.c_void_p),
+                                           u5.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), lo8)
+        assert rc == 0
+        errs[lo8] = np.abs(out - ref).max() / max(1e-6, np.abs(ref).max())
+    # single-pass TF32 operands (truncated) would sit near 1e-3.  The fp32 residual term brings that to fp32 rounding; the 8-bit term
+    # (residual and weight each good to ~3 bits, and truncation makes the residual one-signed, so the weight error does not average
+    # out) to ~6e-5 of the tensor's range - the level of the tensor-core layers before it, 4e-6 on the stems (DESIGN.md section 3)
+    assert errs[0] < 2e-6, errs
+    assert errs[1] < 1.5e-4, errs
